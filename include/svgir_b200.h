@@ -1,0 +1,162 @@
+/* svgir_b200 -- C ABI of the B200-native SVG-IR hot path (libsvgir_b200.so).
+ *
+ * Drop-in boundary: these entry points are what the reference's Python/C++ seam for the
+ * splatting + shading path binds.  Each one cites the reference interface it replaces
+ * (paths relative to learner-shx/SVG-IR @96dd9a5).  All pointers are DEVICE pointers unless a
+ * parameter is documented as host; all tensors are contiguous fp32 unless noted; every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*) and returns 0 on success or a
+ * negative svgir_status (message via svgir_last_error()).  No torch types cross this boundary;
+ * the caller (Python host code under svg-ir_b200/) owns every buffer.
+ */
+#ifndef SVGIR_B200_H_
+#define SVGIR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum svgir_status {
+    SVGIR_OK = 0,
+    SVGIR_ERR_INVALID = -1,   /* bad argument (shape limits, null pointer, misalignment) */
+    SVGIR_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
+    SVGIR_ERR_CAPACITY = -3,  /* a caller-provided buffer is too small */
+};
+
+#define SVGIR_VARIANT_SVGSS 0 /* stage 2: svgss_rasterization (SV materials)          */
+#define SVGIR_VARIANT_RGSS 1  /* stage 1: rgss-rasterization (flat features, config={1,1,1}) */
+
+#define SVGIR_REC_FLOATS 24   /* packed per-surfel record, see svgir_raster_state.rec   */
+#define SVGIR_GEO_GRAD_FLOATS 16
+#define SVGIR_MAX_S 64        /* reference limits: S<=50, VS/4<=20 (forward.cu:483-486)   */
+#define SVGIR_MAX_NV 32
+
+const char* svgir_last_error(void);
+int svgir_version(void);
+
+/* Per-view constants. Mirrors GaussianRasterizationSettings
+ * (gaussian_renderer/svgss_rasterization.py:331-346, rgss_rasterization.py:189-205) plus the
+ * sizes RasterizeGaussiansCUDA derives (svgss_rasterization/rasterize_points.cu:69-73,102-106). */
+typedef struct svgir_raster_cfg {
+    int32_t P, S, VS, sh_degree, M;  /* surfels, flat features, SV floats (VS%4==0), SH degree, SH coeffs */
+    int32_t W, H;
+    int32_t variant;                 /* SVGIR_VARIANT_* */
+    float tan_fovx, tan_fovy, scale_modifier;
+    int32_t prefiltered, debug;      /* debug!=0: synchronise + check after every launch (auxiliary.h:425-432) */
+    int32_t n_config;                /* #floats behind `config` (reference model passes 3; [3] treated as 0) */
+    int32_t backward_geometry;       /* rgss only (rgss backward.cu:646-649) */
+    int32_t computer_pseudo_normal;  /* rgss only */
+    float cx, cy;                    /* rgss only */
+    const float* bg;          /* [3]  */
+    const float* viewmatrix;  /* [16] row-vector convention, read column-major (auxiliary.h:65-84) */
+    const float* projmatrix;  /* [16] */
+    const float* campos;      /* [3]  */
+    const float* patch_bbox;  /* [4] (h0,w0,h1,w1); svgss only */
+    const float* config;      /* [n_config] svgss only: [0]>0 surface [1]>0 normalize_depth [2]>0 per_pixel_depth */
+} svgir_raster_cfg;
+
+/* Per-surfel inputs (rasterize_points.cu:36-63). Absent optional = NULL. */
+typedef struct svgir_raster_in {
+    const float* means3D;        /* [P,3] */
+    const float* opacities;      /* [P,1] */
+    const float* scales;         /* [P,3] or NULL when cov3D_precomp */
+    const float* rotations;      /* [P,4] */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL */
+    const float* features;       /* [P,S]  or NULL when S==0 */
+    const float* vfeatures;      /* [P,VS] or NULL when VS==0 */
+} svgir_raster_in;
+
+/* State carried from forward to backward. Replaces the three opaque byte buffers
+ * geomBuffer/binningBuffer/imgBuffer (rasterizer_impl.h:32-75) with typed arrays the caller
+ * allocates. rec[P][24] = { mx,my,conic.x,conic.y | conic.z,opacity,depth,su | J0,J1,J2,J3 |
+ * J6,J9,sv,radius | r,g,b,n.x | n.y,n.z,lambda.x,lambda.y } with su,sv = 0.5/(0.5*lambda+0.1). */
+typedef struct svgir_raster_state {
+    float* rec;               /* [P,24] written for visible surfels only */
+    float* cov3D;             /* [P,6]  */
+    uint8_t* clamped;         /* [P] bit c set when SH colour channel c was clamped */
+    uint16_t* rect;           /* [P,4] tile rect (x0,y0,x1,y1) */
+    uint32_t* tiles_touched;  /* [P] */
+    uint32_t* tile_count;     /* [T] */
+    uint32_t* tile_cursor;    /* [T] scratch */
+    uint32_t* ranges;         /* [T,2] (start,end), (0,0) for empty tiles */
+    uint32_t* big_tiles;      /* [2*T+4] scratch: work lists of the medium / large tile sorters */
+    int32_t* num_rendered;    /* [2] device: R, overflow flag */
+    uint64_t* keys;           /* [cap_R] scratch, (depth_bits<<32)|surfel */
+    uint32_t* point_list;     /* [cap_R] sorted surfel ids */
+    uint64_t* sorted_keys;    /* [cap_R] optional debug output (tile<<32)|depth_bits, or NULL */
+    int64_t cap_R;            /* capacity of keys / point_list */
+    float* final_T;           /* [H*W] */
+    float* final_D;           /* [H*W] */
+    uint32_t* n_contrib;      /* [H*W] */
+} svgir_raster_state;
+
+/* Outputs of the forward pass; caller zero-fills out_weights, everything else is fully written.
+ * (rasterize_points.cu:78-88,144; rgss: rgss-rasterization/rasterize_points.cu:77-141) */
+typedef struct svgir_raster_out {
+    float* color;    /* [3,H,W] */
+    float* normal;   /* [3,H,W] */
+    float* depth;    /* [1,H,W] */
+    float* opacity;  /* [1,H,W] */
+    float* feature;  /* [S,H,W] */
+    float* vfeature; /* [VS/4,H,W] svgss */
+    float* weights;  /* [P,1] accumulated blend weight (forward.cu:653) */
+    int32_t* radii;  /* [P] */
+    float* pseudo_normal; /* [3,H,W] rgss, zero-filled by caller */
+    float* surface_xyz;   /* [3,H,W] rgss */
+} svgir_raster_out;
+
+/* Forward, part 1: per-surfel preprocess (forward.cu:230-396), per-tile counting and the tile
+ * scan (replaces InclusiveSum + D2H, rasterizer_impl.cu:307-311). Leaves R in
+ * state->num_rendered[0]; needs rec..num_rendered of `state`. */
+int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                            svgir_raster_state* state, svgir_raster_out* out, void* stream);
+
+/* Forward, part 2: duplicateWithKeys + tile|depth radix sort + identifyTileRanges
+ * (rasterizer_impl.cu:70-138,319-348) and the forward compositing kernel (forward.cu:402-750).
+ * If R exceeds state->cap_R the overflow flag num_rendered[1] is set and nothing is rendered. */
+int svgir_raster_render(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                        svgir_raster_state* state, svgir_raster_out* out, void* stream);
+
+/* Pixel gradients in, per-surfel gradients out (RasterizeGaussiansBackwardCUDA,
+ * rasterize_points.cu:147-265; Rasterizer::backward rasterizer_impl.cu:386-523). */
+typedef struct svgir_raster_grads {
+    const float* dL_dcolor;    /* [3,H,W] */
+    const float* dL_dnormal;   /* [3,H,W] */
+    const float* dL_ddepth;    /* [1,H,W] */
+    const float* dL_dopacity;  /* [1,H,W] */
+    const float* dL_dfeature;  /* [S,H,W]  or NULL */
+    const float* dL_dvfeature; /* [VS/4,H,W] or NULL */
+    /* accumulators, zero-filled by the caller */
+    float* geo_grad;           /* [P,16]: mean2D.xy, conic.xyw, opacity, colour rgb, normal xyz, depth, pad */
+    float* dL_dfeatures;       /* [P,S]  (final output) */
+    float* dL_dvfeatures;      /* [P,VS] (final output) */
+    /* outputs fully written by the backward-preprocess kernel */
+    float* dL_dmeans2D;        /* [P,3] */
+    float* dL_dcolors;         /* [P,3] */
+    float* dL_dopacities;      /* [P,1] */
+    float* dL_dmeans3D;        /* [P,3] */
+    float* dL_dcov3D;          /* [P,6] */
+    float* dL_dsh;             /* [P,M,3] */
+    float* dL_dscales;         /* [P,3] */
+    float* dL_drotations;      /* [P,4] */
+    float* dL_dconic;          /* [P,4] optional debug copy or NULL */
+    float* dL_dnormal3;        /* [P,3] optional debug copy or NULL */
+    float* dL_ddepths;         /* [P]   optional debug copy or NULL */
+} svgir_raster_grads;
+
+int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                          const svgir_raster_state* state, const int32_t* radii,
+                          svgir_raster_grads* g, void* stream);
+
+/* mark_visible (rasterize_points.cu:267-286). svgss: all false (rasterizer_impl.cu:54-66);
+ * rgss: frustum test z > 0.2 (rgss auxiliary.h:146-171). present is uint8/bool [P]. */
+int svgir_mark_visible(int variant, int P, const float* means3D, const float* viewmatrix,
+                       const float* projmatrix, uint8_t* present, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGIR_B200_H_ */

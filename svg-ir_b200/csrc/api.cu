@@ -1,0 +1,132 @@
+// extern "C" entry points of libsvgir_b200.so (declared in include/svgir_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace svgir {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// Launch check. With debug set it also synchronises the stream, like the reference's CHECK_CUDA
+// (cuda_rasterizer/auxiliary.h:425-432).
+int check_launch(const char* what, bool debug, cudaStream_t stream) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("[svgir_b200] %s: %s", what, cudaGetErrorString(e));
+        return SVGIR_ERR_CUDA;
+    }
+    return SVGIR_OK;
+}
+
+static int validate(const svgir_raster_cfg* c, const svgir_raster_in* in) {
+    if (!c || !in) { set_error("null cfg/in"); return SVGIR_ERR_INVALID; }
+    if (c->P < 0 || c->W <= 0 || c->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", c->P, c->W, c->H); return SVGIR_ERR_INVALID; }
+    if (c->S < 0 || c->S > SVGIR_MAX_S) { set_error("S=%d outside [0,%d]", c->S, SVGIR_MAX_S); return SVGIR_ERR_INVALID; }
+    if (c->VS < 0 || (c->VS & 3) || c->VS / 4 > SVGIR_MAX_NV) { set_error("VS=%d must be a multiple of 4 and <= %d", c->VS, 4 * SVGIR_MAX_NV); return SVGIR_ERR_INVALID; }
+    if (c->variant == SVGIR_VARIANT_RGSS && c->VS != 0) { set_error("rgss has no vfeatures"); return SVGIR_ERR_INVALID; }
+    if (c->sh_degree > 3) { set_error("SH degree %d > 3", c->sh_degree); return SVGIR_ERR_INVALID; }
+    if (!in->means3D || !in->opacities) { set_error("means3D/opacities missing"); return SVGIR_ERR_INVALID; }
+    if ((in->shs != nullptr) == (in->colors_precomp != nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return SVGIR_ERR_INVALID; }
+    if (in->shs && c->M < (c->sh_degree + 1) * (c->sh_degree + 1)) { set_error("M=%d too small for SH degree %d", c->M, c->sh_degree); return SVGIR_ERR_INVALID; }
+    if (!in->cov3D_precomp && (!in->scales || !in->rotations)) { set_error("provide scales+rotations or cov3D_precomp"); return SVGIR_ERR_INVALID; }
+    if (!in->rotations) { set_error("rotations are required (surfel normals)"); return SVGIR_ERR_INVALID; }
+    if (c->S > 0 && !in->features) { set_error("features missing"); return SVGIR_ERR_INVALID; }
+    if (c->VS > 0 && !in->vfeatures) { set_error("vfeatures missing"); return SVGIR_ERR_INVALID; }
+    if (((uintptr_t)in->rotations & 15) || (c->VS > 0 && ((uintptr_t)in->vfeatures & 15)) ||
+        (c->S > 0 && (c->S & 3) == 0 && ((uintptr_t)in->features & 15))) {
+        set_error("rotations/features/vfeatures must be 16-byte aligned");
+        return SVGIR_ERR_INVALID;
+    }
+    if (!c->bg || !c->viewmatrix || !c->projmatrix || !c->campos) { set_error("camera constants missing"); return SVGIR_ERR_INVALID; }
+    if (c->variant == SVGIR_VARIANT_SVGSS && (!c->patch_bbox || (c->n_config > 0 && !c->config))) { set_error("patch_bbox/config missing"); return SVGIR_ERR_INVALID; }
+    return SVGIR_OK;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ V, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const float pz = V[2] * x + V[6] * y + V[10] * z + V[14];
+    present[idx] = pz > 0.2f;
+}
+
+}  // namespace svgir
+
+using namespace svgir;
+
+extern "C" {
+
+const char* svgir_last_error(void) { return g_err; }
+int svgir_version(void) { return 100; }
+
+int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                            svgir_raster_state* st, svgir_raster_out* out, void* stream) {
+    int rc = validate(cfg, in);
+    if (rc) return rc;
+    if (!st || !out || !st->rec || !st->tile_count || !st->num_rendered || !out->radii) {
+        set_error("state/out buffers missing");
+        return SVGIR_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cfg->P == 0) return SVGIR_OK;
+    rc = launch_preprocess(*cfg, *in, *st, *out, s);
+    if (rc) return rc;
+    return launch_tile_scan(*cfg, *st, s);
+}
+
+int svgir_raster_render(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                        svgir_raster_state* st, svgir_raster_out* out, void* stream) {
+    int rc = validate(cfg, in);
+    if (rc) return rc;
+    if (!st || !out || !st->keys || !st->point_list || !st->final_T || !out->color) {
+        set_error("state/out buffers missing");
+        return SVGIR_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cfg->P == 0) return SVGIR_OK;
+    rc = launch_binning(*cfg, *st, out->radii, s);
+    if (rc) return rc;
+    return launch_composite_fwd(*cfg, *in, *st, *out, s);
+}
+
+int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                          const svgir_raster_state* st, const int32_t* radii,
+                          svgir_raster_grads* g, void* stream) {
+    int rc = validate(cfg, in);
+    if (rc) return rc;
+    if (!st || !g || !radii || !g->geo_grad || !g->dL_dcolor) {
+        set_error("state/grad buffers missing");
+        return SVGIR_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cfg->P == 0) return SVGIR_OK;
+    rc = launch_composite_bwd(*cfg, *in, *st, *g, s);
+    if (rc) return rc;
+    return launch_preprocess_bwd(*cfg, *in, *st, radii, *g, s);
+}
+
+int svgir_mark_visible(int variant, int P, const float* means3D, const float* viewmatrix,
+                       const float* projmatrix, uint8_t* present, void* stream) {
+    (void)projmatrix;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return SVGIR_OK;
+    if (variant == SVGIR_VARIANT_SVGSS) {
+        // the stage-2 reference kernel body is commented out: all false (rasterizer_impl.cu:54-66)
+        if (cudaMemsetAsync(present, 0, (size_t)P, s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+        return SVGIR_OK;
+    }
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+    return check_launch("mark_visible", false, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Shared device helpers for the svgir_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "svgir_b200.h"
+
+#define TILE 16
+#define TILE_PIX 256
+#define REC_F4 (SVGIR_REC_FLOATS / 4)
+
+namespace svgir {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what, bool debug, cudaStream_t stream);
+
+// ---- exactly-rounded fp32 building blocks ------------------------------------------------
+// The binning-relevant chain of the preprocess (projection, culls, covariance, radius, rect,
+// depth key) must reproduce the reference build's roundings bit for bit (SURVEY.md 8(a) a7-a9,
+// Appendix A.1b). nvcc never contracts or reorders the explicit _rn intrinsics, so the
+// contraction pattern read from the reference SASS is spelled out with them.
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_(float a) { return __fsqrt_rn(a); }
+
+// m[i]*x + m[4+i]*y + m[8+i]*z : fma(z,m8, fma(x,m0, rn(y*m4)))
+__device__ __forceinline__ float dot3_col(const float* __restrict__ m, int i, float x, float y, float z) {
+    return fma_(z, m[8 + i], fma_(x, m[i], mul_(y, m[4 + i])));
+}
+// a0*b0 + a1*b1 + a2*b2 : fma(a2,b2, fma(a0,b0, rn(a1*b1)))
+__device__ __forceinline__ float dot3_glm(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return fma_(a2, b2, fma_(a0, b0, mul_(a1, b1)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit read-only streaming load
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- per-pair blend evaluation shared by the forward and backward compositors ------------
+// rec layout: see svgir_raster_state.rec in include/svgir_b200.h
+struct PairEval {
+    float alpha, G, dx, dy;
+};
+
+// svgss: forward.cu:530-547 with the reference build's contraction; rgss: rgss forward.cu:433.
+template <bool RGSS>
+__device__ __forceinline__ bool eval_alpha(float px, float py, float mx, float my, float cx, float cy,
+                                           float cz, float o, PairEval& e) {
+    e.dx = sub_(mx, px);
+    e.dy = sub_(my, py);
+    float power;
+    if (!RGSS) {
+        float dist = fma_(e.dy, mul_(e.dx, add_(cy, cy)), fma_(e.dx, mul_(e.dx, cx), mul_(e.dy, mul_(e.dy, cz))));
+        power = mul_(dist, -0.5f);
+    } else {
+        power = -0.5f * (cx * e.dx * e.dx + cz * e.dy * e.dy) - cy * e.dx * e.dy;
+    }
+    if (power > 0.0f) return false;
+    e.G = expf(power);
+    e.alpha = fminf(0.99f, mul_(o, e.G));
+    return e.alpha >= 1.0f / 255.0f;
+}
+
+// Launchers (one per translation unit)
+int launch_preprocess(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
+                      svgir_raster_out& out, cudaStream_t s);
+int launch_tile_scan(const svgir_raster_cfg& c, svgir_raster_state& st, cudaStream_t s);
+int launch_binning(const svgir_raster_cfg& c, svgir_raster_state& st, const int32_t* radii, cudaStream_t s);
+int launch_composite_fwd(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
+                         svgir_raster_out& out, cudaStream_t s);
+int launch_composite_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
+                         const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s);
+int launch_preprocess_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
+                          const svgir_raster_state& st, const int32_t* radii, svgir_raster_grads& g,
+                          cudaStream_t s);
+
+}  // namespace svgir

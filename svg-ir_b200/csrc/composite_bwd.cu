@@ -1,0 +1,333 @@
+// Backward compositing: per-pixel back-to-front re-traversal producing per-surfel gradients.
+//
+// Replaces renderCUDA<3> of backward.cu (svgss_rasterization/cuda_rasterizer/backward.cu:530-934;
+// stage 1: rgss-rasterization/cuda_rasterizer/backward.cu:432-757), which issues 13+S+VS global
+// fp32 atomics per (pixel, surfel) hit (69 at the stage-2 training shape) and keeps 1.3 KB of
+// per-thread recurrences in local memory.  Here:
+//   * the per-channel recurrences  acc_c <- a_prev*v_prev,c + (1-a_prev)*acc_c  are collapsed into
+//     ONE scalar recurrence on A = sum_c acc_c*g_c (they are linear with channel-independent
+//     coefficients), so a pixel carries 4 floats of state instead of 2*(7+S+VS/4);
+//   * every gradient component is sum_hits s_sel(hit) * G[pixel(hit)][channel], with s a handful of
+//     per-hit scalars and G the tile's pixel-gradient matrix kept in shared memory.  Hit lanes
+//     publish their scalars to a per-warp scratch; then each LANE OWNS A COMPONENT and loops over
+//     the warp's hits -- no shuffle tree, no atomics;
+//   * per-warp partial sums go to warp-private shared accumulators and are combined into one
+//     global atomic per (tile, instance, component);
+//   * the traversal starts at the tile's max n_contrib instead of the end of the tile's range.
+// Gradient semantics (x10 on the normal gradient, un-weighted depth-differencing term on mean2D,
+// no gradient through the bilinear weights, ...) follow the reference; see Appendix C of SURVEY.md.
+#include "common.cuh"
+
+namespace svgir {
+
+#define BWD_BATCH 16
+#define HIT_STRIDE 13   // 12 words per hit, odd stride -> conflict-free publication
+#define NWARP 8
+
+template <int S_T, int NV_T, bool RGSS>
+__global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
+    const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
+    const float4* __restrict__ rec, const uint2* __restrict__ ranges,
+    const uint32_t* __restrict__ point_list, const float* __restrict__ final_T,
+    const float* __restrict__ final_D, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ gpix_color, const float* __restrict__ gpix_normal,
+    const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
+    const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
+    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures) {
+    constexpr bool GENERIC = S_T < 0;
+    const int S = GENERIC ? c.S : S_T;
+    const int NV = GENERIC ? c.VS / 4 : NV_T;
+    const int SP = (S + 3) & ~3;
+    const int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;
+    const int CH = STRIDE / 4;
+    const int NCOMP = SVGIR_GEO_GRAD_FLOATS + SP + 4 * NV;  // accumulator row
+    const int NG = 8 + S + NV;                              // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
+    const int GS = NG | 1;                                  // odd stride
+
+    extern __shared__ __align__(16) float smem[];
+    float* stage = smem;                                   // [BWD_BATCH][STRIDE]
+    float* G = stage + BWD_BATCH * STRIDE;                 // [256][GS]
+    float* hits = G + TILE_PIX * GS;                       // [NWARP][32][HIT_STRIDE]
+    float* acc = hits + NWARP * 32 * HIT_STRIDE;           // [NWARP][BWD_BATCH][NCOMP]
+    int* ids = reinterpret_cast<int*>(acc + NWARP * BWD_BATCH * NCOMP);  // [BWD_BATCH]
+    __shared__ int tile_max_s;
+
+    const int W = c.W, H = c.H;
+    const int gx = (W + TILE - 1) / TILE;
+    const int tile = blockIdx.x;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    if (total == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int px = (tile % gx) * TILE + (tid & 15), py = (tile / gx) * TILE + (tid >> 4);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix_id = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+
+    bool surface = true, ppd = true, normalize_depth = true;
+    if (!RGSS) {
+        surface = c.n_config > 0 && c.config[0] > 0;
+        normalize_depth = c.n_config > 1 && c.config[1] > 0;
+        ppd = c.n_config > 2 && c.config[2] > 0;
+    }
+    const bool sv = surface && ppd;
+    const bool feat_to_alpha = !RGSS || c.backward_geometry != 0;
+
+    const float T_final = inside ? final_T[pix_id] : 0.f;
+    const float D_final = (inside && normalize_depth) ? final_D[pix_id] : 0.f;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    // ---- pixel-gradient row -----------------------------------------------------------------
+    float* Grow = G + tid * GS;
+    float gD = 0.f, gDn = 0.f, Kpix = 0.f;
+    {
+        float gC[3] = {0, 0, 0}, gN[3] = {0, 0, 0}, gO = 0.f;
+        if (inside) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) gC[i] = gpix_color[i * HW + pix_id];
+#pragma unroll
+            for (int i = 0; i < 3; i++) gN[i] = gpix_normal[i * HW + pix_id];
+            gD = gpix_depth[pix_id];
+            gO = gpix_opac[pix_id];
+        }
+        const float omT = 1.f - T_final;
+        gDn = normalize_depth ? gD / omT : gD;
+        Grow[0] = 1.0f;
+        Grow[1] = gC[0]; Grow[2] = gC[1]; Grow[3] = gC[2];
+        Grow[4] = surface ? gN[0] : 0.f;   // the x10 of backward.cu:804 is applied at the flush
+        Grow[5] = surface ? gN[1] : 0.f;
+        Grow[6] = surface ? gN[2] : 0.f;
+        Grow[7] = gDn;
+        for (int i = 0; i < S; i++) Grow[8 + i] = inside ? gpix_feature[i * HW + pix_id] : 0.f;
+        for (int i = 0; i < NV; i++) Grow[8 + S + i] = inside ? gpix_vfeature[i * HW + pix_id] : 0.f;
+        // pixel-constant part of dL/dalpha that is divided by (1-alpha):
+        //   opacity output (+gO*T_f), background (-T_f*bg.gC), depth normalisation or the +10T term
+        const float* bg = c.bg;
+        const float bgdot = bg[0] * gC[0] + bg[1] * gC[1] + bg[2] * gC[2];
+        Kpix = gO * T_final - T_final * bgdot;
+        if (normalize_depth) Kpix += gD * D_final / omT / omT * -T_final;
+        else Kpix += -T_final * (10.f * gD);
+    }
+
+    // ---- component ownership for the reduction ------------------------------------------------
+    // component k of the accumulator row: geo[16] | F[SP] | VF[4*NV]
+    //   geo: 0,1 mean2D.xy  2,3,4 conic.x,y,w  5 opacity  6..8 colour  9..11 normal  12 depth
+    // value(k) = sum_hits hit[sel(k)] * G[pix][gch(k)]
+    //   hit words: 0 w | 1..4 w*w0..w3 | 5,6 dmean | 7,8,9 dconic | 10 dopacity | 11 pixel
+    constexpr int MAXPASS = GENERIC ? (SVGIR_GEO_GRAD_FLOATS + SVGIR_MAX_S + 4 * SVGIR_MAX_NV + 31) / 32
+                                    : (SVGIR_GEO_GRAD_FLOATS + ((S_T + 3) & ~3) + 4 * (NV_T > 0 ? NV_T : 0) + 31) / 32;
+    int csel[MAXPASS], cgch[MAXPASS];
+#pragma unroll
+    for (int p = 0; p < MAXPASS; p++) {
+        const int k = lane + 32 * p;
+        int sel = -1, gch = 0;
+        if (k < 6) { sel = 5 + k; gch = 0; }
+        else if (k < 9) { sel = 0; gch = 1 + (k - 6); }
+        else if (k < 12) { sel = 0; gch = 4 + (k - 9); }
+        else if (k == 12) { sel = 0; gch = 7; }
+        else if (k >= 16 && k < 16 + S) { sel = 0; gch = 8 + (k - 16); }
+        else if (k >= 16 + SP && k < NCOMP) { const int v = k - 16 - SP; sel = 1 + (v & 3); gch = 8 + S + (v >> 2); }
+        csel[p] = sel; cgch[p] = gch;
+    }
+
+    // ---- tile-wide traversal start --------------------------------------------------------------
+    if (tid == 0) tile_max_s = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(&tile_max_s, m);
+    }
+    __syncthreads();
+    const int tile_max = min(tile_max_s, total);
+    if (tile_max == 0) return;
+
+    float* my_hits = hits + wid * 32 * HIT_STRIDE;
+    float* my_acc = acc + wid * BWD_BATCH * NCOMP;
+
+    float T = T_final, A = 0.f, last_alpha = 0.f, V_last = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    for (int top = tile_max; top > 0; top -= BWD_BATCH) {
+        const int nb = min(BWD_BATCH, top);
+        __syncthreads();  // previous batch fully flushed
+        // stage instances top-1, top-2, ... (back to front) and clear the accumulators
+        for (int q = tid; q < nb * CH; q += TILE_PIX) {
+            const int i = q / CH, ch = q - i * CH;
+            const int id = (int)point_list[range.x + top - 1 - i];
+            float4 v;
+            if (ch < REC_F4) {
+                v = __ldg(rec + (size_t)id * REC_F4 + ch);
+                if (ch == 0) ids[i] = id;
+            } else if (ch < REC_F4 + SP / 4) {
+                const int f0 = (ch - REC_F4) * 4;
+                const float* src = features + (size_t)id * S + f0;
+                if ((S & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    v.x = f0 + 0 < S ? __ldg(src + 0) : 0.f;
+                    v.y = f0 + 1 < S ? __ldg(src + 1) : 0.f;
+                    v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
+                    v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
+                }
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + (ch - REC_F4 - SP / 4));
+            }
+            reinterpret_cast<float4*>(stage)[q] = v;
+        }
+        for (int q = tid; q < NWARP * BWD_BATCH * NCOMP; q += TILE_PIX) acc[q] = 0.f;
+        __syncthreads();
+
+        for (int j = 0; j < nb; j++) {
+            const int pos = top - 1 - j;  // 0-based position in the tile's sorted list
+            const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+            const float4 q0 = r[0];
+            const float4 q1 = r[1];
+            PairEval e;
+            bool hit = false;
+            if (pos < last_contributor) hit = eval_alpha<RGSS>(pxf, pyf, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e);
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            if (ballot == 0) continue;
+            if (hit) {
+                const float inv1ma = __frcp_rn(1.f - e.alpha);
+                T = T * inv1ma;
+                const float w = e.alpha * T;
+                float depth_k = q1.z;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                float gzx = 0.f, gzy = 0.f;
+                if (sv) {
+                    const float4 q2 = r[2];
+                    const float4 q3 = r[3];
+                    const float u0 = fma_(e.dx, q2.x, mul_(e.dy, q2.y));
+                    const float u1 = fma_(e.dx, q2.z, mul_(e.dy, q2.w));
+                    depth_k = sub_(q1.z, fma_(q3.x, u0, mul_(q3.y, u1)));
+                    gzx = q3.x * q2.x + q3.y * q2.z;   // J6*J0 + J9*J2 (backward.cu:915)
+                    gzy = q3.x * q2.y + q3.y * q2.w;   // J6*J1 + J9*J3
+                    if (!RGSS) {
+                        float u = fmaf(u0, q1.w, 0.5f), v = fmaf(u1, q3.z, 0.5f);
+                        u = fminf(0.999f, fmaxf(0.001f, u));
+                        v = fminf(0.999f, fmaxf(0.001f, v));
+                        w0 = (1.0f - u) * (1.0f - v);
+                        w1 = u * (1.0f - v);
+                        w2 = (1.0f - u) * v;
+                        w3 = u * v;
+                    }
+                }
+                // V = sum_c value_c * g_c over all blended channels (normal uses the plain gN)
+                const float4 q4 = r[4];
+                float V = q4.x * Grow[1] + q4.y * Grow[2] + q4.z * Grow[3];
+                if (surface) {
+                    const float4 q5 = r[5];
+                    V += q4.w * Grow[4] + q5.x * Grow[5] + q5.y * Grow[6];
+                }
+                V = fmaf(depth_k, gDn, V);
+                const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+                if (feat_to_alpha)
+                    for (int ch = 0; ch < S; ch++) V = fmaf(f[ch], Grow[8 + ch], V);
+                const float4* vf = reinterpret_cast<const float4*>(f + SP);
+                for (int cidx = 0; cidx < NV; cidx++) {
+                    const float4 t = vf[cidx];
+                    const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
+                    V = fmaf(s4, Grow[8 + S + cidx], V);
+                }
+                A = last_alpha * V_last + (1.f - last_alpha) * A;
+                V_last = V;
+                last_alpha = e.alpha;
+                const float dL_dalpha = (V - A) * T + Kpix * inv1ma;
+                const float dL_ddist = dL_dalpha * q1.y * -0.5f * e.G;
+                float dmx = dL_ddist * 2.f * (q0.z * e.dx + q0.w * e.dy) * ddelx_dx;
+                float dmy = dL_ddist * 2.f * (q1.x * e.dy + q0.w * e.dx) * ddely_dy;
+                if (sv) { dmx -= gD * gzx; dmy -= gD * gzy; }
+                const int rank = __popc(ballot & ((1u << lane) - 1u));
+                float* h = my_hits + rank * HIT_STRIDE;
+                h[0] = w; h[1] = w * w0; h[2] = w * w1; h[3] = w * w2; h[4] = w * w3;
+                h[5] = dmx; h[6] = dmy;
+                h[7] = dL_ddist * (e.dx * e.dx);
+                h[8] = dL_ddist * (e.dx * e.dy);
+                h[9] = dL_ddist * (e.dy * e.dy);
+                h[10] = e.G * dL_dalpha;
+                h[11] = __int_as_float(tid);
+            }
+            __syncwarp();
+            const int nh = __popc(ballot);
+            float* arow = my_acc + j * NCOMP;
+#pragma unroll
+            for (int p = 0; p < MAXPASS; p++) {
+                const int sel = csel[p];
+                if (sel < 0) continue;
+                const int gch = cgch[p];
+                float sum = 0.f;
+                for (int hh = 0; hh < nh; hh++) {
+                    const float* h = my_hits + hh * HIT_STRIDE;
+                    const int pix = __float_as_int(h[11]);
+                    sum = fmaf(h[sel], G[pix * GS + gch], sum);
+                }
+                arow[lane + 32 * p] += sum;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // combine the warp-private partial sums; one global atomic per (tile, instance, component)
+        for (int q = tid; q < nb * NCOMP; q += TILE_PIX) {
+            float v = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < NWARP; wv++) v += acc[wv * BWD_BATCH * NCOMP + q];
+            if (v == 0.f) continue;
+            const int j = q / NCOMP, k = q - j * NCOMP;
+            const int id = ids[j];
+            if (k < SVGIR_GEO_GRAD_FLOATS) {
+                if (k >= 9 && k < 12) v *= 10.f;  // dL_dnormal x10 (backward.cu:804)
+                atomicAdd(&geo_grad[(size_t)id * SVGIR_GEO_GRAD_FLOATS + k], v);
+            }
+            else if (k < SVGIR_GEO_GRAD_FLOATS + SP) {
+                if (k - SVGIR_GEO_GRAD_FLOATS < S) atomicAdd(&dL_dfeatures[(size_t)id * S + (k - SVGIR_GEO_GRAD_FLOATS)], v);
+            } else atomicAdd(&dL_dvfeatures[(size_t)id * (4 * NV) + (k - SVGIR_GEO_GRAD_FLOATS - SP)], v);
+        }
+    }
+}
+
+template <int S_T, int NV_T, bool RGSS>
+static int launch_one_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
+                          const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s) {
+    const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
+    const int SP = (c.S + 3) & ~3;
+    const int stride = SVGIR_REC_FLOATS + SP + c.VS;
+    const int ncomp = SVGIR_GEO_GRAD_FLOATS + SP + c.VS;
+    const int gs = (8 + c.S + c.VS / 4) | 1;
+    const size_t smem = sizeof(float) * ((size_t)BWD_BATCH * stride + (size_t)TILE_PIX * gs +
+                                         (size_t)NWARP * 32 * HIT_STRIDE +
+                                         (size_t)NWARP * BWD_BATCH * ncomp + BWD_BATCH);
+    auto k = composite_bwd_kernel<S_T, NV_T, RGSS>;
+    if (smem > 48 * 1024) {
+        if (smem > 227 * 1024) {
+            set_error("composite_bwd: S=%d VS=%d needs %zu B of shared memory (>227 KB)", c.S, c.VS, smem);
+            return SVGIR_ERR_INVALID;
+        }
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("composite_bwd: cannot reserve %zu B of shared memory", smem);
+            return SVGIR_ERR_CUDA;
+        }
+    }
+    k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
+                                      (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
+                                      st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
+                                      g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
+                                      g.dL_dfeatures, g.dL_dvfeatures);
+    return check_launch("composite_bwd", c.debug, s);
+}
+
+int launch_composite_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
+                         const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s) {
+    const int NV = c.VS / 4;
+    if (c.variant == SVGIR_VARIANT_RGSS) {
+        if (c.S == 5) return launch_one_bwd<5, 0, true>(c, in, st, g, s);
+        return launch_one_bwd<-1, -1, true>(c, in, st, g, s);
+    }
+    if (c.S == 4 && NV == 13) return launch_one_bwd<4, 13, false>(c, in, st, g, s);
+    if (c.S == 7 && NV == 16) return launch_one_bwd<7, 16, false>(c, in, st, g, s);
+    if (c.S == 0 && NV == 0) return launch_one_bwd<0, 0, false>(c, in, st, g, s);
+    return launch_one_bwd<-1, -1, false>(c, in, st, g, s);
+}
+
+}  // namespace svgir

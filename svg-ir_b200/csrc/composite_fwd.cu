@@ -1,0 +1,254 @@
+// Forward compositing: one CTA per 16x16 tile, one thread per pixel, front-to-back alpha blending
+// of colour, geometric normal, depth, S flat features and VS/4 bilinearly interpolated
+// spatially-varying features.
+//
+// Replaces renderCUDA<3> (svgss_rasterization/cuda_rasterizer/forward.cu:402-750; stage 1:
+// rgss-rasterization/cuda_rasterizer/forward.cu:324-535).  Differences in *how*, not *what*:
+//   * the whole per-instance payload (24-float packed record + the surfel's feature and vfeature
+//     rows) is staged into shared memory with 128-bit loads, so the per-hit global reads of
+//     features/vfeatures (forward.cu:635-646) disappear;
+//   * (S, VS/4) are template parameters for the shapes the application uses, so accumulators live
+//     in registers instead of the reference's 304 B local-memory stack;
+//   * warps skip instances none of their 32 pixels hit;
+//   * out_weights is reduced per warp and per tile before one global atomic per (tile, instance)
+//     instead of one per (pixel, hit) (forward.cu:653).
+// The alpha chain (power, exp, alpha, T test) uses the reference build's exact roundings.
+//
+// Roofline: algorithmic bytes = R*(104+4S+4VS) + HW*(4*(8+S+VS/4)+12); the kernel is
+// issue-bound, not HBM-bound, whenever tiles terminate early.
+#include "common.cuh"
+
+namespace svgir {
+
+#define FWD_BATCH 64
+
+template <int S_T, int NV_T, bool RGSS>
+__global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
+    const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
+    const float4* __restrict__ rec, const uint2* __restrict__ ranges,
+    const uint32_t* __restrict__ point_list, const int32_t* __restrict__ num_rendered,
+    float* __restrict__ final_T, float* __restrict__ final_D, uint32_t* __restrict__ n_contrib,
+    float* __restrict__ out_color, float* __restrict__ out_normal, float* __restrict__ out_depth,
+    float* __restrict__ out_opac, float* __restrict__ out_feature, float* __restrict__ out_vfeature,
+    float* __restrict__ out_weights) {
+    constexpr bool GENERIC = S_T < 0;
+    constexpr int MAXS = GENERIC ? SVGIR_MAX_S : (S_T > 0 ? S_T : 1);
+    constexpr int MAXNV = GENERIC ? SVGIR_MAX_NV : (NV_T > 0 ? NV_T : 1);
+    const int S = GENERIC ? c.S : S_T;
+    const int NV = GENERIC ? c.VS / 4 : NV_T;
+    const int SP = (S + 3) & ~3;          // feature row padded to float4
+    const int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;  // floats per staged instance
+    const int CH = STRIDE / 4;            // float4 chunks per staged instance
+
+    extern __shared__ __align__(16) float smem[];
+    float* stage = smem;                                  // [FWD_BATCH][STRIDE]
+    float* wsum = smem + FWD_BATCH * STRIDE;              // [2][FWD_BATCH]
+    int* ids = reinterpret_cast<int*>(wsum + 2 * FWD_BATCH);  // [2][FWD_BATCH]
+
+    if (num_rendered[1]) return;  // binning overflowed: nothing valid to render
+    const int W = c.W, H = c.H;
+    const int gx = (W + TILE - 1) / TILE;
+    const int tile = blockIdx.x;
+    const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int px = tx0 + (tid & 15), py = ty0 + (tid >> 4);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix_id = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+
+    bool surface = true, ppd = true, normalize_depth = true;
+    if (!RGSS) {
+        surface = c.n_config > 0 && c.config[0] > 0;
+        normalize_depth = c.n_config > 1 && c.config[1] > 0;
+        ppd = c.n_config > 2 && c.config[2] > 0;
+    }
+    const bool sv = surface && ppd;
+
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+
+    float T = 1.0f, D = 0.f;
+    float C[3] = {0, 0, 0}, N[3] = {0, 0, 0};
+    float F[MAXS], VF[MAXNV];
+#pragma unroll
+    for (int i = 0; i < MAXS; i++) F[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXNV; i++) VF[i] = 0.f;
+    uint32_t last_contributor = 0;
+    bool done = !inside;
+
+    if (tid < 2 * FWD_BATCH) wsum[tid] = 0.f;
+
+    int nbatch = 0;
+    for (int base = 0; base < total; base += FWD_BATCH, nbatch++) {
+        const int par = nbatch & 1;
+        const int ndone = __syncthreads_count(done);
+        // flush the previous batch's per-instance weight sums (one atomic per tile x instance)
+        if (nbatch > 0 && tid < FWD_BATCH) {
+            const float wv = wsum[(par ^ 1) * FWD_BATCH + tid];
+            if (wv != 0.f) {
+                atomicAdd(&out_weights[ids[(par ^ 1) * FWD_BATCH + tid]], wv);
+                wsum[(par ^ 1) * FWD_BATCH + tid] = 0.f;
+            }
+        }
+        if (ndone == TILE_PIX) break;
+        const int nb = min(FWD_BATCH, total - base);
+        // cooperative 128-bit staging of records + feature rows
+        for (int q = tid; q < nb * CH; q += TILE_PIX) {
+            const int i = q / CH, ch = q - i * CH;
+            const int id = (int)point_list[range.x + base + i];
+            float4 v;
+            if (ch < REC_F4) {
+                v = __ldg(rec + (size_t)id * REC_F4 + ch);
+                if (ch == 0) ids[par * FWD_BATCH + i] = id;
+            } else if (ch < REC_F4 + SP / 4) {
+                const int f0 = (ch - REC_F4) * 4;
+                const float* src = features + (size_t)id * S + f0;
+                if ((S & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    v.x = f0 + 0 < S ? __ldg(src + 0) : 0.f;
+                    v.y = f0 + 1 < S ? __ldg(src + 1) : 0.f;
+                    v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
+                    v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
+                }
+            } else {
+                const int cidx = ch - REC_F4 - SP / 4;
+                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + cidx);
+            }
+            reinterpret_cast<float4*>(stage)[q] = v;
+        }
+        __syncthreads();
+
+        for (int j = 0; j < nb; j++) {
+            const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+            const float4 q0 = r[0];
+            const float4 q1 = r[1];
+            PairEval e;
+            bool hit = false;
+            float test_T = 0.f;
+            if (!done) {
+                hit = eval_alpha<RGSS>(pxf, pyf, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e);
+                if (hit) {
+                    test_T = mul_(T, sub_(1.f, e.alpha));
+                    if (test_T < 0.0001f) { done = true; hit = false; }
+                }
+            }
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            float w = 0.f;
+            if (hit) {
+                w = mul_(e.alpha, T);
+                float depth_k = q1.z;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                if (sv) {
+                    const float4 q2 = r[2];
+                    const float4 q3 = r[3];
+                    const float u0 = fma_(e.dx, q2.x, mul_(e.dy, q2.y));
+                    const float u1 = fma_(e.dx, q2.z, mul_(e.dy, q2.w));
+                    depth_k = sub_(q1.z, fma_(q3.x, u0, mul_(q3.y, u1)));
+                    if (!RGSS) {
+                        float u = fmaf(u0, q1.w, 0.5f), v = fmaf(u1, q3.z, 0.5f);
+                        u = fminf(0.999f, fmaxf(0.001f, u));
+                        v = fminf(0.999f, fmaxf(0.001f, v));
+                        w0 = (1.0f - u) * (1.0f - v);
+                        w1 = u * (1.0f - v);
+                        w2 = (1.0f - u) * v;
+                        w3 = u * v;
+                    }
+                }
+                D = fmaf(depth_k, w, D);
+                const float4 q4 = r[4];
+                C[0] = fmaf(q4.x, w, C[0]);
+                C[1] = fmaf(q4.y, w, C[1]);
+                C[2] = fmaf(q4.z, w, C[2]);
+                if (surface) {
+                    const float4 q5 = r[5];
+                    N[0] = fmaf(q4.w, w, N[0]);
+                    N[1] = fmaf(q5.x, w, N[1]);
+                    N[2] = fmaf(q5.y, w, N[2]);
+                }
+                const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+#pragma unroll
+                for (int ch = 0; ch < MAXS; ch++)
+                    if (ch < S) F[ch] = fmaf(f[ch], w, F[ch]);
+                const float4* vf = reinterpret_cast<const float4*>(f + SP);
+#pragma unroll
+                for (int cidx = 0; cidx < MAXNV; cidx++)
+                    if (cidx < NV) {
+                        const float4 t = vf[cidx];
+                        const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
+                        VF[cidx] = fmaf(w, s4, VF[cidx]);
+                    }
+                T = test_T;
+                last_contributor = (uint32_t)(base + j + 1);
+            }
+            const float wt = warp_sum(w);
+            if (lane == 0) atomicAdd(&wsum[par * FWD_BATCH + j], wt);
+        }
+    }
+    // flush the last computed batch's weight sums
+    __syncthreads();
+    if (nbatch > 0 && tid < FWD_BATCH) {
+        const int par = (nbatch - 1) & 1;
+        const float wv = wsum[par * FWD_BATCH + tid];
+        if (wv != 0.f) atomicAdd(&out_weights[ids[par * FWD_BATCH + tid]], wv);
+    }
+
+    if (inside) {
+        T = fminf(1.f - 0.000001f, T);  // forward.cu:671 (double literal, rounds to 0.999999f)
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        const float* bg = c.bg;
+        out_color[0 * HW + pix_id] = fmaf(T, bg[0], C[0]);
+        out_color[1 * HW + pix_id] = fmaf(T, bg[1], C[1]);
+        out_color[2 * HW + pix_id] = fmaf(T, bg[2], C[2]);
+#pragma unroll
+        for (int ch = 0; ch < MAXS; ch++)
+            if (ch < S) out_feature[ch * HW + pix_id] = F[ch];
+#pragma unroll
+        for (int cidx = 0; cidx < MAXNV; cidx++)
+            if (cidx < NV) out_vfeature[cidx * HW + pix_id] = VF[cidx];
+        out_normal[0 * HW + pix_id] = surface ? N[0] : 0.f;
+        out_normal[1 * HW + pix_id] = surface ? N[1] : 0.f;
+        out_normal[2 * HW + pix_id] = surface ? N[2] : 0.f;
+        out_depth[pix_id] = normalize_depth ? __fdiv_rn(D, 1.f - T) : fmaf(T, 10.f, D);
+        out_opac[pix_id] = 1.f - T;
+        if (normalize_depth) final_D[pix_id] = D;
+    }
+}
+
+template <int S_T, int NV_T, bool RGSS>
+static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
+                      svgir_raster_out& out, cudaStream_t s) {
+    const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
+    const int SP = (c.S + 3) & ~3;
+    const int stride = SVGIR_REC_FLOATS + SP + c.VS;
+    const size_t smem = sizeof(float) * ((size_t)FWD_BATCH * stride + 4 * FWD_BATCH);
+    auto k = composite_fwd_kernel<S_T, NV_T, RGSS>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("composite_fwd: cannot reserve %zu B of shared memory", smem);
+            return SVGIR_ERR_CUDA;
+        }
+    }
+    k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
+                                      (const uint2*)st.ranges, st.point_list, st.num_rendered,
+                                      st.final_T, st.final_D, st.n_contrib, out.color, out.normal,
+                                      out.depth, out.opacity, out.feature, out.vfeature, out.weights);
+    return check_launch("composite_fwd", c.debug, s);
+}
+
+int launch_composite_fwd(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
+                         svgir_raster_out& out, cudaStream_t s) {
+    const int NV = c.VS / 4;
+    if (c.variant == SVGIR_VARIANT_RGSS) {
+        if (c.S == 5) return launch_one<5, 0, true>(c, in, st, out, s);
+        return launch_one<-1, -1, true>(c, in, st, out, s);
+    }
+    if (c.S == 4 && NV == 13) return launch_one<4, 13, false>(c, in, st, out, s);   // stage-2 training
+    if (c.S == 7 && NV == 16) return launch_one<7, 16, false>(c, in, st, out, s);   // relight eval
+    if (c.S == 0 && NV == 0) return launch_one<0, 0, false>(c, in, st, out, s);
+    return launch_one<-1, -1, false>(c, in, st, out, s);
+}
+
+}  // namespace svgir

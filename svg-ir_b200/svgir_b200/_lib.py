@@ -1,0 +1,110 @@
+"""ctypes binding of libsvgir_b200.so (the C ABI declared in include/svgir_b200.h).
+
+The library is the only compute path: if it is missing or cannot be loaded this module raises --
+there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libsvgir_b200.so")
+_CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+
+REC_FLOATS = 24
+GEO_GRAD_FLOATS = 16
+MAX_S = 64
+MAX_NV = 32
+VARIANT_SVGSS = 0
+VARIANT_RGSS = 1
+
+c_fp = C.c_void_p  # device pointers travel as integers
+
+
+class RasterCfg(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("S", C.c_int32), ("VS", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32),
+        ("W", C.c_int32), ("H", C.c_int32), ("variant", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("n_config", C.c_int32),
+        ("backward_geometry", C.c_int32), ("computer_pseudo_normal", C.c_int32),
+        ("cx", C.c_float), ("cy", C.c_float),
+        ("bg", c_fp), ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp),
+        ("patch_bbox", c_fp), ("config", c_fp),
+    ]
+
+
+class RasterIn(C.Structure):
+    _fields_ = [(n, c_fp) for n in ("means3D", "opacities", "scales", "rotations", "cov3D_precomp",
+                                    "shs", "colors_precomp", "features", "vfeatures")]
+
+
+class RasterState(C.Structure):
+    _fields_ = [
+        ("rec", c_fp), ("cov3D", c_fp), ("clamped", c_fp), ("rect", c_fp), ("tiles_touched", c_fp),
+        ("tile_count", c_fp), ("tile_cursor", c_fp), ("ranges", c_fp), ("big_tiles", c_fp),
+        ("num_rendered", c_fp), ("keys", c_fp), ("point_list", c_fp), ("sorted_keys", c_fp),
+        ("cap_R", C.c_int64), ("final_T", c_fp), ("final_D", c_fp), ("n_contrib", c_fp),
+    ]
+
+
+class RasterOut(C.Structure):
+    _fields_ = [(n, c_fp) for n in ("color", "normal", "depth", "opacity", "feature", "vfeature",
+                                    "weights", "radii", "pseudo_normal", "surface_xyz")]
+
+
+class RasterGrads(C.Structure):
+    _fields_ = [(n, c_fp) for n in (
+        "dL_dcolor", "dL_dnormal", "dL_ddepth", "dL_dopacity", "dL_dfeature", "dL_dvfeature",
+        "geo_grad", "dL_dfeatures", "dL_dvfeatures",
+        "dL_dmeans2D", "dL_dcolors", "dL_dopacities", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+        "dL_dscales", "dL_drotations", "dL_dconic", "dL_dnormal3", "dL_ddepths")]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", _CSRC, "-j8"], stdout=None if verbose else subprocess.DEVNULL)
+    return _SO
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise RuntimeError(
+            f"svgir_b200: native library {_SO} is missing. Build it with "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` or `make -C {_CSRC}`. "
+            "There is no CPU / PyTorch fallback for this path.")
+    L = C.CDLL(_SO)
+    L.svgir_last_error.restype = C.c_char_p
+    for name in ("svgir_raster_preprocess", "svgir_raster_render"):
+        getattr(L, name).argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
+                                     C.POINTER(RasterOut), C.c_void_p]
+        getattr(L, name).restype = C.c_int
+    L.svgir_raster_backward.argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
+                                        C.c_void_p, C.POINTER(RasterGrads), C.c_void_p]
+    L.svgir_raster_backward.restype = C.c_int
+    L.svgir_mark_visible.argtypes = [C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
+    L.svgir_mark_visible.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    """Nonzero status -> RuntimeError, like the reference's AT_ERROR / std::runtime_error path
+    (svgss_rasterization/rasterize_points.cu:65-67, cuda_rasterizer/auxiliary.h:425-432)."""
+    if rc != 0:
+        msg = lib().svgir_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"svgir_b200.{what} failed (status {rc}): {msg}")
+
+
+EXPORTED_SYMBOLS = [
+    "svgir_last_error", "svgir_version", "svgir_raster_preprocess", "svgir_raster_render",
+    "svgir_raster_backward", "svgir_mark_visible",
+]
