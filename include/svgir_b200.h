@@ -156,6 +156,77 @@ int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in
 int svgir_mark_visible(int variant, int P, const float* means3D, const float* viewmatrix,
                        const float* projmatrix, uint8_t* present, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * PBR render_equation (shading).  Replaces the live torch path rendering_equation4 +
+ * GGX_specular4 (gaussian_renderer/svgss.py:537-631) fused with the env-map lookup
+ * DirectLightMap.direct_light / EnvLight.direct_light (scene/direct_light_map.py:70-106,
+ * scene/envmap.py:54-72); the optional per-vertex metallic follows the legacy CUDA
+ * render_equation (rgss-rasterization/render_equation.cu:55-190: f_d=(1-m)base/pi,
+ * F0=0.04(1-m)+base*m).  All [N,12] tensors are channel-major (R v0..v3, G v0..v3, B v0..v3). */
+typedef struct svgir_shade_cfg {
+    int32_t N, Ns;            /* surfels, light samples per surfel */
+    int32_t env_h, env_w;     /* lat-long env map size */
+    int32_t env_mode;         /* 0: learnable map -- softplus(param), result x2 (direct_light_map.py:83,106);
+                                 1: fixed linear map as given (EnvLight after its 32x64 resize), x1 */
+    int32_t debug;
+} svgir_shade_cfg;
+
+typedef struct svgir_shade_in {
+    const float* base_color;     /* [N,12] */
+    const float* roughness;      /* [N,4]  */
+    const float* metallic;       /* [N,4] or NULL (= 0, the reference's formula) */
+    const float* normals;        /* [N,4,3] shading normals */
+    const float* viewdirs;       /* [N,3]  */
+    const float* radiance;       /* [N,Ns,3] cached indirect radiance */
+    const float* visibility;     /* [N,Ns,1] */
+    const float* incident_dirs;  /* [N,Ns,3] */
+    const float* incident_areas; /* [N,Ns,1] */
+    const float* env;            /* [env_h,env_w,3] parameter (mode 0) or map (mode 1) */
+    const float* env_transform;  /* [3,3] or NULL (envmap.py:58-61) */
+    float* env_act_scratch;      /* [env_h,env_w,3] scratch for the activated map */
+} svgir_shade_in;
+
+typedef struct svgir_shade_out {
+    float* pbr; float* diffuse_light; float* specular; float* direct; float* indirect; /* [N,12] */
+    float* mean_visibility;  /* [N,1] sample means that render_view packs into `features` */
+    float* mean_local;       /* [N,3]  (svgss.py:149-156); any of the four may be NULL */
+    float* mean_incident;    /* [N,3] */
+    float* mean_global;      /* [N,3] */
+} svgir_shade_out;
+
+typedef struct svgir_shade_grads {
+    const float* g_pbr; const float* g_diffuse_light; const float* g_specular; const float* g_direct;
+    const float* g_indirect;            /* [N,12] upstream gradients, each may be NULL */
+    const float* g_mean_visibility;     /* [N,1] or NULL */
+    const float* g_mean_local;          /* [N,3] or NULL */
+    const float* g_mean_incident;       /* [N,3] or NULL */
+    const float* g_mean_global;         /* [N,3] or NULL */
+    float* d_base_color;                /* [N,12] */
+    float* d_roughness;                 /* [N,4]  */
+    float* d_metallic;                  /* [N,4] or NULL */
+    float* d_normals;                   /* [N,4,3] */
+    float* d_viewdirs;                  /* [N,3] */
+    float* d_radiance;                  /* [N,Ns,3] or NULL */
+    float* d_visibility;                /* [N,Ns,1] or NULL */
+    float* d_env;                       /* [env_h,env_w,3] zero-filled by the caller, or NULL */
+} svgir_shade_grads;
+
+int svgir_shade_forward(const svgir_shade_cfg* cfg, const svgir_shade_in* in, const svgir_shade_out* out,
+                        void* stream);
+int svgir_shade_backward(const svgir_shade_cfg* cfg, const svgir_shade_in* in, const svgir_shade_grads* g,
+                         void* stream);
+
+/* Stand-alone env lookup for arbitrary directions [n,3] -> rgb [n,3]
+ * (DirectLightMap.direct_light, scene/direct_light_map.py:70-83; EnvLight.direct_light,
+ * scene/envmap.py:54-72 after its resize). Backward scatters into d_env (zero-filled by caller). */
+int svgir_direct_light_forward(int n, int env_h, int env_w, int env_mode, const float* env,
+                               float* env_act_scratch, const float* transform, const float* dirs,
+                               float* out, void* stream);
+int svgir_direct_light_backward(int n, int env_h, int env_w, int env_mode, const float* env,
+                                const float* transform, const float* dirs, const float* g_out,
+                                float* d_env, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

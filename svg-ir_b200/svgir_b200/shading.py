@@ -1,0 +1,279 @@
+"""Host side of the fused PBR render_equation (shading) kernels.
+
+Public entry points
+  shade_surfels(...)        fused fast path: every [N,*] output of the reference's
+                            rendering_equation4 plus the sample means render_view packs
+                            (gaussian_renderer/svgss.py:116-166), differentiable.
+  rendering_equation4(...)  same 9 arguments and return value `(pbr, extra_results)` as
+                            gaussian_renderer/svgss.py:537-593 (drop-in).
+  direct_light(...)         DirectLightMap.direct_light / EnvLight.direct_light
+                            (scene/direct_light_map.py:70-83, scene/envmap.py:54-72), differentiable
+                            w.r.t. the env parameter.
+All arithmetic runs in libsvgir_b200.so (csrc/shading.cu); there is no torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+c_fp = C.c_void_p
+
+
+class ShadeCfg(C.Structure):
+    _fields_ = [("N", C.c_int32), ("Ns", C.c_int32), ("env_h", C.c_int32), ("env_w", C.c_int32),
+                ("env_mode", C.c_int32), ("debug", C.c_int32)]
+
+
+class ShadeIn(C.Structure):
+    _fields_ = [(n, c_fp) for n in ("base_color", "roughness", "metallic", "normals", "viewdirs", "radiance",
+                                    "visibility", "incident_dirs", "incident_areas", "env", "env_transform",
+                                    "env_act_scratch")]
+
+
+class ShadeOut(C.Structure):
+    _fields_ = [(n, c_fp) for n in ("pbr", "diffuse_light", "specular", "direct", "indirect",
+                                    "mean_visibility", "mean_local", "mean_incident", "mean_global")]
+
+
+class ShadeGrads(C.Structure):
+    _fields_ = [(n, c_fp) for n in ("g_pbr", "g_diffuse_light", "g_specular", "g_direct", "g_indirect",
+                                    "g_mean_visibility", "g_mean_local", "g_mean_incident", "g_mean_global",
+                                    "d_base_color", "d_roughness", "d_metallic", "d_normals", "d_viewdirs",
+                                    "d_radiance", "d_visibility", "d_env")]
+
+
+_bound = False
+
+
+def _L():
+    global _bound
+    L = _lib.lib()
+    if not _bound:
+        L.svgir_shade_forward.argtypes = [C.POINTER(ShadeCfg), C.POINTER(ShadeIn), C.POINTER(ShadeOut), C.c_void_p]
+        L.svgir_shade_forward.restype = C.c_int
+        L.svgir_shade_backward.argtypes = [C.POINTER(ShadeCfg), C.POINTER(ShadeIn), C.POINTER(ShadeGrads), C.c_void_p]
+        L.svgir_shade_backward.restype = C.c_int
+        L.svgir_direct_light_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
+        L.svgir_direct_light_forward.restype = C.c_int
+        L.svgir_direct_light_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
+        L.svgir_direct_light_backward.restype = C.c_int
+        _bound = True
+    return L
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+MODE_LEARNABLE = 0  # softplus(param), x2   (DirectLightMap)
+MODE_FIXED = 1      # linear map as given, x1 (EnvLight after its 32x64 resize)
+
+
+def env_of(light):
+    """(env tensor [He,We,3], mode, transform) of one of the reference's light objects, or of a
+    (tensor, mode[, transform]) tuple."""
+    if isinstance(light, (tuple, list)):
+        env, mode = light[0], light[1]
+        tr = light[2] if len(light) > 2 else None
+    elif hasattr(light, "env"):  # DirectLightMap: nn.Parameter [1,H,W,3] (direct_light_map.py:11-16)
+        env, mode, tr = light.env, MODE_LEARNABLE, None
+    elif hasattr(light, "envmap"):  # EnvLight: [H,W,3] resized to 32x64 at every lookup (envmap.py:63-64)
+        e = light.envmap.permute(2, 0, 1).unsqueeze(0)
+        e = F.interpolate(e, size=(32, 64), mode="bilinear", align_corners=False)
+        env, mode, tr = e[0].permute(1, 2, 0), MODE_FIXED, getattr(light, "transform", None)
+    else:
+        raise TypeError("unsupported env light object: %r" % type(light))
+    if env.dim() == 4:
+        env = env[0]
+    return env, mode, tr
+
+
+class _ShadeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
+                incident_areas, env, metallic, env_mode, transform, debug):
+        if not base_color.is_cuda:
+            raise RuntimeError("svgir_b200 shading needs CUDA tensors (no CPU fallback)")
+        L = _L()
+        dev = base_color.device
+        N, Ns = incident_dirs.shape[0], incident_dirs.shape[1]
+        t = dict(base_color=_c(base_color), roughness=_c(roughness), normals=_c(normals), viewdirs=_c(viewdirs),
+                 radiance=_c(radiance), visibility=_c(visibility), incident_dirs=_c(incident_dirs),
+                 incident_areas=_c(incident_areas), env=_c(env), metallic=_c(metallic), transform=_c(transform))
+        He, We = t["env"].shape[0], t["env"].shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        outs = [torch.empty((N, 12), **f32) for _ in range(5)]
+        mv, ml, mi, mg = (torch.empty((N, 1), **f32), torch.empty((N, 3), **f32), torch.empty((N, 3), **f32),
+                          torch.empty((N, 3), **f32))
+        scratch = torch.empty((He, We, 3), **f32)
+        cfg = ShadeCfg(N, Ns, He, We, int(env_mode), int(bool(debug)))
+        cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
+                      _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
+                      _p(t["env"]), _p(t["transform"]), _p(scratch))
+        cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg))
+        if N > 0:
+            with torch.cuda.device(dev):
+                _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
+        ctx.cfg = (N, Ns, He, We, int(env_mode), int(bool(debug)))
+        ctx.has = (metallic is not None, transform is not None)
+        ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
+                                            t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
+                                            t["metallic"], t["transform"]) if x is not None])
+        return (*outs, mv, ml, mi, mg)
+
+    @staticmethod
+    def backward(ctx, g_pbr, g_diff, g_spec, g_dir, g_ind, g_mv, g_ml, g_mi, g_mg):
+        L = _L()
+        saved = list(ctx.saved_tensors)
+        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env = saved[:9]
+        rest = saved[9:]
+        metallic = rest.pop(0) if ctx.has[0] else None
+        transform = rest.pop(0) if ctx.has[1] else None
+        N, Ns, He, We, env_mode, debug = ctx.cfg
+        dev = base_color.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad
+        d_base = torch.empty((N, 12), **f32)
+        d_rough = torch.empty((N, 4), **f32)
+        d_norm = torch.empty((N, 4, 3), **f32)
+        d_view = torch.empty((N, 3), **f32)
+        d_rad = torch.empty((N, Ns, 3), **f32) if need[4] else None
+        d_vis = torch.empty(tuple(visibility.shape), **f32) if need[5] else None
+        d_env = torch.zeros((He, We, 3), **f32) if need[8] else None
+        d_met = torch.empty((N, 4), **f32) if (metallic is not None and need[9]) else None
+        scratch = torch.empty((He, We, 3), **f32)
+        gs = [_c(x) for x in (g_pbr, g_diff, g_spec, g_dir, g_ind, g_mv, g_ml, g_mi, g_mg)]
+        cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
+        cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
+                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch))
+        cg = ShadeGrads(*[_p(x) for x in gs], _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad),
+                        _p(d_vis), _p(d_env))
+        if N > 0:
+            with torch.cuda.device(dev):
+                _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
+        if need[6] or need[7]:
+            raise NotImplementedError("svgir_b200 shading: gradients w.r.t. incident_dirs / incident_areas are not "
+                                      "provided (they are precomputed buffers in the reference, gaussian_model.py:462-463)")
+        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None)
+
+
+def shade_surfels(base_color, roughness, normals, viewdirs, radiance, env_light, visibility, incident_dirs,
+                  incident_areas, metallic=None, debug=False) -> dict:
+    """Fused render_equation. Shapes as in the reference: base_color [N,12] (channel-major),
+    roughness [N,4], normals [N,4,3], viewdirs [N,3], radiance [N,Ns,3], visibility [N,Ns,1],
+    incident_dirs [N,Ns,3], incident_areas [N,Ns,1]. Returns a dict of [N,*] tensors."""
+    env, mode, tr = env_of(env_light)
+    o = _ShadeFn.apply(base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
+                       incident_areas, env, metallic, mode, tr, debug)
+    keys = ("pbr", "diffuse_light", "specular", "direct", "indirect", "mean_visibility", "mean_local_lights",
+            "mean_incident_lights", "mean_global_lights")
+    return dict(zip(keys, o))
+
+
+class _DirectLightFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, env, dirs, env_mode, transform):
+        L = _L()
+        dev = dirs.device
+        env_c, dirs_c, tr = _c(env), _c(dirs.reshape(-1, 3)), _c(transform)
+        n = dirs_c.shape[0]
+        He, We = env_c.shape[0], env_c.shape[1]
+        out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        scratch = torch.empty((He, We, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.svgir_direct_light_forward(n, He, We, int(env_mode), _p(env_c), _p(scratch), _p(tr), _p(dirs_c),
+                                                    _p(out), _stream(dev)), "direct_light_forward")
+        ctx.meta = (n, He, We, int(env_mode), tr is not None)
+        ctx.save_for_backward(*[x for x in (env_c, dirs_c, tr) if x is not None])
+        return out.reshape(dirs.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _L()
+        n, He, We, mode, has_tr = ctx.meta
+        sv = list(ctx.saved_tensors)
+        env_c, dirs_c = sv[0], sv[1]
+        tr = sv[2] if has_tr else None
+        d_env = None
+        if ctx.needs_input_grad[0]:
+            d_env = torch.zeros((He, We, 3), dtype=torch.float32, device=g.device)
+            gc = _c(g.reshape(-1, 3))
+            with torch.cuda.device(g.device):
+                _lib.check(L.svgir_direct_light_backward(n, He, We, mode, _p(env_c), _p(tr), _p(dirs_c), _p(gc), _p(d_env),
+                                                         _stream(g.device)), "direct_light_backward")
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("svgir_b200.direct_light: no gradient w.r.t. directions")
+        return d_env, None, None, None
+
+
+def direct_light(env_light, dirs, transform=None):
+    """Env radiance for arbitrary directions [...,3] -> [...,3]."""
+    env, mode, tr = env_of(env_light)
+    if transform is not None:
+        tr = transform
+    if not dirs.is_cuda:
+        raise RuntimeError("svgir_b200.direct_light needs CUDA tensors (no CPU fallback)")
+    return _DirectLightFn.apply(env, dirs, mode, tr)
+
+
+class _LazyResults(dict):
+    """extra_results of rendering_equation4. The [N,Ns,3] per-sample light tensors the reference
+    materialises eagerly (svgss.py:544-553) are only built when somebody reads them."""
+
+    def __init__(self, eager: dict, lazy: dict):
+        super().__init__(eager)
+        self._lazy = lazy
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            val = self._lazy[key]()
+            self[key] = val
+            return val
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def keys(self):
+        return list(dict.keys(self)) + [k for k in self._lazy if not dict.__contains__(self, k)]
+
+
+def rendering_equation4(base_color, roughness, normals, viewdirs, radiance, direct_light_env_light=None,
+                        visibility_precompute=None, incident_dirs_precompute=None,
+                        incident_areas_precompute=None, metallic=None):
+    """Drop-in for gaussian_renderer/svgss.py:537-593 (same arguments, same `(pbr, extra_results)`)."""
+    r = shade_surfels(base_color, roughness, normals, viewdirs, radiance, direct_light_env_light,
+                      visibility_precompute, incident_dirs_precompute, incident_areas_precompute, metallic)
+
+    def global_lights():
+        return direct_light(direct_light_env_light, incident_dirs_precompute).clamp(0, 64) * visibility_precompute
+
+    def incident_lights():
+        return radiance + extra["global_incident_lights"]
+
+    extra = _LazyResults(
+        {"incident_dirs": incident_dirs_precompute, "local_incident_lights": radiance,
+         "incident_visibility": visibility_precompute, "diffuse_light": r["diffuse_light"],
+         "specular": r["specular"], "direct": r["direct"], "indirect": r["indirect"],
+         # fused sample means (what render_view computes with .mean(-2), svgss.py:149-156)
+         "mean_visibility": r["mean_visibility"], "mean_local_lights": r["mean_local_lights"],
+         "mean_incident_lights": r["mean_incident_lights"]},
+        {"global_incident_lights": global_lights, "incident_lights": incident_lights})
+    return r["pbr"], extra
