@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the svgir_b200 hot path.
+
+Metric (BASELINE.json): stage-2 `svgss + render_equation` forward+backward iterations per second at
+800x800 on a TensoIR-shaped synthetic cloud (config C3-train of SURVEY.md 8(d): 300k spatially-varying
+surfels, one 800x800 view per iteration, 64 light samples, S=4 / VS=52 G-buffer channels).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU; under
+                                                           torchrun every rank renders its own view and
+                                                           the per-surfel gradients are all-reduced)
+  python bench.py --impl reference ...                     the reference path restated on the host CPU
+                                                           (oracle/), bounded sample per step
+  python bench.py --impl reference_cuda ...                (extra) reference CUDA rasteriser (oracle/_ref)
+                                                           + the reference's torch shading graph on the GPU
+
+One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "svg-ir_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+P_SURFELS, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT, N_VIEWS = 300_000, 800, 800, 64, 4, 52, 8
+WORKLOAD = ("C3-train: stage-2 svgss+render_equation fwd+bwd, %dk SV surfels, one %dx%d view/iter, Ns=%d, S=%d, VS=%d"
+            % (P_SURFELS // 1000, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT))
+METRIC, UNIT = "fwd+bwd iters/sec at 800x800", "it/s"
+REF_TILE_STEP = 4        # --impl reference renders 1/16 of the tiles and shades 1/16 of the surfels per step
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def build_host_workload(seed=1234):
+    from svgir_b200 import scene
+    cloud = scene.make_surfels(P_SURFELS, seed=seed)
+    mats = scene.make_materials(cloud, NS, seed=seed + 1)
+    cams = [scene.look_at_camera(WIDTH, HEIGHT, v, N_VIEWS) for v in range(N_VIEWS)]
+    rng = np.random.default_rng(seed + 2)
+    gts = [rng.uniform(0, 1, (3, HEIGHT, WIDTH)).astype(np.float32) for _ in range(2)]
+    return cloud, mats, cams, gts
+
+
+def flat_grads(params):
+    return torch.cat([p.grad.reshape(-1) for p in params])
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from svgir_b200 import _lib, pipeline, shading
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the extension is missing
+
+    cloud, mats, cams, gts = build_host_workload()
+    pc = pipeline.model_from_scene(cloud, mats, dev)
+    env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+    bg = torch.zeros(3, device=dev)
+    cam_dev = [pipeline.camera_from_scene(c, dev) for c in cams]
+    gt_dev = [torch.from_numpy(g).to(dev) for g in gts]
+    params = pc.trainable() + [env]
+
+    def step(i):
+        v = (i * world + rank) % N_VIEWS
+        loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
+        if world > 1:
+            fg = flat_grads(params)
+            dist.all_reduce(fg)  # per-surfel gradient exchange over NVLink
+        return loss, res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) --------------------------------------------------
+    for i in range(args.warmup):
+        loss, res = step(i)
+    sync_all()
+    stats = {"R": int(res["num_rendered"]), "P_vis": int(res["visibility_filter"].sum())}
+    _lib.launch_count(reset=True)
+    _lib.timing_collect(reset=True)
+    _lib.timing_enable(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        loss, res = step(args.warmup + i)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    _lib.timing_enable(False)
+    launches = _lib.launch_count()
+    ktimes = {k: _lib.timing_collect(k) for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess",
+                                                  "preprocess_bwd", "emit", "sort_small", "tile_scan")}
+    _lib.timing_collect(reset=True)
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * args.steps / (ms_max / 1e3)
+
+    # ---- end-to-end through the public API with host buffers (`e2e`) ----------------------------
+    host = {}
+    for name, arr in (("xyz", cloud.means3D), ("opacity", cloud.opacity), ("scaling", cloud.scales),
+                      ("rotation", cloud.rotations), ("shs", cloud.shs), ("base_color", mats["base_color"]),
+                      ("roughness", mats["roughness"]), ("shading_normal", mats["shading_normals"]),
+                      ("radiance", mats["radiance"]), ("visibility", mats["visibility"]),
+                      ("incident_dirs", mats["incident_dirs"]), ("incident_areas", mats["incident_areas"]),
+                      ("env", mats["env_param"]), ("gt", gts[0])):
+        host[name] = torch.from_numpy(arr).pin_memory()
+    cam_host = [{k: torch.from_numpy(getattr(c, k)).pin_memory() for k in ("viewmatrix", "projmatrix", "campos",
+                                                                           "patch_bbox", "prcppoint")} for c in cams]
+    h2d_bytes = sum(t.numel() * 4 for t in host.values()) + sum(t.numel() * 4 for t in cam_host[0].values())
+
+    def e2e_step(i):
+        v = (i * world + rank) % N_VIEWS
+        d = {k: t.to(dev, non_blocking=True) for k, t in host.items()}
+        c = {k: t.to(dev, non_blocking=True) for k, t in cam_host[v].items()}
+        m = pipeline.SurfelModel(d["xyz"], d["opacity"], d["scaling"], d["rotation"], d["shs"], d["base_color"],
+                                 d["roughness"], d["shading_normal"], d["radiance"], d["visibility"],
+                                 d["incident_dirs"], d["incident_areas"])
+        for t in m.trainable():
+            t.requires_grad_(True)
+        envp = d["env"].requires_grad_(True)
+        cam = pipeline.ViewCamera(HEIGHT, WIDTH, cams[v].tanfovx, cams[v].tanfovy, c["viewmatrix"], c["projmatrix"],
+                                  c["campos"], c["patch_bbox"], c["prcppoint"])
+        loss, res = pipeline.training_step(cam, m, envp, bg, d["gt"], zero_grad=False)
+        if world > 1:
+            dist.all_reduce(flat_grads(m.trainable() + [envp]))
+        return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
+
+    for i in range(max(1, min(args.warmup, 2))):
+        e2e_step(i)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    sync_all()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(t_ms.item()) / 1e3)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        R, Pv = stats["R"], stats["P_vis"]
+        b_rec = 104 + 4 * S_FEAT + 4 * VS_FEAT
+        b_pix = 4 * (3 + 3 + 1 + 1 + S_FEAT + VS_FEAT // 4)
+        alg = {  # SURVEY.md 8(d) algorithmic bytes per launch, at this view's measured R / P_vis
+            "composite_bwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12) + Pv * 4 * (15 + S_FEAT + VS_FEAT),
+            "composite_fwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12),
+            "shade_fwd": P_SURFELS * (NS * 32 + 124) + P_SURFELS * 4 * (12 * 5 + S_FEAT),
+            "shade_bwd": P_SURFELS * (NS * 32 + 124) + P_SURFELS * 4 * (12 * 5 + S_FEAT) + P_SURFELS * 4 * (12 + 4 + 12 + 3),
+        }
+        kt = {k: (v[0] / max(v[1], 1)) for k, v in ktimes.items()}  # avg ms per launch
+        dom = max(("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd"), key=lambda k: kt[k])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
+        achieved = alg[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step": world, "parallelism": f"view-dp{world}",
+                       "l2": "working set > L2 (per-sample light buffers 614 MB/iter)", "R": R, "P_vis": Pv},
+            "clocks": clk,
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 12},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+                         "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
+                         "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
+            "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_sample(1, 0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+_REF_CACHE = {}
+
+
+def _ref_inputs():
+    if "w" not in _REF_CACHE:
+        _REF_CACHE["w"] = build_host_workload()
+    return _REF_CACHE["w"]
+
+
+def reference_cpu_step(view: int) -> float:
+    """One BOUNDED SAMPLE of the workload on the host CPU with the oracle: full preprocess + binning,
+    compositing fwd+bwd of every 4th tile row/column (1/16 of the tiles), shading fwd+bwd of every
+    16th surfel. Returns seconds."""
+    from oracle import svgss as O, shading_oracle as SO
+    cloud, mats, cams, gts = _ref_inputs()
+    cam = cams[view % N_VIEWS]
+    t0 = time.perf_counter()
+    sl = slice(view % 16, None, 16)
+    tt = {k: torch.from_numpy(np.ascontiguousarray(mats[k][sl])) for k in
+          ("base_color", "roughness", "shading_normals", "radiance", "visibility", "incident_dirs", "incident_areas")}
+    envp = torch.from_numpy(mats["env_param"]).requires_grad_(True)
+    for k in ("base_color", "roughness", "shading_normals"):
+        tt[k].requires_grad_(True)
+    vd = torch.from_numpy(cam.campos[None] - cloud.means3D[sl])
+    vd = torch.nn.functional.normalize(vd, dim=-1)
+    pbr, extra = SO.rendering_equation4(tt["base_color"], tt["roughness"], tt["shading_normals"], vd, tt["radiance"],
+                                        lambda d: SO.direct_light_learnable(envp, d), tt["visibility"],
+                                        tt["incident_dirs"], tt["incident_areas"])
+    feats, vfeats = SO.pack_features(pbr, extra, tt["base_color"], tt["roughness"], tt["shading_normals"],
+                                     torch.from_numpy(cam.viewmatrix[:3, :3].copy()), True)
+    (vfeats.sum() + feats.sum()).backward()
+    # rasteriser: features of the un-shaded surfels do not change its cost
+    rng = np.random.default_rng(view)
+    f = rng.uniform(0, 1, (P_SURFELS, S_FEAT)).astype(np.float32)
+    vf = rng.uniform(0, 1, (P_SURFELS, VS_FEAT)).astype(np.float32)
+    O.lib().oracle_set_tile_step(REF_TILE_STEP)
+    try:
+        fw = O.forward(cam, cloud.means3D, cloud.opacity, cloud.scales, cloud.rotations, f, vf, shs=cloud.shs)
+        g = [np.full(fw[k].shape, 1.0 / (HEIGHT * WIDTH), np.float32) for k in
+             ("color", "normal_img", "depth", "opacity", "feature", "vfeature")]
+        O.backward(fw, *g)
+    finally:
+        O.lib().oracle_set_tile_step(1)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_sample(steps: int, warmup: int) -> dict:
+    torch.set_num_threads(os.cpu_count() or 1)
+    for i in range(warmup):
+        reference_cpu_step(i)
+    ts = [reference_cpu_step(warmup + i) for i in range(steps)]
+    frac = 1.0 / (REF_TILE_STEP * REF_TILE_STEP)
+    t = float(np.mean(ts))
+    return {"value": round(frac / t, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": ("oracle (C + torch-CPU restatement of the reference path) on 1/%d of the step: all %dk surfels "
+                       "preprocessed+binned, every %dth tile row/col composited fwd+bwd, every 16th surfel shaded fwd+bwd; "
+                       "%.2f s per sample, value = sample fraction / time" % (REF_TILE_STEP ** 2, P_SURFELS // 1000,
+                                                                               REF_TILE_STEP, t)),
+            "sample_seconds": round(t, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_sample(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["sample_seconds"] * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda(args):
+    """Extra arm: the reference's own CUDA rasteriser (oracle/_ref, unmodified sources) plus the
+    reference's torch shading graph, both on this GPU (BASELINE.md 'R-step')."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import ref_cuda, shading_oracle as SO
+    if not (torch.cuda.is_available() and ref_cuda.available()):
+        print(json.dumps({"impl": "reference_cuda", "unavailable": "needs a GPU and oracle/_ref/libsvgss_ref.so"}))
+        return
+    dev = torch.device("cuda:0")
+    cloud, mats, cams, gts = build_host_workload()
+    d = lambda a: torch.from_numpy(a).to(dev)
+    t = {k: d(v) for k, v in mats.items()}
+    geo = dict(means3D=d(cloud.means3D), opacity=d(cloud.opacity), scales=d(cloud.scales), rotations=d(cloud.rotations),
+               shs=d(cloud.shs))
+    for k in ("base_color", "roughness", "shading_normals", "env_param"):
+        t[k].requires_grad_(True)
+    bg = torch.zeros(3, device=dev)
+    cfg3 = torch.ones(3, device=dev)
+    r = ref_cuda.RefSvgss()
+    n = HEIGHT * WIDTH
+    gpix = [torch.full(s, 1.0 / n, device=dev) for s in ((3, HEIGHT, WIDTH), (3, HEIGHT, WIDTH), (1, HEIGHT, WIDTH),
+                                                         (1, HEIGHT, WIDTH), (S_FEAT, HEIGHT, WIDTH), (VS_FEAT // 4, HEIGHT, WIDTH))]
+
+    def step(i):
+        cam = cams[i % N_VIEWS]
+        for k in ("base_color", "roughness", "shading_normals", "env_param"):
+            t[k].grad = None
+        vd = torch.nn.functional.normalize(d(cam.campos)[None] - geo["means3D"], dim=-1)
+        pbr, extra = SO.rendering_equation4(t["base_color"], t["roughness"], t["shading_normals"], vd, t["radiance"],
+                                            lambda x: SO.direct_light_learnable(t["env_param"], x), t["visibility"],
+                                            t["incident_dirs"], t["incident_areas"])
+        feats, vfeats = SO.pack_features(pbr, extra, t["base_color"], t["roughness"], t["shading_normals"],
+                                         d(cam.viewmatrix[:3, :3].copy()), True)
+        r.forward(bg=bg, means3D=geo["means3D"], features=feats.detach().contiguous(), vfeatures=vfeats.detach().contiguous(),
+                  colors=None, opacity=geo["opacity"], scales=geo["scales"], rotations=geo["rotations"], scale_modifier=1.0,
+                  viewmatrix=d(cam.viewmatrix), projmatrix=d(cam.projmatrix), prcppoint=d(cam.prcppoint),
+                  patchbbox=d(cam.patch_bbox), tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, H=HEIGHT, W=WIDTH, sh=geo["shs"],
+                  degree=3, campos=d(cam.campos), config=cfg3)
+        g = r.backward(*gpix)
+        torch.autograd.backward([vfeats], [g["dL_dvfeatures"]])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"impl": "reference_cuda", "metric": METRIC, "value": round(args.steps / (ms / 1e3), 3), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+                      "config": {"workload": WORKLOAD}, "note": "reference CUDA rasteriser (sm_100 build of the unmodified "
+                      "sources) + reference torch shading graph on the same B200"}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.impl == "reference_cuda":
+        run_reference_cuda(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

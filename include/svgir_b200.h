@@ -35,6 +35,15 @@ enum svgir_status {
 const char* svgir_last_error(void);
 int svgir_version(void);
 
+/* Measurement hooks (no reference counterpart; the reference has only commented-out timers,
+ * SURVEY.md section 5). With timing enabled every kernel launch of this library is bracketed by
+ * CUDA events on the launching stream; svgir_timing_collect sums elapsed ms / launch count for one
+ * kernel name (NULL = all) and synchronises the device. svgir_launch_count returns the number of
+ * kernels this library has launched (bench.py's gpu_launches). */
+void svgir_timing_enable(int on);
+int svgir_timing_collect(const char* kernel_name, double* total_ms, int* launches, int reset);
+long long svgir_launch_count(int reset);
+
 /* Per-view constants. Mirrors GaussianRasterizationSettings
  * (gaussian_renderer/svgss_rasterization.py:331-346, rgss_rasterization.py:189-205) plus the
  * sizes RasterizeGaussiansCUDA derives (svgss_rasterization/rasterize_points.cu:69-73,102-106). */

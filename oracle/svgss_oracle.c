@@ -347,6 +347,14 @@ long oracle_bin(int P, const float* means2D, const float* depths, const int* rad
     return R;
 }
 
+/* bench.py's bounded CPU sample: composite only tiles whose row and column index are multiples of
+ * g_tile_step (1 = every tile). */
+static int g_tile_step = 1;
+void oracle_set_tile_step(int s) { g_tile_step = s > 0 ? s : 1; }
+static inline int tile_selected(int px, int py) {
+    return g_tile_step == 1 || (((px / BLOCK_X) % g_tile_step == 0) && ((py / BLOCK_Y) % g_tile_step == 0));
+}
+
 /* Shared per-pair evaluation. Returns 0 = skip, 1 = blend, 2 = terminates pixel. */
 typedef struct {
     float alpha, G, w0, w1, w2, w3, depth, dx, dy;
@@ -414,6 +422,7 @@ void oracle_render_fwd(int variant, int W, int H, int S, int VS, const uint32_t*
 #pragma omp parallel for schedule(dynamic, 64)
     for (long pix_id = 0; pix_id < (long)HW; pix_id++) {
         int py = (int)(pix_id / W), px = (int)(pix_id % W);
+        if (!tile_selected(px, py)) continue;
         int tile = (py / BLOCK_Y) * gx + (px / BLOCK_X);
         uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
         float T = 1.0f, C[3] = {0, 0, 0}, N[3] = {0, 0, 0}, Dacc = 0;
@@ -486,6 +495,7 @@ void oracle_render_bwd(int variant, int W, int H, int S, int VS, const uint32_t*
 #pragma omp parallel for schedule(dynamic, 64)
     for (long pix_id = 0; pix_id < (long)HW; pix_id++) {
         int py = (int)(pix_id / W), px = (int)(pix_id % W);
+        if (!tile_selected(px, py)) continue;
         int tile = (py / BLOCK_Y) * gx + (px / BLOCK_X);
         uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
         const float T_final = final_T[pix_id];

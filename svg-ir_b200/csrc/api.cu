@@ -27,6 +27,28 @@ int check_launch(const char* what, bool debug, cudaStream_t stream) {
     return SVGIR_OK;
 }
 
+// ---- per-kernel timing registry -------------------------------------------------------------
+struct TimingRec { const char* name; cudaEvent_t e0, e1; };
+static bool g_timing = false;
+static TimingRec g_recs[4096];
+static int g_nrec = 0;
+static int g_open = -1;
+static long long g_launches = 0;
+
+void timing_begin(const char* name, cudaStream_t s) {
+    g_launches++;
+    if (!g_timing || g_nrec >= 4096) { g_open = -1; return; }
+    TimingRec& r = g_recs[g_nrec];
+    r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { g_open = -1; return; }
+    cudaEventRecord(r.e0, s);
+    g_open = g_nrec++;
+}
+void timing_end(cudaStream_t s) {
+    if (g_open >= 0) cudaEventRecord(g_recs[g_open].e1, s);
+    g_open = -1;
+}
+
 static int validate(const svgir_raster_cfg* c, const svgir_raster_in* in) {
     if (!c || !in) { set_error("null cfg/in"); return SVGIR_ERR_INVALID; }
     if (c->P < 0 || c->W <= 0 || c->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", c->P, c->W, c->H); return SVGIR_ERR_INVALID; }
@@ -69,6 +91,36 @@ extern "C" {
 const char* svgir_last_error(void) { return g_err; }
 int svgir_version(void) { return 100; }
 
+void svgir_timing_enable(int on) {
+    g_timing = on != 0;
+}
+
+// Sums the elapsed device time (ms) and launch count of every recorded launch whose kernel name
+// equals `name` (NULL = all), then forgets the records if `reset` is set. Synchronises the device.
+int svgir_timing_collect(const char* name, double* total_ms, int* launches, int reset) {
+    cudaDeviceSynchronize();
+    double t = 0; int n = 0;
+    for (int i = 0; i < g_nrec; i++) {
+        if (name && strcmp(name, g_recs[i].name) != 0) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g_recs[i].e0, g_recs[i].e1) == cudaSuccess) { t += ms; n++; }
+    }
+    if (total_ms) *total_ms = t;
+    if (launches) *launches = n;
+    if (reset) {
+        for (int i = 0; i < g_nrec; i++) { cudaEventDestroy(g_recs[i].e0); cudaEventDestroy(g_recs[i].e1); }
+        g_nrec = 0;
+    }
+    return SVGIR_OK;
+}
+
+// Number of kernel launches issued by this library since the last reset (the bench's gpu_launches).
+long long svgir_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
 int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
                             svgir_raster_state* st, svgir_raster_out* out, void* stream) {
     int rc = validate(cfg, in);
@@ -96,7 +148,13 @@ int svgir_raster_render(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
     if (cfg->P == 0) return SVGIR_OK;
     rc = launch_binning(*cfg, *st, out->radii, s);
     if (rc) return rc;
-    return launch_composite_fwd(*cfg, *in, *st, *out, s);
+    rc = launch_composite_fwd(*cfg, *in, *st, *out, s);
+    if (rc) return rc;
+    if (cfg->variant == SVGIR_VARIANT_RGSS && cfg->computer_pseudo_normal) {
+        if (!out->pseudo_normal || !out->surface_xyz) { set_error("pseudo_normal/surface_xyz buffers missing"); return SVGIR_ERR_INVALID; }
+        rc = launch_pseudo_normal(*cfg, *out, s);
+    }
+    return rc;
 }
 
 int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
@@ -125,7 +183,7 @@ int svgir_mark_visible(int variant, int P, const float* means3D, const float* vi
         if (cudaMemsetAsync(present, 0, (size_t)P, s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
         return SVGIR_OK;
     }
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+    { TimedScope ts_("mark_visible", s); mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present); }
     return check_launch("mark_visible", false, s);
 }
 

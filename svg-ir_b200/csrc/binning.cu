@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(1024) sort_large_kernel(int T, const uint2* __
 
 int launch_tile_scan(const svgir_raster_cfg& c, svgir_raster_state& st, cudaStream_t s) {
     const int T = ((c.W + TILE - 1) / TILE) * ((c.H + TILE - 1) / TILE);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, st.tile_count, st.tile_cursor, (uint2*)st.ranges,
-                                         st.big_tiles, st.num_rendered, (long long)st.cap_R);
+    { TimedScope ts_("tile_scan", s); tile_scan_kernel<<<1, 1024, 0, s>>>(T, st.tile_count, st.tile_cursor, (uint2*)st.ranges,
+                                         st.big_tiles, st.num_rendered, (long long)st.cap_R); }
     return check_launch("tile_scan", c.debug, s);
 }
 
@@ -235,20 +235,21 @@ int launch_binning(const svgir_raster_cfg& c, svgir_raster_state& st, const int3
     }
     // cursor[t] was set to start[t] by the scan; tile_scan also re-evaluated the overflow flag
     // against cap_R, which may have changed since svgir_raster_preprocess.
-    tile_scan_kernel<<<1, 1024, 0, s>>>(T, st.tile_count, st.tile_cursor, (uint2*)st.ranges,
-                                         st.big_tiles, st.num_rendered, (long long)st.cap_R);
-    emit_kernel<<<(c.P + 255) / 256, 256, 0, s>>>(c.P, gx, radii, (const ushort4*)st.rect,
+    { TimedScope ts_("tile_scan", s);
+      tile_scan_kernel<<<1, 1024, 0, s>>>(T, st.tile_count, st.tile_cursor, (uint2*)st.ranges,
+                                         st.big_tiles, st.num_rendered, (long long)st.cap_R); }
+    { TimedScope ts_("emit", s); emit_kernel<<<(c.P + 255) / 256, 256, 0, s>>>(c.P, gx, radii, (const ushort4*)st.rect,
                                                   (const float4*)st.rec, st.tile_cursor, st.keys,
-                                                  st.num_rendered);
+                                                  st.num_rendered); }
     int rc = check_launch("emit", c.debug, s);
     if (rc) return rc;
-    sort_small_kernel<<<T, 256, 0, s>>>((const uint2*)st.ranges, st.keys, st.point_list,
-                                        st.sorted_keys, st.num_rendered);
-    sort_medium_kernel<<<148, 1024, MEDIUM_CAP * 8, s>>>(T, (const uint2*)st.ranges, st.big_tiles,
+    { TimedScope ts_("sort_small", s); sort_small_kernel<<<T, 256, 0, s>>>((const uint2*)st.ranges, st.keys, st.point_list,
+                                        st.sorted_keys, st.num_rendered); }
+    { TimedScope ts_("sort_medium", s); sort_medium_kernel<<<148, 1024, MEDIUM_CAP * 8, s>>>(T, (const uint2*)st.ranges, st.big_tiles,
                                                          st.keys, st.point_list, st.sorted_keys,
-                                                         st.num_rendered);
-    sort_large_kernel<<<148, 1024, 0, s>>>(T, (const uint2*)st.ranges, st.big_tiles, st.keys,
-                                           st.point_list, st.sorted_keys, st.num_rendered);
+                                                         st.num_rendered); }
+    { TimedScope ts_("sort_large", s); sort_large_kernel<<<148, 1024, 0, s>>>(T, (const uint2*)st.ranges, st.big_tiles, st.keys,
+                                           st.point_list, st.sorted_keys, st.num_rendered); }
     return check_launch("tile_sort", c.debug, s);
 }
 

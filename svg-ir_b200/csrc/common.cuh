@@ -13,6 +13,16 @@ namespace svgir {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what, bool debug, cudaStream_t stream);
 
+// Optional per-kernel device timing (svgir_timing_enable / svgir_timing_collect in the C ABI):
+// when enabled, every launch is bracketed by a pair of CUDA events on the launching stream.
+void timing_begin(const char* name, cudaStream_t s);
+void timing_end(cudaStream_t s);
+struct TimedScope {
+    cudaStream_t s;
+    TimedScope(const char* name, cudaStream_t st) : s(st) { timing_begin(name, st); }
+    ~TimedScope() { timing_end(s); }
+};
+
 // ---- exactly-rounded fp32 building blocks ------------------------------------------------
 // The binning-relevant chain of the preprocess (projection, culls, covariance, radius, rect,
 // depth key) must reproduce the reference build's roundings bit for bit (SURVEY.md 8(a) a7-a9,
@@ -87,6 +97,7 @@ int launch_tile_scan(const svgir_raster_cfg& c, svgir_raster_state& st, cudaStre
 int launch_binning(const svgir_raster_cfg& c, svgir_raster_state& st, const int32_t* radii, cudaStream_t s);
 int launch_composite_fwd(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
                          svgir_raster_out& out, cudaStream_t s);
+int launch_pseudo_normal(const svgir_raster_cfg& c, svgir_raster_out& out, cudaStream_t s);
 int launch_composite_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                          const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s);
 int launch_preprocess_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,

@@ -309,11 +309,11 @@ static int launch_one_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
             return SVGIR_ERR_CUDA;
         }
     }
-    k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
+    { TimedScope ts_("composite_bwd", s); k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
                                       (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
                                       st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
                                       g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
-                                      g.dL_dfeatures, g.dL_dvfeatures);
+                                      g.dL_dfeatures, g.dL_dvfeatures); }
     return check_launch("composite_bwd", c.debug, s);
 }
 

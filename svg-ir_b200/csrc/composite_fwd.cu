@@ -231,10 +231,10 @@ static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
             return SVGIR_ERR_CUDA;
         }
     }
-    k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
+    { TimedScope ts_("composite_fwd", s); k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
                                       (const uint2*)st.ranges, st.point_list, st.num_rendered,
                                       st.final_T, st.final_D, st.n_contrib, out.color, out.normal,
-                                      out.depth, out.opacity, out.feature, out.vfeature, out.weights);
+                                      out.depth, out.opacity, out.feature, out.vfeature, out.weights); }
     return check_launch("composite_fwd", c.debug, s);
 }
 
@@ -249,6 +249,60 @@ int launch_composite_fwd(const svgir_raster_cfg& c, const svgir_raster_in& in, s
     if (c.S == 7 && NV == 16) return launch_one<7, 16, false>(c, in, st, out, s);   // relight eval
     if (c.S == 0 && NV == 0) return launch_one<0, 0, false>(c, in, st, out, s);
     return launch_one<-1, -1, false>(c, in, st, out, s);
+}
+
+// ---- stage-1 screen-space helpers (rgss-rasterization/cuda_rasterizer/forward.cu:538-631) ------
+// surface_xyz = back-projected (depth/opacity); pseudo normal = -normalize(cross(Sobel_x, Sobel_y))
+// rotated to world space. Only run when computer_pseudo_normal is set.
+__global__ void __launch_bounds__(256) surface_xyz_kernel(int W, int H, float fx, float fy, float cx, float cy,
+                                                          const float* __restrict__ opac,
+                                                          const float* __restrict__ depth,
+                                                          float* __restrict__ xyz) {
+    const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (px >= W || py >= H) return;
+    const size_t HW = (size_t)H * W, id = (size_t)W * py + px;
+    const float d = depth[id] / fmaxf(opac[id], 0.0000001f);
+    xyz[id] = (px - cx) / fx * d;
+    xyz[HW + id] = (py - cy) / fy * d;
+    xyz[2 * HW + id] = d;
+}
+
+__global__ void __launch_bounds__(256) pseudo_normal_kernel(int W, int H, const float* __restrict__ V,
+                                                            const float* __restrict__ xyz,
+                                                            float* __restrict__ normals) {
+    const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (px >= W || py >= H) return;
+    const size_t HW = (size_t)H * W;
+    const int xm = px == 0 ? 0 : px - 1, xp = px == W - 1 ? W - 1 : px + 1;
+    const int ym = py == 0 ? 0 : py - 1, yp = py == H - 1 ? H - 1 : py + 1;
+    float ga[3], gb[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float* p = xyz + i * HW;
+        const float v00 = p[(size_t)W * ym + xm], v01 = p[(size_t)W * ym + px], v02 = p[(size_t)W * ym + xp];
+        const float v10 = p[(size_t)W * py + xm], v12 = p[(size_t)W * py + xp];
+        const float v20 = p[(size_t)W * yp + xm], v21 = p[(size_t)W * yp + px], v22 = p[(size_t)W * yp + xp];
+        ga[i] = -0.125f * v00 + 0.125f * v02 - 0.25f * v10 + 0.25f * v12 - 0.125f * v20 + 0.125f * v22;
+        gb[i] = -0.125f * v00 - 0.25f * v01 - 0.125f * v02 + 0.125f * v20 + 0.25f * v21 + 0.125f * v22;
+    }
+    float n[3] = {ga[1] * gb[2] - ga[2] * gb[1], -ga[0] * gb[2] + ga[2] * gb[0], ga[0] * gb[1] - ga[1] * gb[0]};
+    const float norm = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (norm <= 0.00000f) return;
+    n[0] = -n[0] / norm; n[1] = -n[1] / norm; n[2] = -n[2] / norm;
+    const size_t id = (size_t)W * py + px;
+    normals[id] = V[0] * n[0] + V[1] * n[1] + V[2] * n[2];
+    normals[HW + id] = V[4] * n[0] + V[5] * n[1] + V[6] * n[2];
+    normals[2 * HW + id] = V[8] * n[0] + V[9] * n[1] + V[10] * n[2];
+}
+
+int launch_pseudo_normal(const svgir_raster_cfg& c, svgir_raster_out& out, cudaStream_t s) {
+    const dim3 grid((c.W + TILE - 1) / TILE, (c.H + TILE - 1) / TILE);
+    const float fy = c.H / (2.0f * c.tan_fovy), fx = c.W / (2.0f * c.tan_fovx);
+    { TimedScope ts_("surface_xyz", s);
+      surface_xyz_kernel<<<grid, 256, 0, s>>>(c.W, c.H, fx, fy, c.cx, c.cy, out.opacity, out.depth, out.surface_xyz); }
+    { TimedScope ts_("pseudo_normal", s);
+      pseudo_normal_kernel<<<grid, 256, 0, s>>>(c.W, c.H, c.viewmatrix, out.surface_xyz, out.pseudo_normal); }
+    return check_launch("pseudo_normal", c.debug, s);
 }
 
 }  // namespace svgir

@@ -274,13 +274,13 @@ int launch_preprocess(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
     }
     const int grid = (c.P + 255) / 256;
     if (c.variant == SVGIR_VARIANT_RGSS)
-        preprocess_kernel<true><<<grid, 256, 0, s>>>(c, in, (float4*)st.rec, st.cov3D, st.clamped,
+        { TimedScope ts_("preprocess", s); preprocess_kernel<true><<<grid, 256, 0, s>>>(c, in, (float4*)st.rec, st.cov3D, st.clamped,
                                                       (ushort4*)st.rect, st.tiles_touched,
-                                                      st.tile_count, out.radii);
+                                                      st.tile_count, out.radii); }
     else
-        preprocess_kernel<false><<<grid, 256, 0, s>>>(c, in, (float4*)st.rec, st.cov3D, st.clamped,
+        { TimedScope ts_("preprocess", s); preprocess_kernel<false><<<grid, 256, 0, s>>>(c, in, (float4*)st.rec, st.cov3D, st.clamped,
                                                        (ushort4*)st.rect, st.tiles_touched,
-                                                       st.tile_count, out.radii);
+                                                       st.tile_count, out.radii); }
     return check_launch("preprocess", c.debug, s);
 }
 

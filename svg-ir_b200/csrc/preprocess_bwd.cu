@@ -292,9 +292,9 @@ int launch_preprocess_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                           cudaStream_t s) {
     const int grid = (c.P + 255) / 256;
     if (c.variant == SVGIR_VARIANT_RGSS)
-        preprocess_bwd_kernel<true><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g);
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<true><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g); }
     else
-        preprocess_bwd_kernel<false><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g);
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<false><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g); }
     return check_launch("preprocess_bwd", c.debug, s);
 }
 

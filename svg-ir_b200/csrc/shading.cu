@@ -622,7 +622,7 @@ static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, Sha
         return SVGIR_ERR_INVALID;
     }
     const int nenv = c->env_h * c->env_w * 3;
-    env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, in->env, in->env_act_scratch, c->env_mode);
+    { TimedScope ts_("env_activate", s); env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, in->env, in->env_act_scratch, c->env_mode); }
     a.N = c->N; a.Ns = c->Ns; a.He = c->env_h; a.We = c->env_w;
     a.env_scale = c->env_mode == 0 ? 2.0f : 1.0f;
     a.env_act = in->env_act_scratch; a.transform = in->env_transform;
@@ -646,9 +646,9 @@ int svgir_shade_forward(const svgir_shade_cfg* c, const svgir_shade_in* in, cons
     if (env_bytes <= 96 * 1024) {
         if (env_bytes > 48 * 1024)
             cudaFuncSetAttribute(shade_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_bytes);
-        shade_fwd_kernel<true><<<grid, SH_THREADS, env_bytes, s>>>(a, so);
+        { TimedScope ts_("shade_fwd", s); shade_fwd_kernel<true><<<grid, SH_THREADS, env_bytes, s>>>(a, so); }
     } else {
-        shade_fwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, so);
+        { TimedScope ts_("shade_fwd", s); shade_fwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, so); }
     }
     return check_launch("shade_forward", c->debug, s);
 }
@@ -669,9 +669,9 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
     if (2 * env_bytes <= 96 * 1024) {
         if (2 * env_bytes > 48 * 1024)
             cudaFuncSetAttribute(shade_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * env_bytes));
-        shade_bwd_kernel<true><<<grid, SH_THREADS, 2 * env_bytes, s>>>(a, g, c->env_mode);
+        { TimedScope ts_("shade_bwd", s); shade_bwd_kernel<true><<<grid, SH_THREADS, 2 * env_bytes, s>>>(a, g, c->env_mode); }
     } else {
-        shade_bwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, g, c->env_mode);
+        { TimedScope ts_("shade_bwd", s); shade_bwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, g, c->env_mode); }
     }
     return check_launch("shade_backward", c->debug, s);
 }
@@ -683,8 +683,8 @@ int svgir_direct_light_forward(int n, int env_h, int env_w, int env_mode, const 
     const int nenv = env_h * env_w * 3;
     env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, env, env_act_scratch, env_mode);
     if (n > 0)
-        direct_light_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, env_h, env_w, env_mode == 0 ? 2.0f : 1.0f,
-                                                               env_act_scratch, transform, dirs, out);
+        { TimedScope ts_("direct_light_fwd", s); direct_light_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, env_h, env_w, env_mode == 0 ? 2.0f : 1.0f,
+                                                               env_act_scratch, transform, dirs, out); }
     return check_launch("direct_light_forward", false, s);
 }
 
@@ -693,8 +693,8 @@ int svgir_direct_light_backward(int n, int env_h, int env_w, int env_mode, const
     cudaStream_t s = (cudaStream_t)stream;
     if (n < 0 || env_h <= 0 || env_w <= 0 || !env || !d_env || (n > 0 && (!dirs || !g_out))) { set_error("direct_light_backward: bad args"); return SVGIR_ERR_INVALID; }
     if (n > 0)
-        direct_light_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, env_h, env_w, env_mode == 0 ? 2.0f : 1.0f, env_mode,
-                                                               env, transform, dirs, g_out, d_env);
+        { TimedScope ts_("direct_light_bwd", s); direct_light_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, env_h, env_w, env_mode == 0 ? 2.0f : 1.0f, env_mode,
+                                                               env, transform, dirs, g_out, d_env); }
     return check_launch("direct_light_backward", false, s);
 }
 

@@ -92,8 +92,29 @@ def lib() -> C.CDLL:
     L.svgir_raster_backward.restype = C.c_int
     L.svgir_mark_visible.argtypes = [C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
     L.svgir_mark_visible.restype = C.c_int
+    L.svgir_timing_enable.argtypes = [C.c_int]
+    L.svgir_timing_enable.restype = None
+    L.svgir_timing_collect.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    L.svgir_timing_collect.restype = C.c_int
+    L.svgir_launch_count.argtypes = [C.c_int]
+    L.svgir_launch_count.restype = C.c_longlong
     _lib = L
     return L
+
+
+def timing_enable(on: bool) -> None:
+    lib().svgir_timing_enable(1 if on else 0)
+
+
+def timing_collect(name=None, reset=False):
+    """(total_ms, launches) of the recorded launches of kernel `name` (None = all kernels)."""
+    ms, n = C.c_double(0), C.c_int(0)
+    lib().svgir_timing_collect(name.encode() if name else None, C.byref(ms), C.byref(n), 1 if reset else 0)
+    return ms.value, n.value
+
+
+def launch_count(reset=False) -> int:
+    return int(lib().svgir_launch_count(1 if reset else 0))
 
 
 def check(rc: int, what: str) -> None:
@@ -106,5 +127,7 @@ def check(rc: int, what: str) -> None:
 
 EXPORTED_SYMBOLS = [
     "svgir_last_error", "svgir_version", "svgir_raster_preprocess", "svgir_raster_render",
-    "svgir_raster_backward", "svgir_mark_visible",
+    "svgir_raster_backward", "svgir_mark_visible", "svgir_shade_forward", "svgir_shade_backward",
+    "svgir_direct_light_forward", "svgir_direct_light_backward", "svgir_timing_enable",
+    "svgir_timing_collect", "svgir_launch_count",
 ]

@@ -144,6 +144,7 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
         for k in ("color", "normal", "depth", "opacity", "feature", "vfeature"):
             out[k].zero_()
         st.num_rendered = 0
+        out["n_contrib"] = torch.zeros((H, W), **i32)
         return out, st
 
     keep = st.keep
@@ -218,6 +219,7 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
                            "raster_render")
         _CAP_HINT[hint_key] = int(R * 1.25) + 4096
     st.cfg, st.cin, st.cstate, st.num_rendered = cfg, cin, cst, R
+    out["n_contrib"] = t["n_contrib"].view(H, W)
     if R == 0:
         # nothing binned: the compositor still wrote background-only images
         pass
