@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads and exports every symbol include/svgir_b200.h declares; host-side
+logic of the drop-in packages (argument checking, tuple orders) that needs no GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "svgir_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(svgir_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from svgir_b200 import _lib
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(_lib.EXPORTED_SYMBOLS) <= set(names)
+    assert L.svgir_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    import ctypes as C
+    from svgir_b200 import _lib, shading
+    assert C.sizeof(_lib.RasterCfg) == 18 * 4 + 6 * 8
+    assert C.sizeof(_lib.RasterIn) == 9 * 8
+    assert C.sizeof(_lib.RasterState) == 17 * 8
+    assert C.sizeof(_lib.RasterOut) == 10 * 8
+    assert C.sizeof(_lib.RasterGrads) == 20 * 8
+    assert C.sizeof(shading.ShadeCfg) == 6 * 4
+    assert C.sizeof(shading.ShadeIn) == 12 * 8
+
+
+def test_settings_tuples_have_reference_field_order():
+    import svgss_rasterization as sv
+    import rgss_rasterization as rg
+    assert sv.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "patch_bbox", "prcppoint", "sh_degree", "campos", "prefiltered", "debug", "config")
+    assert rg.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "cx", "cy", "bg", "scale_modifier", "viewmatrix",
+        "projmatrix", "sh_degree", "campos", "prefiltered", "backward_geometry", "computer_pseudo_normal", "debug")
+    for mod in (sv, rg):
+        for name in ("GaussianRasterizer", "rasterize_gaussians", "_RasterizeGaussians", "_C"):
+            assert hasattr(mod, name)
+        for fn in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+            assert callable(getattr(mod._C, fn))
+
+
+def test_rasterizer_argument_checks_match_reference_messages():
+    import svgss_rasterization as sv
+    s = sv.GaussianRasterizationSettings(8, 8, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4),
+                                         torch.tensor([0., 0., 8., 8.]), torch.tensor([.5, .5]), 3, torch.zeros(3),
+                                         False, False, torch.ones(3))
+    r = sv.GaussianRasterizer(s)
+    m = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(m, m, torch.ones(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.ones(4, 1), colors_precomp=torch.ones(4, 3))
+    # no CPU fallback: CPU tensors fail loudly instead of silently computing elsewhere
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r(m, m, torch.ones(4, 1), colors_precomp=torch.ones(4, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "svg-ir_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "liboracle" in txt or "oracle/" in txt.replace("oracle/ ", ""):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
