@@ -194,14 +194,22 @@ typedef struct svgir_shade_in {
     const float* env;            /* [env_h,env_w,3] parameter (mode 0) or map (mode 1) */
     const float* env_transform;  /* [3,3] or NULL (envmap.py:58-61) */
     float* env_act_scratch;      /* [env_h,env_w,3] scratch for the activated map */
+    const float* view3x3;        /* [3,3] = viewmatrix[:3,:3] (row-vector convention), only for `pack` */
 } svgir_shade_in;
 
 typedef struct svgir_shade_out {
-    float* pbr; float* diffuse_light; float* specular; float* direct; float* indirect; /* [N,12] */
+    float* pbr; float* diffuse_light; float* specular; float* direct; float* indirect; /* [N,12]; any may be NULL */
     float* mean_visibility;  /* [N,1] sample means that render_view packs into `features` */
     float* mean_local;       /* [N,3]  (svgss.py:149-156); any of the four may be NULL */
     float* mean_incident;    /* [N,3] */
     float* mean_global;      /* [N,3] */
+    /* Optional fused packing of render_view (gaussian_renderer/svgss.py:141-166): the five [N,12]
+     * outputs may be column blocks of one `vfeatures` tensor (row_stride = VS floats between rows,
+     * 0 = dense 12) and the means column blocks of `features` (mean_vis_stride / mean_stride, 0 = dense
+     * 1 / 3). `pack`, if set, points at the first pass-through column and receives
+     * base_color[12] | view-space shading normals[12, channel-major] | roughness[4]. */
+    float* pack;
+    int32_t row_stride, mean_vis_stride, mean_stride, reserved_;
 } svgir_shade_out;
 
 typedef struct svgir_shade_grads {
@@ -219,6 +227,10 @@ typedef struct svgir_shade_grads {
     float* d_radiance;                  /* [N,Ns,3] or NULL */
     float* d_visibility;                /* [N,Ns,1] or NULL */
     float* d_env;                       /* [env_h,env_w,3] zero-filled by the caller, or NULL */
+    /* packed upstream gradients (see svgir_shade_out): strides of the g_* rows, and the gradient of
+     * the pass-through columns, which is added into d_base_color / d_normals / d_roughness */
+    const float* g_pack;
+    int32_t g_row_stride, g_mean_vis_stride, g_mean_stride, reserved_;
 } svgir_shade_grads;
 
 int svgir_shade_forward(const svgir_shade_cfg* cfg, const svgir_shade_in* in, const svgir_shade_out* out,

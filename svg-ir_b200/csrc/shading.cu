@@ -8,10 +8,12 @@
 // (N*Ns*32 B), keeps the (soft-plus'd) environment map in shared memory and writes only [N,12]
 // results; the backward kernel recomputes the per-sample terms instead of loading saved ones.
 //
-// Mapping: a lane owns one (surfel, vertex) pair -- 8 surfels x 4 vertices per warp -- and loops
-// over all Ns samples, so every per-vertex sum lives in registers and needs no cross-lane
-// reduction.  Sample-level, vertex-independent work (env lookup, half vector, Fresnel power) is
-// split across the 4 lanes of a surfel (one sample each) and exchanged with shuffles.
+// Mapping: one warp per surfel, one lane per light sample.  Every per-sample buffer
+// ([N,Ns,3] dirs and radiance, [N,Ns] visibility and areas) is read with fully coalesced loads exactly
+// once; the vertex-independent work of a sample (env lookup, half vector, Fresnel power) is done once
+// by its lane, which then evaluates all 4 vertices; the 24-48 per-(vertex,channel) sums are combined
+// with one "transposed" warp reduction (~1 shuffle per value instead of 5).  The grid is persistent
+// (a few CTAs per SM striding over the surfels) so the env map is staged into shared memory once per CTA.
 //
 // Algebra: with T = L*area*max(N.w,0), pbr = mean((f_d+f_s) T) = f_d*mean(T) + F0*mean(D T) +
 // (1-F0)*mean(p D T) where f_s = (F0 + (1-F0) p) D, p = 2^((-5.55473 VoH - 6.98316) VoH) and
@@ -25,7 +27,8 @@
 
 namespace svgir {
 
-#define SH_THREADS 256
+#define SH_THREADS 256   // forward: ~120 regs -> 2 CTAs/SM
+#define SHB_THREADS 128  // backward: ~165 regs -> 3 CTAs/SM
 #define PI_F 3.14159265358979323846f
 
 struct SampleShared {  // vertex-independent per-sample quantities, produced by one lane of the quad
@@ -82,9 +85,9 @@ __global__ void env_activate_kernel(int n, const float* __restrict__ param, floa
 struct ShadeArgs {
     int N, Ns, He, We;
     float env_scale;          // 2.0 for the learnable map (direct_light_map.py:83), 1.0 for HDR maps
-    int env_in_smem;
     const float* env_act;     // [He,We,3] activated env
     const float* transform;   // optional [3,3] applied to dirs before the lookup (envmap.py:58-61)
+    const float* view3x3;     // optional: world->view rotation rows (viewmatrix[:3,:3]) for the packed normals
     const float* base_color;  // [N,12] channel-major
     const float* roughness;   // [N,4]
     const float* metallic;    // [N,4] or null
@@ -96,48 +99,58 @@ struct ShadeArgs {
     const float* areas;       // [N,Ns]
 };
 
-struct VertexConst {  // per-lane constants
-    float Nx, Ny, Nz;        // raw shading normal
-    float inv_nlen;
-    float tx, ty, tz;        // normalised, sign-flipped normal  N~
-    float sgn;
-    float Vx, Vy, Vz;        // normalised view dir
-    float inv_vlen;
-    float nov_raw, NoV;
-    float r, a2, k;
-};
-
-__device__ __forceinline__ void load_vertex(const ShadeArgs& a, int n, int v, VertexConst& c) {
-    const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
-    c.Nx = nn[0]; c.Ny = nn[1]; c.Nz = nn[2];
-    const float nl = fmaxf(sqrtf(c.Nx * c.Nx + c.Ny * c.Ny + c.Nz * c.Nz), 1e-12f);
-    c.inv_nlen = 1.f / nl;
-    float hx = c.Nx * c.inv_nlen, hy = c.Ny * c.inv_nlen, hz = c.Nz * c.inv_nlen;
-    const float* vd = a.viewdirs + (size_t)n * 3;
-    const float vl = fmaxf(sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]), 1e-12f);
-    c.inv_vlen = 1.f / vl;
-    c.Vx = vd[0] * c.inv_vlen; c.Vy = vd[1] * c.inv_vlen; c.Vz = vd[2] * c.inv_vlen;
-    const float d = c.Vx * hx + c.Vy * hy + c.Vz * hz;
-    c.sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    c.tx = hx * c.sgn; c.ty = hy * c.sgn; c.tz = hz * c.sgn;
-    c.nov_raw = c.tx * c.Vx + c.ty * c.Vy + c.tz * c.Vz;
-    c.NoV = fminf(fmaxf(c.nov_raw, 1e-6f), 1.f);
-    c.r = a.roughness[(size_t)n * 4 + v];
-    const float al = c.r * c.r;
-    c.a2 = al * al;
-    c.k = (al + 2.f * c.r + 1.0f) / 8.0f;
+// Sum over the warp of K (<= NP, NP a power of two <= 32) per-lane values, "transposed": instead of
+// 5 shuffles per value, each step exchanges half of the remaining slots, so the whole reduction
+// costs ~NP shuffles.  Returns on every lane L the total of slot  L >> (5 - log2(NP)).
+template <int NP>
+__device__ __forceinline__ float warp_reduce_slots(float (&v)[NP], int lane) {
+    const unsigned full = 0xffffffffu;
+    int cur = NP;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        if (cur > 1) {
+            const int half = cur >> 1;
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < NP / 2; i++) {
+                if (i < half) {
+                    const float send = up ? v[i] : v[i + half];
+                    const float keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(full, send, o);
+                }
+            }
+            cur = half;
+        } else {
+            v[0] += __shfl_xor_sync(full, v[0], o);
+        }
+    }
+    return v[0];
 }
 
-// One lane prepares the vertex-independent part of sample s of surfel n.
-__device__ __forceinline__ void prepare_sample(const ShadeArgs& a, const float* env, int n, int s, float Vx, float Vy,
-                                               float Vz, SampleShared& o, float& vis, float raw_env[3],
-                                               EnvTap& tap, float Lg[3], float Ll[3]) {
-    const size_t is = (size_t)n * a.Ns + s;
+// Per-sample, vertex-independent quantities (one lane = one light sample of the warp's surfel).
+struct Sample {
+    float wx, wy, wz, il;   // raw incident direction, 1/|w|
+    float hx, hy, hz, hlen; // half vector (normalised), |(L+V)/2|
+    float voh_raw, p;       // V.H before the clamp, 2^((a1 VoH + a0) VoH)
+    float ag[3], al[3];     // area * clamp(env)*vis , area * radiance
+    float lg[3];            // clamp(env*scale) (without visibility)
+    float raw[3];           // bilinear env value before scale/clamp
+    float rad[3];           // cached radiance
+    float vis, area;
+    EnvTap tap;
+};
+
+__device__ __forceinline__ void load_sample(const ShadeArgs& a, const float* env, size_t is, bool ok, float Vx,
+                                            float Vy, float Vz, Sample& o) {
     const float* d = a.dirs + is * 3;
     o.wx = d[0]; o.wy = d[1]; o.wz = d[2];
-    const float il = 1.f / fmaxf(sqrtf(o.wx * o.wx + o.wy * o.wy + o.wz * o.wz), 1e-12f);
-    o.lx = o.wx * il; o.ly = o.wy * il; o.lz = o.wz * il;
-    float hx = (o.lx + Vx) * 0.5f, hy = (o.ly + Vy) * 0.5f, hz = (o.lz + Vz) * 0.5f;
+    const float* rad = a.radiance + is * 3;
+    const float r0 = rad[0], r1 = rad[1], r2 = rad[2];
+    o.vis = ok ? a.visibility[is] : 0.f;
+    o.area = ok ? a.areas[is] : 0.f;
+    o.il = 1.f / fmaxf(sqrtf(o.wx * o.wx + o.wy * o.wy + o.wz * o.wz), 1e-12f);
+    const float lx = o.wx * o.il, ly = o.wy * o.il, lz = o.wz * o.il;
+    const float hx = (lx + Vx) * 0.5f, hy = (ly + Vy) * 0.5f, hz = (lz + Vz) * 0.5f;
     o.hlen = fmaxf(sqrtf(hx * hx + hy * hy + hz * hz), 1e-12f);
     const float ih = 1.f / o.hlen;
     o.hx = hx * ih; o.hy = hy * ih; o.hz = hz * ih;
@@ -152,60 +165,56 @@ __device__ __forceinline__ void prepare_sample(const ShadeArgs& a, const float* 
         const float tz = qx * t[6] + qy * t[7] + qz * t[8];
         qx = tx; qy = ty; qz = tz;
     }
-    tap = env_coords(qx, qy, qz, a.He, a.We);
-    env_fetch(env, a.He, a.We, tap, raw_env);
-    vis = a.visibility[is];
-    const float area = a.areas[is];
-    const float* rad = a.radiance + is * 3;
+    o.tap = env_coords(qx, qy, qz, a.He, a.We);
+    env_fetch(env, a.He, a.We, o.tap, o.raw);
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-        Lg[ch] = fminf(fmaxf(raw_env[ch] * a.env_scale, 0.f), 64.f) * vis;
-        Ll[ch] = rad[ch];
+        o.lg[ch] = fminf(fmaxf(o.raw[ch] * a.env_scale, 0.f), 64.f);
+        o.ag[ch] = o.area * (o.lg[ch] * o.vis);
     }
-    o.gr = area * Lg[0]; o.gg = area * Lg[1]; o.gb = area * Lg[2];
-    o.lr = area * Ll[0]; o.lg = area * Ll[1]; o.lb = area * Ll[2];
+    o.rad[0] = r0; o.rad[1] = r1; o.rad[2] = r2;
+    o.al[0] = o.area * r0; o.al[1] = o.area * r1; o.al[2] = o.area * r2;
 }
 
-__device__ __forceinline__ SampleShared quad_bcast(const SampleShared& m, int src_lane) {
-    SampleShared o;
-    const unsigned full = 0xffffffffu;
-#define BC(f) o.f = __shfl_sync(full, m.f, src_lane)
-    BC(wx); BC(wy); BC(wz); BC(lx); BC(ly); BC(lz); BC(hx); BC(hy); BC(hz); BC(hlen); BC(voh_raw); BC(p);
-    BC(gr); BC(gg); BC(gb); BC(lr); BC(lg); BC(lb);
-#undef BC
-    return o;
-}
-
-struct VertexSample {  // vertex-level BRDF terms of one sample
-    float ndi, ndi_raw, Dterm;
-    float nol_raw, noh_raw, NoL, NoH, nom0, nom1, nom2, nom_raw;
+// Per-(surfel, vertex) constants. c = sign(V.N^)/|N| so that N~.x = c (N.x) for the normalised,
+// view-facing normal N~ of GGX_specular4 (svgss.py:603-607); N stays raw for n.w (svgss.py:548).
+struct VertexConst {
+    float Nx, Ny, Nz, c;
+    float a2, k, nom1, NoV;
+    float nv_raw, inv_nlen, r;
 };
 
-__device__ __forceinline__ void eval_vertex(const VertexConst& c, const SampleShared& s, VertexSample& o) {
-    o.ndi_raw = c.Nx * s.wx + c.Ny * s.wy + c.Nz * s.wz;
-    o.ndi = fmaxf(o.ndi_raw, 0.f);
-    o.nol_raw = c.tx * s.lx + c.ty * s.ly + c.tz * s.lz;
-    o.noh_raw = c.tx * s.hx + c.ty * s.hy + c.tz * s.hz;
-    o.NoL = fminf(fmaxf(o.nol_raw, 1e-6f), 1.f);
-    o.NoH = fminf(fmaxf(o.noh_raw, 1e-6f), 1.f);
-    o.nom0 = o.NoH * o.NoH * (c.a2 - 1.f) + 1.f;
-    o.nom1 = c.NoV * (1.f - c.k) + c.k;
-    o.nom2 = o.NoL * (1.f - c.k) + c.k;
-    o.nom_raw = 4.f * PI_F * o.nom0 * o.nom0 * o.nom1 * o.nom2;
-    const float nom = fminf(fmaxf(o.nom_raw, 1e-6f), 4.f * PI_F);
-    o.Dterm = c.a2 / nom;
+__device__ __forceinline__ void vertex_consts(const ShadeArgs& a, int n, int v, float Vx, float Vy, float Vz,
+                                              VertexConst& c) {
+    const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
+    c.Nx = nn[0]; c.Ny = nn[1]; c.Nz = nn[2];
+    c.inv_nlen = 1.f / fmaxf(sqrtf(c.Nx * c.Nx + c.Ny * c.Ny + c.Nz * c.Nz), 1e-12f);
+    const float d = (c.Nx * c.inv_nlen) * Vx + (c.Ny * c.inv_nlen) * Vy + (c.Nz * c.inv_nlen) * Vz;
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    c.c = sgn * c.inv_nlen;
+    c.nv_raw = (c.Nx * Vx + c.Ny * Vy + c.Nz * Vz) * c.c;   // N~.V before the clamp
+    c.NoV = fminf(fmaxf(c.nv_raw, 1e-6f), 1.f);
+    c.r = a.roughness[(size_t)n * 4 + v];
+    const float al = c.r * c.r;
+    c.a2 = al * al;
+    c.k = (al + 2.f * c.r + 1.0f) / 8.0f;
+    c.nom1 = c.NoV * (1.f - c.k) + c.k;
 }
 
-struct ShadeOut {
-    float* pbr; float* diffuse; float* specular; float* direct; float* indirect;  // [N,12]
-    float* mean_vis;       // [N,1]
-    float* mean_local;     // [N,3]
-    float* mean_incident;  // [N,3]
-    float* mean_global;    // [N,3]
+struct ShadeOutK {
+    float* pbr; float* diffuse; float* specular; float* direct; float* indirect;  // [N,row_stride] or null
+    float* mean_vis;       // rows of mean_stride floats, or null
+    float* mean_local;
+    float* mean_incident;
+    float* mean_global;
+    float* pack;           // optional: base12 | view-space normals 12 | roughness 4 (row_stride)
+    int row_stride, mean_vis_stride, mean_stride;
 };
 
-template <bool ENV_SMEM>
-__global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a, const ShadeOut out) {
+// One warp per surfel, one lane per light sample: every per-sample buffer is read with fully
+// coalesced loads exactly once; per-vertex sums are combined with one transposed warp reduction.
+template <bool SPLIT, bool MET, bool ENV_SMEM>
+__global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a, const ShadeOutK out) {
     extern __shared__ __align__(16) float env_s[];
     const float* env = a.env_act;
     if (ENV_SMEM) {
@@ -213,94 +222,154 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         __syncthreads();
         env = env_s;
     }
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int quad_base = lane & ~3, v = lane & 3;
-    const int n = (blockIdx.x * SH_THREADS + threadIdx.x) >> 2;
-    const bool valid = n < a.N;
-    const int nc = valid ? n : a.N - 1;  // clamp so every lane runs the shuffles
-    VertexConst c;
-    load_vertex(a, nc, v, c);
-    float Dg[3] = {0, 0, 0}, Dl[3] = {0, 0, 0}, SAg[3] = {0, 0, 0}, SBg[3] = {0, 0, 0}, SAl[3] = {0, 0, 0}, SBl[3] = {0, 0, 0};
-    float m_vis = 0.f, m_g[3] = {0, 0, 0}, m_l[3] = {0, 0, 0};
+    constexpr int WPC = SH_THREADS / 32;
     const int Ns = a.Ns;
-    for (int s0 = 0; s0 < Ns; s0 += 4) {
-        SampleShared mine;
-        float vis = 0.f, raw_env[3], Lg_s[3], Ll_s[3];
-        EnvTap tap;
-        const int s = s0 + v;
-        const bool sv = s < Ns;
-        prepare_sample(a, env, nc, sv ? s : Ns - 1, c.Vx, c.Vy, c.Vz, mine, vis, raw_env, tap, Lg_s, Ll_s);
-        if (sv) {
-            m_vis += vis;
+    const float inv = 1.f / (float)Ns;
+    for (int n = blockIdx.x * WPC + (threadIdx.x >> 5); n < a.N; n += gridDim.x * WPC) {
+        const float* vd = a.viewdirs + (size_t)n * 3;
+        const float inv_vlen = 1.f / fmaxf(sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]), 1e-12f);
+        const float Vx = vd[0] * inv_vlen, Vy = vd[1] * inv_vlen, Vz = vd[2] * inv_vlen;
+        VertexConst vc[4];
+        float F0[4][3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) { m_g[ch] += Lg_s[ch]; m_l[ch] += Ll_s[ch]; }
-        }
+        for (int v = 0; v < 4; v++) {
+            vertex_consts(a, n, v, Vx, Vy, Vz, vc[v]);
+            if (MET) {
+                const float m = a.metallic[(size_t)n * 4 + v];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const SampleShared sh = quad_bcast(mine, quad_base + t);
-            if (s0 + t >= Ns) continue;
-            VertexSample vs;
-            eval_vertex(c, sh, vs);
-            const float tg[3] = {sh.gr * vs.ndi, sh.gg * vs.ndi, sh.gb * vs.ndi};
-            const float tl[3] = {sh.lr * vs.ndi, sh.lg * vs.ndi, sh.lb * vs.ndi};
-            const float pd = sh.p * vs.Dterm;
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                Dg[ch] += tg[ch]; Dl[ch] += tl[ch];
-                SAg[ch] = fmaf(vs.Dterm, tg[ch], SAg[ch]); SBg[ch] = fmaf(pd, tg[ch], SBg[ch]);
-                SAl[ch] = fmaf(vs.Dterm, tl[ch], SAl[ch]); SBl[ch] = fmaf(pd, tl[ch], SBl[ch]);
+                for (int ch = 0; ch < 3; ch++) F0[v][ch] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 4 * ch + v] * m;
             }
         }
-    }
-    // quad-reduce the sample means (each lane saw a quarter of the samples)
-    const unsigned full = 0xffffffffu;
+        // D = sum ndi*A, S = sum f_s*ndi*A; index [0]: env ("direct") light or the total when !SPLIT, [1]: cached radiance
+        float D[SPLIT ? 2 : 1][4][3], S[SPLIT ? 2 : 1][4][3];
 #pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
-        m_vis += __shfl_xor_sync(full, m_vis, o);
+        for (int q = 0; q < (SPLIT ? 2 : 1); q++)
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            m_g[ch] += __shfl_xor_sync(full, m_g[ch], o);
-            m_l[ch] += __shfl_xor_sync(full, m_l[ch], o);
+            for (int v = 0; v < 4; v++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) { D[q][v][ch] = 0.f; S[q][v][ch] = 0.f; }
+        float m_vis = 0.f, m_g[3] = {0, 0, 0}, m_l[3] = {0, 0, 0};
+
+        for (int s0 = 0; s0 < Ns; s0 += 32) {
+            const int s = s0 + lane;
+            const bool ok = s < Ns;
+            Sample sm;
+            load_sample(a, env, (size_t)n * Ns + (ok ? s : Ns - 1), ok, Vx, Vy, Vz, sm);
+            if (ok) {
+                m_vis += sm.vis;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    m_g[ch] += sm.lg[ch] * sm.vis;
+                    m_l[ch] += sm.rad[ch];
+                }
+            }
+            float A0[3], A1[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                A0[ch] = SPLIT ? sm.ag[ch] : sm.ag[ch] + sm.al[ch];
+                A1[ch] = sm.al[ch];
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const VertexConst& c = vc[v];
+                const float ndi_raw = c.Nx * sm.wx + c.Ny * sm.wy + c.Nz * sm.wz;
+                const float ndi = fmaxf(ndi_raw, 0.f);
+                const float nh = c.Nx * sm.hx + c.Ny * sm.hy + c.Nz * sm.hz;
+                const float NoL = fminf(fmaxf(c.c * sm.il * ndi_raw, 1e-6f), 1.f);
+                const float NoH = fminf(fmaxf(c.c * nh, 1e-6f), 1.f);
+                const float nom0 = NoH * NoH * (c.a2 - 1.f) + 1.f;
+                const float nom2 = NoL * (1.f - c.k) + c.k;
+                const float nom = fminf(fmaxf(4.f * PI_F * nom0 * nom0 * c.nom1 * nom2, 1e-6f), 4.f * PI_F);
+                const float Dt = __fdividef(c.a2, nom);
+                const float dn = Dt * ndi;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float f0 = MET ? F0[v][ch] : 0.04f;
+                    const float fsn = (f0 + (1.f - f0) * sm.p) * dn;
+                    D[0][v][ch] = fmaf(ndi, A0[ch], D[0][v][ch]);
+                    S[0][v][ch] = fmaf(fsn, A0[ch], S[0][v][ch]);
+                    if (SPLIT) {
+                        D[1][v][ch] = fmaf(ndi, A1[ch], D[1][v][ch]);
+                        S[1][v][ch] = fmaf(fsn, A1[ch], S[1][v][ch]);
+                    }
+                }
+            }
         }
-    }
-    if (!valid) return;
-    const float inv = 1.f / (float)Ns;
-    const float met = a.metallic ? a.metallic[(size_t)n * 4 + v] : 0.f;
+        // slots: 0..11 D (channel-major: 4*ch+v), 12..23 S, 24 vis, 25..27 local, 28..30 global
+        float r0[32];
 #pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const size_t o = (size_t)n * 12 + 4 * ch + v;
-        const float base = a.base_color[o];
-        const float fd = (1.f - met) * base / PI_F;
-        const float F0 = 0.04f * (1.f - met) + base * met;
-        const float specG = (F0 * SAg[ch] + (1.f - F0) * SBg[ch]) * inv;
-        const float specL = (F0 * SAl[ch] + (1.f - F0) * SBl[ch]) * inv;
-        const float dg = Dg[ch] * inv, dl = Dl[ch] * inv;
-        const float diff = dg + dl;
-        out.diffuse[o] = diff;
-        out.specular[o] = specG + specL;
-        out.pbr[o] = fd * diff + (specG + specL);
-        out.direct[o] = fd * dg + specG;
-        out.indirect[o] = fd * dl + specL;
-    }
-    if (v == 0) {
-        if (out.mean_vis) out.mean_vis[n] = m_vis * inv;
+        for (int v = 0; v < 4; v++)
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            if (out.mean_local) out.mean_local[(size_t)n * 3 + ch] = m_l[ch] * inv;
-            if (out.mean_global) out.mean_global[(size_t)n * 3 + ch] = m_g[ch] * inv;
-            if (out.mean_incident) out.mean_incident[(size_t)n * 3 + ch] = (m_l[ch] + m_g[ch]) * inv;
+            for (int ch = 0; ch < 3; ch++) { r0[4 * ch + v] = D[0][v][ch]; r0[12 + 4 * ch + v] = S[0][v][ch]; }
+        r0[24] = m_vis;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) { r0[25 + ch] = m_l[ch]; r0[28 + ch] = m_g[ch]; }
+        r0[31] = 0.f;
+        const float t0 = warp_reduce_slots<32>(r0, lane) * inv;
+        float t1 = 0.f;
+        if (SPLIT) {
+            float r1[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) r1[i] = 0.f;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) { r1[4 * ch + v] = D[1][v][ch]; r1[12 + 4 * ch + v] = S[1][v][ch]; }
+            t1 = warp_reduce_slots<32>(r1, lane) * inv;
+        }
+        const float s0v = __shfl_down_sync(full, t0, 12);   // lanes 0..11: S of the same (ch,v)
+        const float s1v = __shfl_down_sync(full, t1, 12);
+        const float gl = __shfl_down_sync(full, t0, 3);     // lanes 25..27: global light of the same channel
+        if (lane < 12) {
+            const int v = lane & 3;
+            const size_t o = (size_t)n * out.row_stride + lane;
+            const float base = a.base_color[(size_t)n * 12 + lane];
+            const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
+            const float fd = (1.f - met) * base / PI_F;
+            if (!SPLIT) {
+                if (out.diffuse) out.diffuse[o] = t0;
+                if (out.specular) out.specular[o] = s0v;
+                if (out.pbr) out.pbr[o] = fd * t0 + s0v;
+            } else {
+                const float dir = fd * t0 + s0v, ind = fd * t1 + s1v;
+                if (out.diffuse) out.diffuse[o] = t0 + t1;
+                if (out.specular) out.specular[o] = s0v + s1v;
+                if (out.pbr) out.pbr[o] = fd * (t0 + t1) + (s0v + s1v);
+                if (out.direct) out.direct[o] = dir;
+                if (out.indirect) out.indirect[o] = ind;
+            }
+            if (out.pack) {  // render_view's pass-through columns (svgss.py:157-166)
+                float* pk = out.pack + (size_t)n * out.row_stride;
+                pk[lane] = base;
+                const int j = lane >> 2;  // view-space axis; n_view[v][j] = sum_i N[v][i] R[i][j], R row-major [3,3]
+                const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
+                pk[12 + lane] = nn[0] * a.view3x3[j] + nn[1] * a.view3x3[3 + j] + nn[2] * a.view3x3[6 + j];
+                if (lane < 4) pk[24 + lane] = a.roughness[(size_t)n * 4 + lane];
+            }
+        } else if (lane == 24) {
+            if (out.mean_vis) out.mean_vis[(size_t)n * out.mean_vis_stride] = t0;
+        } else if (lane >= 25 && lane < 28) {
+            const int ch = lane - 25;
+            if (out.mean_local) out.mean_local[(size_t)n * out.mean_stride + ch] = t0;
+            if (out.mean_incident) out.mean_incident[(size_t)n * out.mean_stride + ch] = t0 + gl;
+        } else if (lane >= 28 && lane < 31) {
+            if (out.mean_global) out.mean_global[(size_t)n * out.mean_stride + (lane - 28)] = t0;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-struct ShadeGrads {
+struct ShadeGradsK {
     const float* g_pbr; const float* g_diffuse; const float* g_specular; const float* g_direct;
-    const float* g_indirect;                     // [N,12] or null
-    const float* g_mean_vis;                     // [N,1] or null
-    const float* g_mean_local;                   // [N,3] or null
-    const float* g_mean_incident;                // [N,3] or null
-    const float* g_mean_global;                  // [N,3] or null
+    const float* g_indirect;                     // rows of g_row_stride floats, or null
+    const float* g_mean_vis;                     // rows of g_mean_stride floats, or null
+    const float* g_mean_local;
+    const float* g_mean_incident;
+    const float* g_mean_global;
+    const float* g_pack;                         // optional grads of the pass-through columns (base|normal|roughness)
+    int g_row_stride, g_mean_vis_stride, g_mean_stride;
     const float* env_param;                      // raw parameter (learnable mode) for softplus'
     float* d_base_color; float* d_roughness; float* d_metallic; float* d_normals; float* d_viewdirs;
     float* d_radiance;                           // [N,Ns,3] or null
@@ -308,244 +377,288 @@ struct ShadeGrads {
     float* d_env;                                // [He,We,3] accumulated with atomics, or null
 };
 
-template <bool ENV_SMEM>
-__global__ void __launch_bounds__(SH_THREADS) shade_bwd_kernel(const ShadeArgs a, const ShadeGrads g, int env_mode) {
+#define VU_FLOATS 24  // per-vertex uniform block in shared memory (see shade_bwd_kernel)
+
+template <bool MET, bool ENV_SMEM>
+__global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs a, const ShadeGradsK g, int env_mode) {
     extern __shared__ __align__(16) float smem_b[];
+    constexpr int WPC = SHB_THREADS / 32;
     const int nenv = a.He * a.We * 3;
-    float* env_s = smem_b;                               // activated env (if it fits)
-    float* denv_s = ENV_SMEM ? smem_b + nenv : nullptr;  // per-CTA env gradient accumulator
+    float* vu_all = smem_b;                                         // [WPC][4][VU_FLOATS]
+    float* env_s = smem_b + WPC * 4 * VU_FLOATS;                    // activated env (if it fits)
+    float* denv_s = ENV_SMEM ? env_s + nenv : nullptr;              // per-CTA env gradient accumulator
     const float* env = a.env_act;
     if (ENV_SMEM) {
-        for (int i = threadIdx.x; i < nenv; i += SH_THREADS) { env_s[i] = a.env_act[i]; denv_s[i] = 0.f; }
+        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) { env_s[i] = a.env_act[i]; denv_s[i] = 0.f; }
         __syncthreads();
         env = env_s;
     }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int quad_base = lane & ~3, v = lane & 3;
-    const int n = (blockIdx.x * SH_THREADS + threadIdx.x) >> 2;
-    const bool valid = n < a.N;
-    const int nc = valid ? n : a.N - 1;
+    float* vu = vu_all + (threadIdx.x >> 5) * 4 * VU_FLOATS;
     const int Ns = a.Ns;
     const float inv = 1.f / (float)Ns;
-    VertexConst c;
-    load_vertex(a, nc, v, c);
-    const float met = a.metallic ? a.metallic[(size_t)nc * 4 + v] : 0.f;
+    const bool want_rad = g.d_radiance != nullptr;
 
-    // upstream gradients of the per-(surfel,vertex) sums
-    float gDg[3], gDl[3], gSAg[3], gSBg[3], gSAl[3], gSBl[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const size_t o = (size_t)nc * 12 + 4 * ch + v;
-        const float base = a.base_color[o];
-        const float fd = (1.f - met) * base / PI_F;
-        const float F0 = 0.04f * (1.f - met) + base * met;
-        const float Gp = (valid && g.g_pbr) ? g.g_pbr[o] : 0.f;
-        const float Gd = (valid && g.g_diffuse) ? g.g_diffuse[o] : 0.f;
-        const float Gs = (valid && g.g_specular) ? g.g_specular[o] : 0.f;
-        const float Gdi = (valid && g.g_direct) ? g.g_direct[o] : 0.f;
-        const float Gin = (valid && g.g_indirect) ? g.g_indirect[o] : 0.f;
-        gDg[ch] = (Gd + (Gp + Gdi) * fd) * inv;
-        gDl[ch] = (Gd + (Gp + Gin) * fd) * inv;
-        const float sg = (Gs + Gp + Gdi) * inv, sl = (Gs + Gp + Gin) * inv;
-        gSAg[ch] = F0 * sg; gSBg[ch] = (1.f - F0) * sg;
-        gSAl[ch] = F0 * sl; gSBl[ch] = (1.f - F0) * sl;
-    }
-    float gmv = 0.f, gml[3] = {0, 0, 0}, gmg[3] = {0, 0, 0};
-    if (valid) {
-        if (g.g_mean_vis) gmv = g.g_mean_vis[nc] * inv;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            float gi = g.g_mean_incident ? g.g_mean_incident[(size_t)nc * 3 + ch] : 0.f;
-            gml[ch] = ((g.g_mean_local ? g.g_mean_local[(size_t)nc * 3 + ch] : 0.f) + gi) * inv;
-            gmg[ch] = ((g.g_mean_global ? g.g_mean_global[(size_t)nc * 3 + ch] : 0.f) + gi) * inv;
+    for (int n = blockIdx.x * WPC + (threadIdx.x >> 5); n < a.N; n += gridDim.x * WPC) {
+        const float* vd = a.viewdirs + (size_t)n * 3;
+        const float inv_vlen = 1.f / fmaxf(sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]), 1e-12f);
+        const float Vx = vd[0] * inv_vlen, Vy = vd[1] * inv_vlen, Vz = vd[2] * inv_vlen;
+        // ---- per-vertex uniforms -> shared: [0..3] N,c | [4..7] a2,k,nom1,NoV | [8..10] gDg,[11] F0r |
+        //      [12..14] gDl,[15] F0g | [16..18] gSg,[19] F0b | [20..22] gSl,[23] -
+        __syncwarp();
+        if (lane < 4) {
+            VertexConst c;
+            vertex_consts(a, n, lane, Vx, Vy, Vz, c);
+            float* u = vu + lane * VU_FLOATS;
+            u[0] = c.Nx; u[1] = c.Ny; u[2] = c.Nz; u[3] = c.c;
+            u[4] = c.a2; u[5] = c.k; u[6] = c.nom1; u[7] = c.NoV;
         }
-    }
-
-    float dN[3] = {0, 0, 0};      // raw-normal gradient through n.w
-    float dNt[3] = {0, 0, 0};     // gradient w.r.t. N~ (normalised, flipped)
-    float dV[3] = {0, 0, 0};      // gradient w.r.t. normalised V
-    float d_a2 = 0.f, d_k = 0.f, d_nov = 0.f;
-    float Dl_sum[3] = {0, 0, 0}, Dg_sum[3] = {0, 0, 0};  // sum_s T (for d f_d)
-    float SA_g[3] = {0, 0, 0}, SB_g[3] = {0, 0, 0}, SA_l[3] = {0, 0, 0}, SB_l[3] = {0, 0, 0};  // for d F0 (metallic)
-    const bool has_met = a.metallic != nullptr;
-
-    for (int s0 = 0; s0 < Ns; s0 += 4) {
-        SampleShared mine;
-        float vis = 0.f, raw_env[3];
-        EnvTap tap;
-        const int s = s0 + v;
-        const bool sv = s < Ns;
-        const int sc = sv ? s : Ns - 1;
-        float Lg_s[3], Ll_s[3];
-        prepare_sample(a, env, nc, sc, c.Vx, c.Vy, c.Vz, mine, vis, raw_env, tap, Lg_s, Ll_s);
-        // per-sample gradient slots owned by this lane (its sample s): d(area*Lg), d(area*Ll)
-        float dLg_mine[3] = {0, 0, 0}, dLl_mine[3] = {0, 0, 0};
+        float met_l = 0.f, base_l = 0.f, Gp = 0.f, Gdi = 0.f, Gin = 0.f, Gs = 0.f;
+        if (lane < 12) {
+            const int v = lane & 3, ch = lane >> 2;
+            const size_t og = (size_t)n * g.g_row_stride + lane;
+            base_l = a.base_color[(size_t)n * 12 + lane];
+            met_l = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
+            const float fd = (1.f - met_l) * base_l / PI_F;
+            Gp = g.g_pbr ? g.g_pbr[og] : 0.f;
+            const float Gd = g.g_diffuse ? g.g_diffuse[og] : 0.f;
+            Gs = g.g_specular ? g.g_specular[og] : 0.f;
+            Gdi = g.g_direct ? g.g_direct[og] : 0.f;
+            Gin = g.g_indirect ? g.g_indirect[og] : 0.f;
+            float* u = vu + v * VU_FLOATS;
+            u[8 + ch] = (Gd + (Gp + Gdi) * fd) * inv;
+            u[12 + ch] = (Gd + (Gp + Gin) * fd) * inv;
+            u[16 + ch] = (Gs + Gp + Gdi) * inv;
+            u[20 + ch] = (Gs + Gp + Gin) * inv;
+            u[11 + 4 * ch] = MET ? 0.04f * (1.f - met_l) + base_l * met_l : 0.04f;
+        }
+        __syncwarp();
+        float gmv = 0.f, gml[3] = {0, 0, 0}, gmg[3] = {0, 0, 0};
+        {
+            const size_t om = (size_t)n * g.g_mean_stride;
+            if (g.g_mean_vis) gmv = g.g_mean_vis[(size_t)n * g.g_mean_vis_stride] * inv;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const SampleShared sh = quad_bcast(mine, quad_base + t);
-            float dlg[3] = {0, 0, 0}, dll[3] = {0, 0, 0};
-            if (s0 + t < Ns) {
-                VertexSample vs;
-                eval_vertex(c, sh, vs);
-                const float Lg[3] = {sh.gr, sh.gg, sh.gb}, Ll[3] = {sh.lr, sh.lg, sh.lb};
-                float d_ndi = 0.f, d_D = 0.f, d_p = 0.f;
+            for (int ch = 0; ch < 3; ch++) {
+                const float gi = g.g_mean_incident ? g.g_mean_incident[om + ch] : 0.f;
+                gml[ch] = ((g.g_mean_local ? g.g_mean_local[om + ch] : 0.f) + gi) * inv;
+                gmg[ch] = ((g.g_mean_global ? g.g_mean_global[om + ch] : 0.f) + gi) * inv;
+            }
+        }
+
+        // per-vertex partial sums of this lane: 0..2 dN, 3 d_c, 4 d_a2, 5 d_k, 6 d_nom1, 7..9 sum ndi*Ag,
+        // 10..12 sum ndi*Al, 13..15 dF0 (metallic only)
+        float acc[4][16];
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[v][i] = 0.f;
+        float dV[3] = {0, 0, 0};
+
+        for (int s0 = 0; s0 < Ns; s0 += 32) {
+            const int s = s0 + lane;
+            const bool ok = s < Ns;
+            const size_t is = (size_t)n * Ns + (ok ? s : Ns - 1);
+            Sample sm;
+            load_sample(a, env, is, ok, Vx, Vy, Vz, sm);
+            float dAg[3] = {0, 0, 0}, dAl[3] = {0, 0, 0}, dp_acc = 0.f, dhN[3] = {0, 0, 0};
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const float4 u0 = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS);
+                const float4 u1 = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS + 4);
+                const float4 uDg = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS + 8);
+                const float4 uDl = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS + 12);
+                const float4 uSg = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS + 16);
+                const float4 uSl = *reinterpret_cast<const float4*>(vu + v * VU_FLOATS + 20);
+                const float Nx = u0.x, Ny = u0.y, Nz = u0.z, cc = u0.w;
+                const float a2 = u1.x, k = u1.y, nom1 = u1.z, NoV = u1.w;
+                const float gDg[3] = {uDg.x, uDg.y, uDg.z}, gDl[3] = {uDl.x, uDl.y, uDl.z};
+                const float gSg[3] = {uSg.x, uSg.y, uSg.z}, gSl[3] = {uSl.x, uSl.y, uSl.z};
+                const float F0[3] = {uDg.w, uDl.w, uSg.w};
+
+                const float ndi_raw = Nx * sm.wx + Ny * sm.wy + Nz * sm.wz;
+                const float ndi = fmaxf(ndi_raw, 0.f);
+                const float nh = Nx * sm.hx + Ny * sm.hy + Nz * sm.hz;
+                const float nol_raw = cc * sm.il * ndi_raw, noh_raw = cc * nh;
+                const float NoL = fminf(fmaxf(nol_raw, 1e-6f), 1.f);
+                const float NoH = fminf(fmaxf(noh_raw, 1e-6f), 1.f);
+                const float nom0 = NoH * NoH * (a2 - 1.f) + 1.f;
+                const float nom2 = NoL * (1.f - k) + k;
+                const float n02 = nom0 * nom0;
+                const float nom_raw = 4.f * PI_F * n02 * nom1 * nom2;
+                const float nom = fminf(fmaxf(nom_raw, 1e-6f), 4.f * PI_F);
+                const float rn = __fdividef(1.f, nom);
+                const float Dt = a2 * rn;
+
+                float qD = 0.f, Fq = 0.f, Gq = 0.f;   // sum gD*A ; sum F[ch]*qs[ch] ; sum (1-F0[ch])*qs[ch]
+                float* ac = acc[v];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-                    const float tg = Lg[ch] * vs.ndi, tl = Ll[ch] * vs.ndi;
-                    Dg_sum[ch] += tg; Dl_sum[ch] += tl;
-                    if (has_met) {
-                        SA_g[ch] = fmaf(vs.Dterm, tg, SA_g[ch]); SB_g[ch] = fmaf(sh.p * vs.Dterm, tg, SB_g[ch]);
-                        SA_l[ch] = fmaf(vs.Dterm, tl, SA_l[ch]); SB_l[ch] = fmaf(sh.p * vs.Dterm, tl, SB_l[ch]);
-                    }
-                    const float gTg = gDg[ch] + vs.Dterm * (gSAg[ch] + sh.p * gSBg[ch]);
-                    const float gTl = gDl[ch] + vs.Dterm * (gSAl[ch] + sh.p * gSBl[ch]);
-                    dlg[ch] = gTg * vs.ndi;
-                    dll[ch] = gTl * vs.ndi;
-                    d_ndi += gTg * Lg[ch] + gTl * Ll[ch];
-                    d_D += tg * (gSAg[ch] + sh.p * gSBg[ch]) + tl * (gSAl[ch] + sh.p * gSBl[ch]);
-                    d_p += vs.Dterm * (tg * gSBg[ch] + tl * gSBl[ch]);
+                    const float F = F0[ch] + (1.f - F0[ch]) * sm.p;
+                    const float qs = gSg[ch] * sm.ag[ch] + gSl[ch] * sm.al[ch];
+                    qD = fmaf(gDg[ch], sm.ag[ch], fmaf(gDl[ch], sm.al[ch], qD));
+                    Fq = fmaf(F, qs, Fq);
+                    Gq = fmaf(1.f - F0[ch], qs, Gq);
+                    const float fsn = F * Dt * ndi;
+                    dAg[ch] += ndi * gDg[ch] + fsn * gSg[ch];
+                    dAl[ch] += ndi * gDl[ch] + fsn * gSl[ch];
+                    ac[7 + ch] = fmaf(ndi, sm.ag[ch], ac[7 + ch]);
+                    ac[10 + ch] = fmaf(ndi, sm.al[ch], ac[10 + ch]);
+                    if (MET) ac[13 + ch] = fmaf(ndi * Dt * (1.f - sm.p), qs, ac[13 + ch]);
                 }
-                // ndi = max(N.w, 0)
-                if (vs.ndi_raw >= 0.f) { dN[0] += d_ndi * sh.wx; dN[1] += d_ndi * sh.wy; dN[2] += d_ndi * sh.wz; }
-                // Dterm = a2 / clamp(nom_raw)
-                const bool nom_in = vs.nom_raw >= 1e-6f && vs.nom_raw <= 4.f * PI_F;
-                const float nom = fminf(fmaxf(vs.nom_raw, 1e-6f), 4.f * PI_F);
-                d_a2 += d_D / nom;
-                const float d_nom = nom_in ? -d_D * c.a2 / (nom * nom) : 0.f;
-                const float c4 = 4.f * PI_F * d_nom;
-                const float d_nom0 = c4 * 2.f * vs.nom0 * vs.nom1 * vs.nom2;
-                const float d_nom1 = c4 * vs.nom0 * vs.nom0 * vs.nom2;
-                const float d_nom2 = c4 * vs.nom0 * vs.nom0 * vs.nom1;
-                float d_noh = d_nom0 * 2.f * vs.NoH * (c.a2 - 1.f);
-                d_a2 += d_nom0 * vs.NoH * vs.NoH;
-                d_nov += d_nom1 * (1.f - c.k);
-                d_k += d_nom1 * (1.f - c.NoV) + d_nom2 * (1.f - vs.NoL);
-                float d_nol = d_nom2 * (1.f - c.k);
-                if (!(vs.noh_raw >= 1e-6f && vs.noh_raw <= 1.f)) d_noh = 0.f;
-                if (!(vs.nol_raw >= 1e-6f && vs.nol_raw <= 1.f)) d_nol = 0.f;
-                // p = 2^((a1 voh + a0) voh)
-                const float voh = fminf(fmaxf(sh.voh_raw, 1e-6f), 1.f);
-                float d_voh = d_p * sh.p * 0.6931471805599453f * (2.f * -5.55473f * voh - 6.98316f);
-                if (!(sh.voh_raw >= 1e-6f && sh.voh_raw <= 1.f)) d_voh = 0.f;
-                // N~.L , N~.H , V.H
-                dNt[0] += d_nol * sh.lx + d_noh * sh.hx;
-                dNt[1] += d_nol * sh.ly + d_noh * sh.hy;
-                dNt[2] += d_nol * sh.lz + d_noh * sh.hz;
-                float dH[3] = {d_noh * c.tx + d_voh * c.Vx, d_noh * c.ty + d_voh * c.Vy, d_noh * c.tz + d_voh * c.Vz};
-                dV[0] += d_voh * sh.hx; dV[1] += d_voh * sh.hy; dV[2] += d_voh * sh.hz;
-                // H = h/|h|, h = (L + V)/2
-                const float hd = sh.hx * dH[0] + sh.hy * dH[1] + sh.hz * dH[2];
-                const float ih = 0.5f / sh.hlen;
-                dV[0] += (dH[0] - sh.hx * hd) * ih;
-                dV[1] += (dH[1] - sh.hy * hd) * ih;
-                dV[2] += (dH[2] - sh.hz * hd) * ih;
+                const float d_ndi = qD + Dt * Fq;
+                const float d_Dt = ndi * Fq;
+                dp_acc = fmaf(ndi * Dt, Gq, dp_acc);
+                // Dt = a2 / clamp(nom_raw)
+                const bool nom_in = nom_raw >= 1e-6f && nom_raw <= 4.f * PI_F;
+                float d_a2 = d_Dt * rn;
+                const float c4 = nom_in ? -4.f * PI_F * d_Dt * Dt * rn : 0.f;
+                const float d_nom0 = c4 * 2.f * nom0 * nom1 * nom2;
+                const float g1 = c4 * n02 * nom2;
+                const float d_nom2 = c4 * n02 * nom1;
+                const bool noh_in = noh_raw >= 1e-6f && noh_raw <= 1.f;
+                const bool nol_in = nol_raw >= 1e-6f && nol_raw <= 1.f;
+                const float d_noh = noh_in ? d_nom0 * 2.f * NoH * (a2 - 1.f) : 0.f;
+                d_a2 = fmaf(d_nom0, NoH * NoH, d_a2);
+                const float d_nol = nol_in ? d_nom2 * (1.f - k) : 0.f;
+                const float g_ndi_raw = (ndi_raw >= 0.f ? d_ndi : 0.f) + d_nol * cc * sm.il;
+                const float g_nh = d_noh * cc;
+                ac[0] += g_ndi_raw * sm.wx + g_nh * sm.hx;
+                ac[1] += g_ndi_raw * sm.wy + g_nh * sm.hy;
+                ac[2] += g_ndi_raw * sm.wz + g_nh * sm.hz;
+                ac[3] += d_nol * sm.il * ndi_raw + d_noh * nh;
+                ac[4] += d_a2;
+                ac[5] += g1 * (1.f - NoV) + d_nom2 * (1.f - NoL);
+                ac[6] += g1;
+                dhN[0] = fmaf(g_nh, Nx, dhN[0]);
+                dhN[1] = fmaf(g_nh, Ny, dhN[1]);
+                dhN[2] = fmaf(g_nh, Nz, dhN[2]);
             }
-            // sum the 4 vertices' contributions to this sample's light gradients; owner lane keeps them
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                float x = dlg[ch], y = dll[ch];
-                x += __shfl_xor_sync(full, x, 1); x += __shfl_xor_sync(full, x, 2);
-                y += __shfl_xor_sync(full, y, 1); y += __shfl_xor_sync(full, y, 2);
-                if (t == v) { dLg_mine[ch] = x; dLl_mine[ch] = y; }
+            // ---- per-sample tail: V.H and H -> view direction; light gradients ------------------
+            {
+                const float voh = fminf(fmaxf(sm.voh_raw, 1e-6f), 1.f);
+                const bool voh_in = sm.voh_raw >= 1e-6f && sm.voh_raw <= 1.f;
+                const float d_voh = voh_in ? dp_acc * sm.p * 0.6931471805599453f * (2.f * -5.55473f * voh - 6.98316f) : 0.f;
+                const float dH[3] = {dhN[0] + d_voh * Vx, dhN[1] + d_voh * Vy, dhN[2] + d_voh * Vz};
+                const float hd = sm.hx * dH[0] + sm.hy * dH[1] + sm.hz * dH[2];
+                const float ih = 0.5f / sm.hlen;
+                dV[0] += d_voh * sm.hx + (dH[0] - sm.hx * hd) * ih;
+                dV[1] += d_voh * sm.hy + (dH[1] - sm.hy * hd) * ih;
+                dV[2] += d_voh * sm.hz + (dH[2] - sm.hz * hd) * ih;
             }
-        }
-        if (sv && valid) {
-            const size_t is = (size_t)nc * Ns + s;
-            const float area = a.areas[is];
-            if (g.d_radiance) {
+            if (ok) {
+                if (want_rad) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) g.d_radiance[is * 3 + ch] = dLl_mine[ch] * area + gml[ch];
-            }
-            // Lg = clamp(env_scale*raw,0,64)*vis
-            float dvis = gmv, draw[3];
+                    for (int ch = 0; ch < 3; ch++) g.d_radiance[is * 3 + ch] = dAl[ch] * sm.area + gml[ch];
+                }
+                float dvis = gmv, draw[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float x = raw_env[ch] * a.env_scale;
-                const float cl = fminf(fmaxf(x, 0.f), 64.f);
-                const float dLg = dLg_mine[ch] * area + gmg[ch];
-                dvis += dLg * cl;
-                draw[ch] = (x >= 0.f && x <= 64.f) ? dLg * vis * a.env_scale : 0.f;
-            }
-            if (g.d_visibility) g.d_visibility[is] = dvis;
-            if (g.d_env) {
-                const float wx0 = 1.f - tap.wx1, wy0 = 1.f - tap.wy1;
+                for (int ch = 0; ch < 3; ch++) {
+                    const float x = sm.raw[ch] * a.env_scale;
+                    const float dLg = dAg[ch] * sm.area + gmg[ch];
+                    dvis = fmaf(dLg, sm.lg[ch], dvis);
+                    draw[ch] = (x >= 0.f && x <= 64.f) ? dLg * sm.vis * a.env_scale : 0.f;
+                }
+                if (g.d_visibility) g.d_visibility[is] = dvis;
+                if (g.d_env) {
+                    const float wx0 = 1.f - sm.tap.wx1, wy0 = 1.f - sm.tap.wy1;
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const int x = tap.x0 + (kk & 1), y = tap.y0 + (kk >> 1);
-                    if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
-                    const float w = ((kk & 1) ? tap.wx1 : wx0) * ((kk >> 1) ? tap.wy1 : wy0);
-                    const int base_i = (y * a.We + x) * 3;
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int x = sm.tap.x0 + (kk & 1), y = sm.tap.y0 + (kk >> 1);
+                        if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
+                        const float w = ((kk & 1) ? sm.tap.wx1 : wx0) * ((kk >> 1) ? sm.tap.wy1 : wy0);
+                        const int base_i = (y * a.We + x) * 3;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float val = draw[ch] * w;
-                        if (val != 0.f) {
-                            if (ENV_SMEM) atomicAdd(&denv_s[base_i + ch], val);
-                            else atomicAdd(&g.d_env[base_i + ch], env_mode == 0 ? val / (1.f + expf(-g.env_param[base_i + ch])) : val);
+                        for (int ch = 0; ch < 3; ch++) {
+                            const float val = draw[ch] * w;
+                            if (val != 0.f) {
+                                if (ENV_SMEM) atomicAdd(&denv_s[base_i + ch], val);
+                                else atomicAdd(&g.d_env[base_i + ch], env_mode == 0 ? val / (1.f + expf(-g.env_param[base_i + ch])) : val);
+                            }
                         }
                     }
                 }
             }
         }
-    }
 
-    if (valid) {
-        // roughness: a2 = r^4, k = (r^2 + 2r + 1)/8
-        g.d_roughness[(size_t)n * 4 + v] = d_a2 * 4.f * c.r * c.r * c.r + d_k * (2.f * c.r + 2.f) / 8.0f;
-        // base colour / metallic through f_d = (1-m) base/pi
-        float dm = 0.f;
+        // ---- per-vertex epilogue --------------------------------------------------------------------
+        // after the reduction slot i lives on lanes 2i, 2i+1
+        float dVu[3] = {0, 0, 0};   // uniform (vertex-level) view-direction terms, added once below
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const size_t o = (size_t)n * 12 + 4 * ch + v;
-            const float base = a.base_color[o];
-            const float Gp = g.g_pbr ? g.g_pbr[o] : 0.f;
-            const float Gs = g.g_specular ? g.g_specular[o] : 0.f;
-            const float Gdi = g.g_direct ? g.g_direct[o] : 0.f;
-            const float Gin = g.g_indirect ? g.g_indirect[o] : 0.f;
-            const float dgm = Dg_sum[ch] * inv, dlm = Dl_sum[ch] * inv;
-            const float dfd = Gp * (dgm + dlm) + Gdi * dgm + Gin * dlm;
-            float db = dfd * (1.f - met) / PI_F;
-            dm += dfd * (-base / PI_F);
-            if (has_met) {  // F0 = 0.04(1-m) + base*m
-                const float dF0 = ((Gs + Gp) * ((SA_g[ch] + SA_l[ch]) - (SB_g[ch] + SB_l[ch])) +
-                                   Gdi * (SA_g[ch] - SB_g[ch]) + Gin * (SA_l[ch] - SB_l[ch])) * inv;
-                db += dF0 * met;
-                dm += dF0 * (base - 0.04f);
+        for (int v = 0; v < 4; v++) {
+            const float tot = warp_reduce_slots<16>(acc[v], lane);
+            const float* u = vu + v * VU_FLOATS;
+            const float Nx = u[0], Ny = u[1], Nz = u[2], cc = u[3];
+            const float k = u[5], NoVc = u[7];
+            const float d_c = __shfl_sync(full, tot, 6), d_a2 = __shfl_sync(full, tot, 8);
+            const float d_k = __shfl_sync(full, tot, 10), d_nom1 = __shfl_sync(full, tot, 12);
+            // recompute the un-clamped N~.V and |N| (uniform)
+            const float nvr = (Nx * Vx + Ny * Vy + Nz * Vz);
+            const float nv_raw = nvr * cc;
+            const float d_nov = (nv_raw >= 1e-6f && nv_raw <= 1.f) ? d_nom1 * (1.f - k) : 0.f;
+            (void)NoVc;
+            const float nl2 = fmaxf(Nx * Nx + Ny * Ny + Nz * Nz, 1e-24f);
+            const float d_c_tot = d_c + d_nov * nvr;
+            dVu[0] += d_nov * cc * Nx; dVu[1] += d_nov * cc * Ny; dVu[2] += d_nov * cc * Nz;
+            const float rgh = a.roughness[(size_t)n * 4 + v];
+            if ((lane & 1) == 0) {
+                const int slot = lane >> 1;
+                if (slot < 3) {
+                    const float Nk = slot == 0 ? Nx : (slot == 1 ? Ny : Nz);
+                    const float Vk = slot == 0 ? Vx : (slot == 1 ? Vy : Vz);
+                    // c = sgn/|N|  ->  dc/dN = -c N/|N|^2
+                    float val = tot + d_nov * cc * Vk - d_c_tot * cc * Nk / nl2;
+                    if (g.g_pack) {  // packed view-space normals: n_view[v][j] = sum_i N[v][i] R[i][j]
+                        const float* gp = g.g_pack + (size_t)n * g.g_row_stride + 12;
+                        val += gp[v] * a.view3x3[3 * slot] + gp[4 + v] * a.view3x3[3 * slot + 1] + gp[8 + v] * a.view3x3[3 * slot + 2];
+                    }
+                    g.d_normals[((size_t)n * 4 + v) * 3 + slot] = val;
+                } else if (slot == 4) {
+                    float val = d_a2 * 4.f * rgh * rgh * rgh + d_k * (2.f * rgh + 2.f) / 8.0f;
+                    if (g.g_pack) val += g.g_pack[(size_t)n * g.g_row_stride + 24 + v];
+                    g.d_roughness[(size_t)n * 4 + v] = val;
+                }
             }
-            g.d_base_color[o] = db;
+            // base colour / metallic: lanes 14,16,18 hold sum ndi*Ag per channel; 20,22,24 the Al sums; 26,28,30 dF0
+            const float sumL = __shfl_down_sync(full, tot, 6);
+            const float dF0 = __shfl_down_sync(full, tot, 12);
+            float dm = 0.f;
+            if (lane >= 14 && lane < 20 && (lane & 1) == 0) {
+                const int ch = (lane - 14) >> 1;
+                const size_t o12 = (size_t)n * 12 + 4 * ch + v;
+                const size_t og = (size_t)n * g.g_row_stride + 4 * ch + v;
+                const float base = a.base_color[o12];
+                const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
+                const float gp = g.g_pbr ? g.g_pbr[og] : 0.f;
+                const float gdi = g.g_direct ? g.g_direct[og] : 0.f;
+                const float gin = g.g_indirect ? g.g_indirect[og] : 0.f;
+                const float dgm = tot * inv, dlm = sumL * inv;
+                const float dfd = gp * (dgm + dlm) + gdi * dgm + gin * dlm;
+                float db = dfd * (1.f - met) / PI_F;
+                dm = dfd * (-base / PI_F);
+                if (MET) { db += dF0 * met; dm += dF0 * (base - 0.04f); }
+                if (g.g_pack) db += g.g_pack[og];
+                g.d_base_color[o12] = db;
+            }
+            if (MET && g.d_metallic) {  // uniform branch: all lanes shuffle
+                const float t = __shfl_sync(full, dm, 14) + __shfl_sync(full, dm, 16) + __shfl_sync(full, dm, 18);
+                if (lane == 0) g.d_metallic[(size_t)n * 4 + v] = t;
+            }
         }
-        if (g.d_metallic) g.d_metallic[(size_t)n * 4 + v] = dm;
-        // NoV = clamp(N~.V): contributes to N~ and V
-        if (!(c.nov_raw >= 1e-6f && c.nov_raw <= 1.f)) d_nov = 0.f;
-        dNt[0] += d_nov * c.Vx; dNt[1] += d_nov * c.Vy; dNt[2] += d_nov * c.Vz;
-        dV[0] += d_nov * c.tx; dV[1] += d_nov * c.ty; dV[2] += d_nov * c.tz;
-        // N~ = sgn * N/|N|
-        const float hx = c.tx * c.sgn, hy = c.ty * c.sgn, hz = c.tz * c.sgn;  // N^ (sgn^2 = 1 unless 0)
-        const float dh[3] = {dNt[0] * c.sgn, dNt[1] * c.sgn, dNt[2] * c.sgn};
-        const float nd = hx * dh[0] + hy * dh[1] + hz * dh[2];
-        float* dn = g.d_normals + ((size_t)n * 4 + v) * 3;
-        dn[0] = dN[0] + (dh[0] - hx * nd) * c.inv_nlen;
-        dn[1] = dN[1] + (dh[1] - hy * nd) * c.inv_nlen;
-        dn[2] = dN[2] + (dh[2] - hz * nd) * c.inv_nlen;
-    } else {
-        dV[0] = dV[1] = dV[2] = 0.f;
-    }
-    // view direction: sum over the 4 vertices, then through the normalisation
+        // view direction: per-sample terms summed over the warp + the uniform N~.V terms, then normalisation
 #pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        dV[ch] += __shfl_xor_sync(full, dV[ch], 1);
-        dV[ch] += __shfl_xor_sync(full, dV[ch], 2);
-    }
-    if (valid && v == 0) {
-        const float vd = c.Vx * dV[0] + c.Vy * dV[1] + c.Vz * dV[2];
-        float* o = g.d_viewdirs + (size_t)n * 3;
-        o[0] = (dV[0] - c.Vx * vd) * c.inv_vlen;
-        o[1] = (dV[1] - c.Vy * vd) * c.inv_vlen;
-        o[2] = (dV[2] - c.Vz * vd) * c.inv_vlen;
+        for (int ch = 0; ch < 3; ch++) dV[ch] = warp_sum(dV[ch]) + dVu[ch];
+        if (lane == 0) {
+            const float vdot = Vx * dV[0] + Vy * dV[1] + Vz * dV[2];
+            float* o = g.d_viewdirs + (size_t)n * 3;
+            o[0] = (dV[0] - Vx * vdot) * inv_vlen;
+            o[1] = (dV[1] - Vy * vdot) * inv_vlen;
+            o[2] = (dV[2] - Vz * vdot) * inv_vlen;
+        }
     }
     if (ENV_SMEM && g.d_env) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nenv; i += SH_THREADS) {
+        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) {
             float val = denv_s[i];
             if (val != 0.f) {
                 if (env_mode == 0) val = val / (1.f + expf(-g.env_param[i]));  // softplus'
@@ -612,6 +725,41 @@ __global__ void __launch_bounds__(256) direct_light_bwd_kernel(int n, int He, in
 
 using namespace svgir;
 
+// persistent grid: enough CTAs to fill the 148 SMs a few times over, never more than the work
+static int shade_grid(int N, int threads, int ctas_per_sm) {
+    const int wpc = threads / 32;
+    const int need = (N + wpc - 1) / wpc;
+    return need < 148 * ctas_per_sm ? need : 148 * ctas_per_sm;
+}
+
+template <bool SPLIT, bool MET>
+static void launch_shade_fwd(const ShadeArgs& a, const ShadeOutK& so, cudaStream_t s) {
+    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
+    const int grid = shade_grid(a.N, SH_THREADS, 2);
+    if (env_bytes <= 96 * 1024) {
+        if (env_bytes > 48 * 1024)
+            cudaFuncSetAttribute(shade_fwd_kernel<SPLIT, MET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_bytes);
+        shade_fwd_kernel<SPLIT, MET, true><<<grid, SH_THREADS, env_bytes, s>>>(a, so);
+    } else {
+        shade_fwd_kernel<SPLIT, MET, false><<<grid, SH_THREADS, 0, s>>>(a, so);
+    }
+}
+
+template <bool MET>
+static void launch_shade_bwd(const ShadeArgs& a, const ShadeGradsK& g, int env_mode, cudaStream_t s) {
+    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
+    const size_t vu_bytes = (size_t)(SHB_THREADS / 32) * 4 * VU_FLOATS * sizeof(float);
+    const int grid = shade_grid(a.N, SHB_THREADS, 3);
+    if (2 * env_bytes + vu_bytes <= 96 * 1024) {
+        const size_t smem = 2 * env_bytes + vu_bytes;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(shade_bwd_kernel<MET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        shade_bwd_kernel<MET, true><<<grid, SHB_THREADS, smem, s>>>(a, g, env_mode);
+    } else {
+        shade_bwd_kernel<MET, false><<<grid, SHB_THREADS, vu_bytes, s>>>(a, g, env_mode);
+    }
+}
+
 extern "C" {
 
 static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, ShadeArgs& a, cudaStream_t s) {
@@ -625,7 +773,7 @@ static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, Sha
     { TimedScope ts_("env_activate", s); env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, in->env, in->env_act_scratch, c->env_mode); }
     a.N = c->N; a.Ns = c->Ns; a.He = c->env_h; a.We = c->env_w;
     a.env_scale = c->env_mode == 0 ? 2.0f : 1.0f;
-    a.env_act = in->env_act_scratch; a.transform = in->env_transform;
+    a.env_act = in->env_act_scratch; a.transform = in->env_transform; a.view3x3 = in->view3x3;
     a.base_color = in->base_color; a.roughness = in->roughness; a.metallic = in->metallic;
     a.normals = in->normals; a.viewdirs = in->viewdirs; a.radiance = in->radiance;
     a.visibility = in->visibility; a.dirs = in->incident_dirs; a.areas = in->incident_areas;
@@ -637,18 +785,19 @@ int svgir_shade_forward(const svgir_shade_cfg* c, const svgir_shade_in* in, cons
     ShadeArgs a;
     int rc = shade_prepare(c, in, a, s);
     if (rc) return rc;
-    if (!o || !o->pbr || !o->diffuse_light || !o->specular || !o->direct || !o->indirect) { set_error("shade: missing output"); return SVGIR_ERR_INVALID; }
+    if (!o || !(o->pbr || o->diffuse_light || o->specular || o->direct || o->indirect)) { set_error("shade: no output requested"); return SVGIR_ERR_INVALID; }
+    if (o->pack && !in->view3x3) { set_error("shade: packed pass-through columns need view3x3"); return SVGIR_ERR_INVALID; }
     if (c->N == 0) return SVGIR_OK;
-    ShadeOut so{o->pbr, o->diffuse_light, o->specular, o->direct, o->indirect, o->mean_visibility,
-                o->mean_local, o->mean_incident, o->mean_global};
-    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
-    const int grid = (int)(((size_t)c->N * 4 + SH_THREADS - 1) / SH_THREADS);
-    if (env_bytes <= 96 * 1024) {
-        if (env_bytes > 48 * 1024)
-            cudaFuncSetAttribute(shade_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_bytes);
-        { TimedScope ts_("shade_fwd", s); shade_fwd_kernel<true><<<grid, SH_THREADS, env_bytes, s>>>(a, so); }
-    } else {
-        { TimedScope ts_("shade_fwd", s); shade_fwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, so); }
+    ShadeOutK so{o->pbr, o->diffuse_light, o->specular, o->direct, o->indirect, o->mean_visibility,
+                 o->mean_local, o->mean_incident, o->mean_global, o->pack,
+                 o->row_stride > 0 ? o->row_stride : 12, o->mean_vis_stride > 0 ? o->mean_vis_stride : 1,
+                 o->mean_stride > 0 ? o->mean_stride : 3};
+    const bool split = o->direct || o->indirect;
+    const bool met = in->metallic != nullptr;
+    {
+        TimedScope ts_("shade_fwd", s);
+        if (split) { if (met) launch_shade_fwd<true, true>(a, so, s); else launch_shade_fwd<true, false>(a, so, s); }
+        else { if (met) launch_shade_fwd<false, true>(a, so, s); else launch_shade_fwd<false, false>(a, so, s); }
     }
     return check_launch("shade_forward", c->debug, s);
 }
@@ -659,19 +808,17 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
     int rc = shade_prepare(c, in, a, s);
     if (rc) return rc;
     if (!gr || !gr->d_base_color || !gr->d_roughness || !gr->d_normals || !gr->d_viewdirs) { set_error("shade_backward: missing buffers"); return SVGIR_ERR_INVALID; }
+    if (gr->g_pack && !in->view3x3) { set_error("shade_backward: packed pass-through columns need view3x3"); return SVGIR_ERR_INVALID; }
     if (c->N == 0) return SVGIR_OK;
-    ShadeGrads g{gr->g_pbr, gr->g_diffuse_light, gr->g_specular, gr->g_direct, gr->g_indirect, gr->g_mean_visibility,
-                 gr->g_mean_local, gr->g_mean_incident, gr->g_mean_global, in->env,
-                 gr->d_base_color, gr->d_roughness, gr->d_metallic, gr->d_normals, gr->d_viewdirs,
-                 gr->d_radiance, gr->d_visibility, gr->d_env};
-    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
-    const int grid = (int)(((size_t)c->N * 4 + SH_THREADS - 1) / SH_THREADS);
-    if (2 * env_bytes <= 96 * 1024) {
-        if (2 * env_bytes > 48 * 1024)
-            cudaFuncSetAttribute(shade_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * env_bytes));
-        { TimedScope ts_("shade_bwd", s); shade_bwd_kernel<true><<<grid, SH_THREADS, 2 * env_bytes, s>>>(a, g, c->env_mode); }
-    } else {
-        { TimedScope ts_("shade_bwd", s); shade_bwd_kernel<false><<<grid, SH_THREADS, 0, s>>>(a, g, c->env_mode); }
+    ShadeGradsK g{gr->g_pbr, gr->g_diffuse_light, gr->g_specular, gr->g_direct, gr->g_indirect, gr->g_mean_visibility,
+                  gr->g_mean_local, gr->g_mean_incident, gr->g_mean_global, gr->g_pack,
+                  gr->g_row_stride > 0 ? gr->g_row_stride : 12, gr->g_mean_vis_stride > 0 ? gr->g_mean_vis_stride : 1,
+                  gr->g_mean_stride > 0 ? gr->g_mean_stride : 3, in->env,
+                  gr->d_base_color, gr->d_roughness, gr->d_metallic, gr->d_normals, gr->d_viewdirs,
+                  gr->d_radiance, gr->d_visibility, gr->d_env};
+    {
+        TimedScope ts_("shade_bwd", s);
+        if (in->metallic) launch_shade_bwd<true>(a, g, c->env_mode, s); else launch_shade_bwd<false>(a, g, c->env_mode, s);
     }
     return check_launch("shade_backward", c->debug, s);
 }

@@ -97,19 +97,10 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
 
     viewdirs = torch.nn.functional.normalize(cam.camera_center - means3D, dim=-1)
-    normal = pc.shading_normal if is_training else pc.shading_normal.detach()  # svgss.py:127
-    sh = shading.shade_surfels(pc.base_color, pc.roughness, normal, viewdirs, pc.radiance, env_light,
-                               pc.visibility, pc.incident_dirs, pc.incident_areas, debug=debug)
-    if is_training:  # svgss.py:148-166
-        features = torch.cat([sh["mean_visibility"], sh["mean_local_lights"]], dim=-1)
-    else:
-        features = torch.cat([sh["mean_incident_lights"], sh["mean_local_lights"], sh["mean_visibility"]], dim=-1)
-    nview = pc.shading_normal @ cam.world_view_transform[:3, :3]
-    nview = nview.transpose(1, 2).reshape(nview.shape[0], -1)
-    if is_training:
-        vfeatures = torch.cat([sh["pbr"], pc.base_color, nview, pc.roughness, sh["diffuse_light"]], dim=-1)
-    else:
-        vfeatures = torch.cat([sh["pbr"], pc.base_color, nview, pc.roughness, sh["direct"], sh["indirect"]], dim=-1)
+    # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel
+    features, vfeatures = shading.shade_and_pack(
+        pc.base_color, pc.roughness, pc.shading_normal, viewdirs, pc.radiance, env_light, pc.visibility,
+        pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug)
 
     (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
      rendered_vfeature, weights, radii) = rasterizer(
@@ -141,7 +132,7 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
         "base_color": opacity_filter(rgb_to_srgb(base)), "roughness": opacity_filter(rough),
         "local_lights": opacity_filter(rgb_to_srgb(local)), "visibility": opacity_filter(vis),
         "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
-        "num_rendered": num_rendered, "weights": weights, "diffuse_light": sh["diffuse_light"]})
+        "num_rendered": num_rendered, "weights": weights, "diffuse_light": vfeatures[:, 40:52] if is_training else None})
     return res
 
 

@@ -32,19 +32,21 @@ class ShadeCfg(C.Structure):
 class ShadeIn(C.Structure):
     _fields_ = [(n, c_fp) for n in ("base_color", "roughness", "metallic", "normals", "viewdirs", "radiance",
                                     "visibility", "incident_dirs", "incident_areas", "env", "env_transform",
-                                    "env_act_scratch")]
+                                    "env_act_scratch", "view3x3")]
 
 
 class ShadeOut(C.Structure):
     _fields_ = [(n, c_fp) for n in ("pbr", "diffuse_light", "specular", "direct", "indirect",
-                                    "mean_visibility", "mean_local", "mean_incident", "mean_global")]
+                                    "mean_visibility", "mean_local", "mean_incident", "mean_global", "pack")] + \
+               [(n, C.c_int32) for n in ("row_stride", "mean_vis_stride", "mean_stride", "reserved_")]
 
 
 class ShadeGrads(C.Structure):
     _fields_ = [(n, c_fp) for n in ("g_pbr", "g_diffuse_light", "g_specular", "g_direct", "g_indirect",
                                     "g_mean_visibility", "g_mean_local", "g_mean_incident", "g_mean_global",
                                     "d_base_color", "d_roughness", "d_metallic", "d_normals", "d_viewdirs",
-                                    "d_radiance", "d_visibility", "d_env")]
+                                    "d_radiance", "d_visibility", "d_env", "g_pack")] + \
+               [(n, C.c_int32) for n in ("g_row_stride", "g_mean_vis_stride", "g_mean_stride", "reserved_")]
 
 
 _bound = False
@@ -126,8 +128,8 @@ class _ShadeFn(torch.autograd.Function):
         cfg = ShadeCfg(N, Ns, He, We, int(env_mode), int(bool(debug)))
         cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
-                      _p(t["env"]), _p(t["transform"]), _p(scratch))
-        cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg))
+                      _p(t["env"]), _p(t["transform"]), _p(scratch), None)
+        cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg), None, 0, 0, 0, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
@@ -162,9 +164,9 @@ class _ShadeFn(torch.autograd.Function):
         gs = [_c(x) for x in (g_pbr, g_diff, g_spec, g_dir, g_ind, g_mv, g_ml, g_mi, g_mg)]
         cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
         cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
-                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch))
+                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), None)
         cg = ShadeGrads(*[_p(x) for x in gs], _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad),
-                        _p(d_vis), _p(d_env))
+                        _p(d_vis), _p(d_env), None, 0, 0, 0, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
@@ -185,6 +187,103 @@ def shade_surfels(base_color, roughness, normals, viewdirs, radiance, env_light,
     keys = ("pbr", "diffuse_light", "specular", "direct", "indirect", "mean_visibility", "mean_local_lights",
             "mean_incident_lights", "mean_global_lights")
     return dict(zip(keys, o))
+
+
+class _ShadePackedFn(torch.autograd.Function):
+    """Shading fused with render_view's packing (gaussian_renderer/svgss.py:141-166): the kernel writes
+    `features` [N,S] and `vfeatures` [N,VS] in the rasteriser's layout directly -- train: S=4
+    [mean visibility, mean local light], VS=52 [pbr, base colour, view-space normal, roughness, diffuse
+    light]; eval: S=7 [mean light, mean local light, mean visibility], VS=64 [.., direct, indirect] --
+    and the backward kernel consumes their gradients with row strides, so no torch cat / split / matmul
+    runs on the [N,*] tensors."""
+
+    @staticmethod
+    def forward(ctx, base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
+                incident_areas, env, metallic, view3x3, env_mode, transform, is_training, debug):
+        if not base_color.is_cuda:
+            raise RuntimeError("svgir_b200 shading needs CUDA tensors (no CPU fallback)")
+        L = _L()
+        dev = base_color.device
+        N, Ns = incident_dirs.shape[0], incident_dirs.shape[1]
+        t = dict(base_color=_c(base_color), roughness=_c(roughness), normals=_c(normals), viewdirs=_c(viewdirs),
+                 radiance=_c(radiance), visibility=_c(visibility), incident_dirs=_c(incident_dirs),
+                 incident_areas=_c(incident_areas), env=_c(env), metallic=_c(metallic), transform=_c(transform),
+                 view3x3=_c(view3x3))
+        He, We = t["env"].shape[0], t["env"].shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        S, VS = (4, 52) if is_training else (7, 64)
+        feats = torch.empty((N, S), **f32)
+        vfeats = torch.empty((N, VS), **f32)
+        scratch = torch.empty((He, We, 3), **f32)
+        cfg = ShadeCfg(N, Ns, He, We, int(env_mode), int(bool(debug)))
+        cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
+                      _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
+                      _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]))
+        vp, fp = vfeats.data_ptr(), feats.data_ptr()
+        if is_training:
+            cout = ShadeOut(vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None, vp + 4 * 12, VS, S, S, 0)
+        else:
+            cout = ShadeOut(vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None, vp + 4 * 12,
+                            VS, S, S, 0)
+        if N > 0:
+            with torch.cuda.device(dev):
+                _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
+        ctx.cfg = (N, Ns, He, We, int(env_mode), int(bool(debug)), bool(is_training))
+        ctx.has = (metallic is not None, transform is not None)
+        ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
+                                            t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
+                                            t["view3x3"], t["metallic"], t["transform"]) if x is not None])
+        return feats, vfeats
+
+    @staticmethod
+    def backward(ctx, g_feats, g_vfeats):
+        L = _L()
+        saved = list(ctx.saved_tensors)
+        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env, view3x3 = saved[:10]
+        rest = saved[10:]
+        metallic = rest.pop(0) if ctx.has[0] else None
+        transform = rest.pop(0) if ctx.has[1] else None
+        N, Ns, He, We, env_mode, debug, is_training = ctx.cfg
+        dev = base_color.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad
+        S, VS = (4, 52) if is_training else (7, 64)
+        g_feats = _c(g_feats) if g_feats is not None else torch.zeros((N, S), **f32)
+        g_vfeats = _c(g_vfeats) if g_vfeats is not None else torch.zeros((N, VS), **f32)
+        d_base = torch.empty((N, 12), **f32)
+        d_rough = torch.empty((N, 4), **f32)
+        d_norm = torch.empty((N, 4, 3), **f32)
+        d_view = torch.empty((N, 3), **f32)
+        d_rad = torch.empty((N, Ns, 3), **f32) if need[4] else None
+        d_vis = torch.empty(tuple(visibility.shape), **f32) if need[5] else None
+        d_env = torch.zeros((He, We, 3), **f32) if need[8] else None
+        d_met = torch.empty((N, 4), **f32) if (metallic is not None and need[9]) else None
+        scratch = torch.empty((He, We, 3), **f32)
+        cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
+        cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
+                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), _p(view3x3))
+        vp, fp = g_vfeats.data_ptr(), g_feats.data_ptr()
+        if is_training:
+            gin = (vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None)
+        else:
+            gin = (vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None)
+        cg = ShadeGrads(*gin, _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad), _p(d_vis),
+                        _p(d_env), vp + 4 * 12, VS, S, S, 0)
+        if N > 0:
+            with torch.cuda.device(dev):
+                _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
+        if need[6] or need[7]:
+            raise NotImplementedError("svgir_b200 shading: no gradients w.r.t. incident_dirs / incident_areas")
+        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None, None, None)
+
+
+def shade_and_pack(base_color, roughness, normals, viewdirs, radiance, env_light, visibility, incident_dirs,
+                   incident_areas, view3x3, is_training=True, metallic=None, debug=False):
+    """(features [N,S], vfeatures [N,VS]) exactly as render_view packs them (svgss.py:141-166), computed by
+    one fused kernel. view3x3 = world_view_transform[:3,:3]."""
+    env, mode, tr = env_of(env_light)
+    return _ShadePackedFn.apply(base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
+                                incident_areas, env, metallic, view3x3, mode, tr, bool(is_training), debug)
 
 
 class _DirectLightFn(torch.autograd.Function):

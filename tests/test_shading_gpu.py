@@ -122,3 +122,44 @@ def test_shade_metallic_against_restatement():
                               (tc["env_param"], shading.MODE_LEARNABLE), tc["visibility"], tc["incident_dirs"],
                               tc["incident_areas"], metallic=met.cuda())
     np.testing.assert_allclose(r["pbr"].cpu().numpy(), pbr.numpy(), rtol=5e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("is_training", [True, False])
+def test_shade_and_pack_matches_torch_packing(is_training):
+    """Fused shading + render_view packing (svgss.py:141-166) against the un-fused kernel followed by the
+    reference's torch cat / matmul packing, values and gradients."""
+    from svgir_b200 import shading
+    g = dict(np.load(os.path.join(GOLD, "ref_shading_train_small.npz")))
+    names = ("base_color", "roughness", "shading_normals", "viewdirs", "env_param")
+    view = torch.tensor(g["in_view3x3"]).cuda()
+
+    def inputs():
+        t = {k[3:]: torch.tensor(v).cuda() for k, v in g.items() if k.startswith("in_")}
+        for k in names:
+            t[k].requires_grad_(True)
+        return t
+
+    t = inputs()
+    r = shading.shade_surfels(t["base_color"], t["roughness"], t["shading_normals"], t["viewdirs"], t["radiance"],
+                              (t["env_param"], shading.MODE_LEARNABLE), t["visibility"], t["incident_dirs"],
+                              t["incident_areas"])
+    nview = (t["shading_normals"] @ view).transpose(1, 2).reshape(t["shading_normals"].shape[0], -1)
+    if is_training:
+        f_ref = torch.cat([r["mean_visibility"], r["mean_local_lights"]], -1)
+        vf_ref = torch.cat([r["pbr"], t["base_color"], nview, t["roughness"], r["diffuse_light"]], -1)
+    else:
+        f_ref = torch.cat([r["mean_incident_lights"], r["mean_local_lights"], r["mean_visibility"]], -1)
+        vf_ref = torch.cat([r["pbr"], t["base_color"], nview, t["roughness"], r["direct"], r["indirect"]], -1)
+    gen = torch.Generator().manual_seed(5)
+    cf, cvf = torch.randn(f_ref.shape, generator=gen).cuda(), torch.randn(vf_ref.shape, generator=gen).cuda()
+    ((f_ref * cf).sum() + (vf_ref * cvf).sum()).backward()
+
+    t2 = inputs()
+    f, vf = shading.shade_and_pack(t2["base_color"], t2["roughness"], t2["shading_normals"], t2["viewdirs"], t2["radiance"],
+                                   (t2["env_param"], shading.MODE_LEARNABLE), t2["visibility"], t2["incident_dirs"],
+                                   t2["incident_areas"], view, is_training=is_training)
+    np.testing.assert_allclose(f.detach().cpu().numpy(), f_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(vf.detach().cpu().numpy(), vf_ref.detach().cpu().numpy(), rtol=2e-4, atol=1e-5)
+    ((f * cf).sum() + (vf * cvf).sum()).backward()
+    for k in names:
+        assert _rel(t2[k].grad.cpu().numpy(), t[k].grad.cpu().numpy()) < 1e-4, k
