@@ -209,6 +209,12 @@ typedef struct svgir_shade_out {
      * 1 / 3). `pack`, if set, points at the first pass-through column and receives
      * base_color[12] | view-space shading normals[12, channel-major] | roughness[4]. */
     float* pack;
+    /* Saved for svgir_shade_backward (replaces autograd's saved [N,Ns,12] tensors): per (vertex,channel)
+     * mean_s max(n.w,0)*area*L for the env light and the cached radiance. With sum_indirect NULL the
+     * kernel runs un-split and sum_direct receives the total (enough when no direct/indirect gradient
+     * will be requested). */
+    float* sum_direct;    /* [N,12] */
+    float* sum_indirect;  /* [N,12] or NULL */
     int32_t row_stride, mean_vis_stride, mean_stride, reserved_;
 } svgir_shade_out;
 
@@ -226,10 +232,13 @@ typedef struct svgir_shade_grads {
     float* d_viewdirs;                  /* [N,3] */
     float* d_radiance;                  /* [N,Ns,3] or NULL */
     float* d_visibility;                /* [N,Ns,1] or NULL */
-    float* d_env;                       /* [env_h,env_w,3] zero-filled by the caller, or NULL */
+    float* d_env;                       /* [env_h,env_w,3] zero-filled by the caller (accumulated into), or NULL */
     /* packed upstream gradients (see svgir_shade_out): strides of the g_* rows, and the gradient of
      * the pass-through columns, which is added into d_base_color / d_normals / d_roughness */
     const float* g_pack;
+    const float* sum_direct;    /* [N,12] written by svgir_shade_forward (required) */
+    const float* sum_indirect;  /* [N,12] or NULL; required when g_direct / g_indirect are given */
+    float* d_env_scratch;       /* [env_h,env_w,4] scratch (library zeroes it); required with d_env */
     int32_t g_row_stride, g_mean_vis_stride, g_mean_stride, reserved_;
 } svgir_shade_grads;
 

@@ -29,6 +29,11 @@ namespace svgir {
 
 #define SH_THREADS 256   // forward: ~120 regs -> 2 CTAs/SM
 #define SHB_THREADS 128  // backward: ~165 regs -> 3 CTAs/SM
+#ifndef SHB_MIN_CTAS
+#define SHB_MIN_CTAS 3
+#endif
+#define VUF_FLOATS 12    // forward per-vertex uniform block in shared memory
+#define VU_FLOATS 24     // backward per-vertex uniform block (see shade_bwd_kernel)
 #define PI_F 3.14159265358979323846f
 
 struct SampleShared {  // vertex-independent per-sample quantities, produced by one lane of the quad
@@ -50,8 +55,8 @@ struct EnvTap { int x0, y0; float wx1, wy1; };
 __device__ __forceinline__ EnvTap env_coords(float dx, float dy, float dz, int He, int We) {
     const float phi = acosf(dz) - 1e-6f;
     const float theta = atan2f(dy, dx);
-    const float qy = (phi / PI_F) * 2.f - 1.f;
-    const float qx = -theta / PI_F;
+    const float qy = (phi * (1.f / PI_F)) * 2.f - 1.f;   // one rounding away from phi / pi: < 1e-7 of a texel
+    const float qx = -theta * (1.f / PI_F);
     const float ix = (qx + 1.f) / 2.f * (float)(We - 1);
     const float iy = (qy + 1.f) / 2.f * (float)(He - 1);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -99,60 +104,94 @@ struct ShadeArgs {
     const float* areas;       // [N,Ns]
 };
 
-// Sum over the warp of K (<= NP, NP a power of two <= 32) per-lane values, "transposed": instead of
-// 5 shuffles per value, each step exchanges half of the remaining slots, so the whole reduction
-// costs ~NP shuffles.  Returns on every lane L the total of slot  L >> (5 - log2(NP)).
-template <int NP>
-__device__ __forceinline__ float warp_reduce_slots(float (&v)[NP], int lane) {
-    const unsigned full = 0xffffffffu;
-    int cur = NP;
+// Sum over the warp of NP (a power of two <= 32) per-lane values, "transposed": instead of 5 shuffles
+// per value, each step exchanges half of the remaining slots, so the whole reduction costs ~NP
+// shuffles.  Returns on every lane L the total of slot  L >> (5 - log2(NP)).  CUR / O are template
+// parameters so that every slot index is a compile-time constant (registers, no predication).
+template <int NP, int CUR, int O>
+struct WarpSlotReduce {
+    static __device__ __forceinline__ void run(float (&v)[NP], int lane) {
+        const unsigned full = 0xffffffffu;
+        if constexpr (CUR > 1) {
+            constexpr int HALF = CUR / 2;
+            const bool up = (lane & O) != 0;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        if (cur > 1) {
-            const int half = cur >> 1;
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < NP / 2; i++) {
-                if (i < half) {
-                    const float send = up ? v[i] : v[i + half];
-                    const float keep = up ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(full, send, o);
-                }
+            for (int i = 0; i < HALF; i++) {
+                const float send = up ? v[i] : v[i + HALF];
+                const float keep = up ? v[i + HALF] : v[i];
+                v[i] = keep + __shfl_xor_sync(full, send, O);
             }
-            cur = half;
+            if constexpr (O > 1) WarpSlotReduce<NP, HALF, O / 2>::run(v, lane);
         } else {
-            v[0] += __shfl_xor_sync(full, v[0], o);
+            v[0] += __shfl_xor_sync(full, v[0], O);
+            if constexpr (O > 1) WarpSlotReduce<NP, 1, O / 2>::run(v, lane);
         }
     }
+};
+template <int NP>
+__device__ __forceinline__ float warp_reduce_slots(float (&v)[NP], int lane) {
+    WarpSlotReduce<NP, NP, 16>::run(v, lane);
     return v[0];
+}
+
+// 1/sqrt(x) to ~1 ulp (MUFU.RSQ + one Newton step): same quality as the reference's x / max(|x|, eps)
+// (an IEEE sqrt followed by an IEEE divide) at a quarter of the instructions.
+__device__ __forceinline__ float inv_len(float ss) {
+    if (ss < 1e-24f) return 1e12f;   // F.normalize eps = 1e-12 on the norm
+    const float y = rsqrtf(ss);
+    return y * fmaf(-0.5f * ss * y, y, 1.5f);
+}
+
+// Raw per-sample inputs of one lane: loaded one (surfel, pass) ahead of their use so that the HBM
+// latency of the next 32 samples hides behind the arithmetic of the current ones.
+struct RawSample { float wx, wy, wz, r0, r1, r2, vis, area; };
+
+__device__ __forceinline__ void fetch_raw(const ShadeArgs& a, int n, int s0, int lane, RawSample& r) {
+    const int s = s0 + lane;
+    const bool ok = s < a.Ns;
+    const size_t is = (size_t)n * a.Ns + (ok ? s : a.Ns - 1);
+    const float* d = a.dirs + is * 3;
+    r.wx = __ldg(d); r.wy = __ldg(d + 1); r.wz = __ldg(d + 2);
+    const float* rad = a.radiance + is * 3;
+    const float r0 = __ldg(rad), r1 = __ldg(rad + 1), r2 = __ldg(rad + 2);
+    const float vis = __ldg(a.visibility + is), area = __ldg(a.areas + is);
+    r.r0 = ok ? r0 : 0.f; r.r1 = ok ? r1 : 0.f; r.r2 = ok ? r2 : 0.f;
+    r.vis = ok ? vis : 0.f; r.area = ok ? area : 0.f;   // a padded lane contributes nothing
+}
+
+// Raw per-surfel inputs: view direction (all lanes) and, on lanes 0..3, that vertex's normal/roughness.
+struct RawSurfel { float vx, vy, vz, nx, ny, nz, rough, met; };
+
+template <bool MET>
+__device__ __forceinline__ void fetch_surfel(const ShadeArgs& a, int n, int lane, RawSurfel& r) {
+    const float* vd = a.viewdirs + (size_t)n * 3;
+    r.vx = __ldg(vd); r.vy = __ldg(vd + 1); r.vz = __ldg(vd + 2);
+    const int v = lane & 3;
+    const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
+    r.nx = __ldg(nn); r.ny = __ldg(nn + 1); r.nz = __ldg(nn + 2);
+    r.rough = __ldg(a.roughness + (size_t)n * 4 + v);
+    r.met = MET ? __ldg(a.metallic + (size_t)n * 4 + v) : 0.f;
 }
 
 // Per-sample, vertex-independent quantities (one lane = one light sample of the warp's surfel).
 struct Sample {
     float wx, wy, wz, il;   // raw incident direction, 1/|w|
-    float hx, hy, hz, hlen; // half vector (normalised), |(L+V)/2|
+    float hx, hy, hz, ih;   // half vector (normalised), 1/|(L+V)/2|
     float voh_raw, p;       // V.H before the clamp, 2^((a1 VoH + a0) VoH)
     float ag[3], al[3];     // area * clamp(env)*vis , area * radiance
     float lg[3];            // clamp(env*scale) (without visibility)
     float raw[3];           // bilinear env value before scale/clamp
-    float rad[3];           // cached radiance
-    float vis, area;
     EnvTap tap;
 };
 
-__device__ __forceinline__ void load_sample(const ShadeArgs& a, const float* env, size_t is, bool ok, float Vx,
+__device__ __forceinline__ void make_sample(const ShadeArgs& a, const float* env, const RawSample& r, float Vx,
                                             float Vy, float Vz, Sample& o) {
-    const float* d = a.dirs + is * 3;
-    o.wx = d[0]; o.wy = d[1]; o.wz = d[2];
-    const float* rad = a.radiance + is * 3;
-    const float r0 = rad[0], r1 = rad[1], r2 = rad[2];
-    o.vis = ok ? a.visibility[is] : 0.f;
-    o.area = ok ? a.areas[is] : 0.f;
-    o.il = 1.f / fmaxf(sqrtf(o.wx * o.wx + o.wy * o.wy + o.wz * o.wz), 1e-12f);
+    o.wx = r.wx; o.wy = r.wy; o.wz = r.wz;
+    o.il = inv_len(o.wx * o.wx + o.wy * o.wy + o.wz * o.wz);
     const float lx = o.wx * o.il, ly = o.wy * o.il, lz = o.wz * o.il;
     const float hx = (lx + Vx) * 0.5f, hy = (ly + Vy) * 0.5f, hz = (lz + Vz) * 0.5f;
-    o.hlen = fmaxf(sqrtf(hx * hx + hy * hy + hz * hz), 1e-12f);
-    const float ih = 1.f / o.hlen;
+    const float ih = inv_len(hx * hx + hy * hy + hz * hz);
+    o.ih = ih;
     o.hx = hx * ih; o.hy = hy * ih; o.hz = hz * ih;
     o.voh_raw = Vx * o.hx + Vy * o.hy + Vz * o.hz;
     const float voh = fminf(fmaxf(o.voh_raw, 1e-6f), 1.f);
@@ -170,10 +209,9 @@ __device__ __forceinline__ void load_sample(const ShadeArgs& a, const float* env
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
         o.lg[ch] = fminf(fmaxf(o.raw[ch] * a.env_scale, 0.f), 64.f);
-        o.ag[ch] = o.area * (o.lg[ch] * o.vis);
+        o.ag[ch] = r.area * (o.lg[ch] * r.vis);
     }
-    o.rad[0] = r0; o.rad[1] = r1; o.rad[2] = r2;
-    o.al[0] = o.area * r0; o.al[1] = o.area * r1; o.al[2] = o.area * r2;
+    o.al[0] = r.area * r.r0; o.al[1] = r.area * r.r1; o.al[2] = r.area * r.r2;
 }
 
 // Per-(surfel, vertex) constants. c = sign(V.N^)/|N| so that N~.x = c (N.x) for the normalised,
@@ -181,33 +219,31 @@ __device__ __forceinline__ void load_sample(const ShadeArgs& a, const float* env
 struct VertexConst {
     float Nx, Ny, Nz, c;
     float a2, k, nom1, NoV;
-    float nv_raw, inv_nlen, r;
 };
 
-__device__ __forceinline__ void vertex_consts(const ShadeArgs& a, int n, int v, float Vx, float Vy, float Vz,
-                                              VertexConst& c) {
-    const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
-    c.Nx = nn[0]; c.Ny = nn[1]; c.Nz = nn[2];
-    c.inv_nlen = 1.f / fmaxf(sqrtf(c.Nx * c.Nx + c.Ny * c.Ny + c.Nz * c.Nz), 1e-12f);
-    const float d = (c.Nx * c.inv_nlen) * Vx + (c.Ny * c.inv_nlen) * Vy + (c.Nz * c.inv_nlen) * Vz;
+__device__ __forceinline__ void vertex_consts(const RawSurfel& s, float Vx, float Vy, float Vz, VertexConst& c) {
+    c.Nx = s.nx; c.Ny = s.ny; c.Nz = s.nz;
+    const float inv_nlen = inv_len(c.Nx * c.Nx + c.Ny * c.Ny + c.Nz * c.Nz);
+    const float d = (c.Nx * inv_nlen) * Vx + (c.Ny * inv_nlen) * Vy + (c.Nz * inv_nlen) * Vz;
     const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    c.c = sgn * c.inv_nlen;
-    c.nv_raw = (c.Nx * Vx + c.Ny * Vy + c.Nz * Vz) * c.c;   // N~.V before the clamp
-    c.NoV = fminf(fmaxf(c.nv_raw, 1e-6f), 1.f);
-    c.r = a.roughness[(size_t)n * 4 + v];
-    const float al = c.r * c.r;
+    c.c = sgn * inv_nlen;
+    const float nv_raw = (c.Nx * Vx + c.Ny * Vy + c.Nz * Vz) * c.c;   // N~.V before the clamp
+    c.NoV = fminf(fmaxf(nv_raw, 1e-6f), 1.f);
+    const float al = s.rough * s.rough;
     c.a2 = al * al;
-    c.k = (al + 2.f * c.r + 1.0f) / 8.0f;
+    c.k = (al + 2.f * s.rough + 1.0f) * 0.125f;
     c.nom1 = c.NoV * (1.f - c.k) + c.k;
 }
 
 struct ShadeOutK {
     float* pbr; float* diffuse; float* specular; float* direct; float* indirect;  // [N,row_stride] or null
-    float* mean_vis;       // rows of mean_stride floats, or null
+    float* mean_vis;       // rows of mean_*stride floats, or null
     float* mean_local;
     float* mean_incident;
     float* mean_global;
     float* pack;           // optional: base12 | view-space normals 12 | roughness 4 (row_stride)
+    float* sum_direct;     // [N,12] mean_s n.w*A_env (or of the total light when sum_indirect is null): saved for backward
+    float* sum_indirect;   // [N,12] mean_s n.w*A_radiance, or null
     int row_stride, mean_vis_stride, mean_stride;
 };
 
@@ -215,7 +251,9 @@ struct ShadeOutK {
 // coalesced loads exactly once; per-vertex sums are combined with one transposed warp reduction.
 template <bool SPLIT, bool MET, bool ENV_SMEM>
 __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a, const ShadeOutK out) {
-    extern __shared__ __align__(16) float env_s[];
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int WPC = SH_THREADS / 32;
+    float* env_s = smem_f + WPC * 4 * VUF_FLOATS;
     const float* env = a.env_act;
     if (ENV_SMEM) {
         for (int i = threadIdx.x; i < a.He * a.We * 3; i += SH_THREADS) env_s[i] = a.env_act[i];
@@ -224,25 +262,42 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
     }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    constexpr int WPC = SH_THREADS / 32;
+    float* vu = smem_f + (threadIdx.x >> 5) * 4 * VUF_FLOATS;
     const int Ns = a.Ns;
     const float inv = 1.f / (float)Ns;
-    for (int n = blockIdx.x * WPC + (threadIdx.x >> 5); n < a.N; n += gridDim.x * WPC) {
-        const float* vd = a.viewdirs + (size_t)n * 3;
-        const float inv_vlen = 1.f / fmaxf(sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]), 1e-12f);
-        const float Vx = vd[0] * inv_vlen, Vy = vd[1] * inv_vlen, Vz = vd[2] * inv_vlen;
-        VertexConst vc[4];
-        float F0[4][3];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            vertex_consts(a, n, v, Vx, Vy, Vz, vc[v]);
+    const int stride = gridDim.x * WPC;
+    int n = blockIdx.x * WPC + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+
+    RawSample raw;
+    RawSurfel rs;
+    fetch_surfel<MET>(a, n, lane, rs);
+    fetch_raw(a, n, 0, lane, raw);
+    while (n < a.N) {
+        // ---- surfel prologue --------------------------------------------------------------------
+        const float inv_vlen = inv_len(rs.vx * rs.vx + rs.vy * rs.vy + rs.vz * rs.vz);
+        const float Vx = rs.vx * inv_vlen, Vy = rs.vy * inv_vlen, Vz = rs.vz * inv_vlen;
+        // per-vertex uniforms, computed by lanes 0..3 and read back as broadcast LDS.128:
+        //   [0..3] N, c | [4..7] a2, k, nom1, F0.r | [8..11] F0.g, F0.b, -, -
+        __syncwarp();
+        if (lane < 4) {
+            VertexConst c;
+            vertex_consts(rs, Vx, Vy, Vz, c);
+            float* u = vu + lane * VUF_FLOATS;
+            u[0] = c.Nx; u[1] = c.Ny; u[2] = c.Nz; u[3] = c.c;
+            u[4] = c.a2; u[5] = c.k; u[6] = c.nom1;
             if (MET) {
-                const float m = a.metallic[(size_t)n * 4 + v];
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) F0[v][ch] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 4 * ch + v] * m;
+                const float m = rs.met;
+                u[7] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + lane] * m;
+                u[8] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 4 + lane] * m;
+                u[9] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 8 + lane] * m;
             }
         }
-        // D = sum ndi*A, S = sum f_s*ndi*A; index [0]: env ("direct") light or the total when !SPLIT, [1]: cached radiance
+        __syncwarp();
+        const int n_next = n + stride;
+        if (n_next < a.N) fetch_surfel<MET>(a, n_next, lane, rs);
+
+        // D = sum ndi*A, S = sum f_s*ndi*A; [0]: env ("direct") light or the total when !SPLIT, [1]: cached radiance
         float D[SPLIT ? 2 : 1][4][3], S[SPLIT ? 2 : 1][4][3];
 #pragma unroll
         for (int q = 0; q < (SPLIT ? 2 : 1); q++)
@@ -253,40 +308,42 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         float m_vis = 0.f, m_g[3] = {0, 0, 0}, m_l[3] = {0, 0, 0};
 
         for (int s0 = 0; s0 < Ns; s0 += 32) {
-            const int s = s0 + lane;
-            const bool ok = s < Ns;
+            const RawSample cur = raw;
+            if (s0 + 32 < Ns) fetch_raw(a, n, s0 + 32, lane, raw);
+            else if (n_next < a.N) fetch_raw(a, n_next, 0, lane, raw);
             Sample sm;
-            load_sample(a, env, (size_t)n * Ns + (ok ? s : Ns - 1), ok, Vx, Vy, Vz, sm);
-            if (ok) {
-                m_vis += sm.vis;
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    m_g[ch] += sm.lg[ch] * sm.vis;
-                    m_l[ch] += sm.rad[ch];
-                }
-            }
+            make_sample(a, env, cur, Vx, Vy, Vz, sm);
+            m_vis += cur.vis;
+            m_l[0] += cur.r0; m_l[1] += cur.r1; m_l[2] += cur.r2;
             float A0[3], A1[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
+                m_g[ch] = fmaf(sm.lg[ch], cur.vis, m_g[ch]);
                 A0[ch] = SPLIT ? sm.ag[ch] : sm.ag[ch] + sm.al[ch];
                 A1[ch] = sm.al[ch];
             }
 #pragma unroll
             for (int v = 0; v < 4; v++) {
-                const VertexConst& c = vc[v];
-                const float ndi_raw = c.Nx * sm.wx + c.Ny * sm.wy + c.Nz * sm.wz;
+                const float4 u0 = *reinterpret_cast<const float4*>(vu + v * VUF_FLOATS);
+                const float4 u1 = *reinterpret_cast<const float4*>(vu + v * VUF_FLOATS + 4);
+                float F0[3] = {0.04f, 0.04f, 0.04f};
+                if (MET) {
+                    const float2 u2 = *reinterpret_cast<const float2*>(vu + v * VUF_FLOATS + 8);
+                    F0[0] = u1.w; F0[1] = u2.x; F0[2] = u2.y;
+                }
+                const float ndi_raw = u0.x * sm.wx + u0.y * sm.wy + u0.z * sm.wz;
                 const float ndi = fmaxf(ndi_raw, 0.f);
-                const float nh = c.Nx * sm.hx + c.Ny * sm.hy + c.Nz * sm.hz;
-                const float NoL = fminf(fmaxf(c.c * sm.il * ndi_raw, 1e-6f), 1.f);
-                const float NoH = fminf(fmaxf(c.c * nh, 1e-6f), 1.f);
-                const float nom0 = NoH * NoH * (c.a2 - 1.f) + 1.f;
-                const float nom2 = NoL * (1.f - c.k) + c.k;
-                const float nom = fminf(fmaxf(4.f * PI_F * nom0 * nom0 * c.nom1 * nom2, 1e-6f), 4.f * PI_F);
-                const float Dt = __fdividef(c.a2, nom);
+                const float nh = u0.x * sm.hx + u0.y * sm.hy + u0.z * sm.hz;
+                const float NoL = fminf(fmaxf(u0.w * sm.il * ndi_raw, 1e-6f), 1.f);
+                const float NoH = fminf(fmaxf(u0.w * nh, 1e-6f), 1.f);
+                const float nom0 = NoH * NoH * (u1.x - 1.f) + 1.f;
+                const float nom2 = NoL * (1.f - u1.y) + u1.y;
+                const float nom = fminf(fmaxf(4.f * PI_F * nom0 * nom0 * u1.z * nom2, 1e-6f), 4.f * PI_F);
+                const float Dt = __fdividef(u1.x, nom);
                 const float dn = Dt * ndi;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-                    const float f0 = MET ? F0[v][ch] : 0.04f;
+                    const float f0 = F0[ch];
                     const float fsn = (f0 + (1.f - f0) * sm.p) * dn;
                     D[0][v][ch] = fmaf(ndi, A0[ch], D[0][v][ch]);
                     S[0][v][ch] = fmaf(fsn, A0[ch], S[0][v][ch]);
@@ -327,13 +384,15 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
             const size_t o = (size_t)n * out.row_stride + lane;
             const float base = a.base_color[(size_t)n * 12 + lane];
             const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
-            const float fd = (1.f - met) * base / PI_F;
+            const float fd = (1.f - met) * base * (1.f / PI_F);
+            if (out.sum_direct) out.sum_direct[(size_t)n * 12 + lane] = t0;
             if (!SPLIT) {
                 if (out.diffuse) out.diffuse[o] = t0;
                 if (out.specular) out.specular[o] = s0v;
                 if (out.pbr) out.pbr[o] = fd * t0 + s0v;
             } else {
                 const float dir = fd * t0 + s0v, ind = fd * t1 + s1v;
+                if (out.sum_indirect) out.sum_indirect[(size_t)n * 12 + lane] = t1;
                 if (out.diffuse) out.diffuse[o] = t0 + t1;
                 if (out.specular) out.specular[o] = s0v + s1v;
                 if (out.pbr) out.pbr[o] = fd * (t0 + t1) + (s0v + s1v);
@@ -357,6 +416,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         } else if (lane >= 28 && lane < 31) {
             if (out.mean_global) out.mean_global[(size_t)n * out.mean_stride + (lane - 28)] = t0;
         }
+        n = n_next;
     }
 }
 
@@ -364,32 +424,49 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
 struct ShadeGradsK {
     const float* g_pbr; const float* g_diffuse; const float* g_specular; const float* g_direct;
     const float* g_indirect;                     // rows of g_row_stride floats, or null
-    const float* g_mean_vis;                     // rows of g_mean_stride floats, or null
+    const float* g_mean_vis;                     // rows of g_mean_*stride floats, or null
     const float* g_mean_local;
     const float* g_mean_incident;
     const float* g_mean_global;
     const float* g_pack;                         // optional grads of the pass-through columns (base|normal|roughness)
+    const float* sum_direct;                     // [N,12] saved by the forward kernel
+    const float* sum_indirect;                   // [N,12] or null (then sum_direct is the total)
     int g_row_stride, g_mean_vis_stride, g_mean_stride;
     const float* env_param;                      // raw parameter (learnable mode) for softplus'
     float* d_base_color; float* d_roughness; float* d_metallic; float* d_normals; float* d_viewdirs;
     float* d_radiance;                           // [N,Ns,3] or null
     float* d_visibility;                         // [N,Ns] or null
-    float* d_env;                                // [He,We,3] accumulated with atomics, or null
+    float* d_env_acc;                            // [He,We,4] zeroed accumulator of the env gradient, or null
 };
 
-#define VU_FLOATS 24  // per-vertex uniform block in shared memory (see shade_bwd_kernel)
+// Env-map gradient scatter. sm_100 has no native shared-memory float atomic (atomicAdd on shared
+// compiles to a compare-and-swap loop that costs ~2 ms at the training shape), so the four bilinear
+// taps of a sample go straight to L2 as four fire-and-forget vector reductions
+// (REDG.E.ADD.F32x4) into a [He,We,4] accumulator; a tiny kernel folds it into d_env afterwards.
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
+}
+
+__global__ void env_grad_finalize_kernel(int ntex, int env_mode, const float* __restrict__ acc,
+                                         const float* __restrict__ env_param, float* __restrict__ d_env) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntex * 3) return;
+    float val = acc[(i / 3) * 4 + (i % 3)];
+    if (env_mode == 0) val = val / (1.f + expf(-env_param[i]));  // softplus'
+    d_env[i] += val;
+}
 
 template <bool MET, bool ENV_SMEM>
-__global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs a, const ShadeGradsK g, int env_mode) {
+__global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(const ShadeArgs a, const ShadeGradsK g) {
     extern __shared__ __align__(16) float smem_b[];
     constexpr int WPC = SHB_THREADS / 32;
+    constexpr int NACC = MET ? 10 : 7;   // per-vertex partial sums kept by every lane
     const int nenv = a.He * a.We * 3;
     float* vu_all = smem_b;                                         // [WPC][4][VU_FLOATS]
     float* env_s = smem_b + WPC * 4 * VU_FLOATS;                    // activated env (if it fits)
-    float* denv_s = ENV_SMEM ? env_s + nenv : nullptr;              // per-CTA env gradient accumulator
     const float* env = a.env_act;
     if (ENV_SMEM) {
-        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) { env_s[i] = a.env_act[i]; denv_s[i] = 0.f; }
+        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) env_s[i] = a.env_act[i];
         __syncthreads();
         env = env_s;
     }
@@ -399,33 +476,40 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
     const int Ns = a.Ns;
     const float inv = 1.f / (float)Ns;
     const bool want_rad = g.d_radiance != nullptr;
+    const int stride = gridDim.x * WPC;
+    int n = blockIdx.x * WPC + (threadIdx.x >> 5);
 
-    for (int n = blockIdx.x * WPC + (threadIdx.x >> 5); n < a.N; n += gridDim.x * WPC) {
-        const float* vd = a.viewdirs + (size_t)n * 3;
-        const float inv_vlen = 1.f / fmaxf(sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]), 1e-12f);
-        const float Vx = vd[0] * inv_vlen, Vy = vd[1] * inv_vlen, Vz = vd[2] * inv_vlen;
+    RawSample raw;
+    RawSurfel rs;
+    if (n < a.N) {
+        fetch_surfel<MET>(a, n, lane, rs);
+        fetch_raw(a, n, 0, lane, raw);
+    }
+    while (n < a.N) {
+        const float inv_vlen = inv_len(rs.vx * rs.vx + rs.vy * rs.vy + rs.vz * rs.vz);
+        const float Vx = rs.vx * inv_vlen, Vy = rs.vy * inv_vlen, Vz = rs.vz * inv_vlen;
         // ---- per-vertex uniforms -> shared: [0..3] N,c | [4..7] a2,k,nom1,NoV | [8..10] gDg,[11] F0r |
-        //      [12..14] gDl,[15] F0g | [16..18] gSg,[19] F0b | [20..22] gSl,[23] -
+        //      [12..14] gDl,[15] F0g | [16..18] gSg,[19] F0b | [20..22] gSl,[23] roughness
         __syncwarp();
         if (lane < 4) {
             VertexConst c;
-            vertex_consts(a, n, lane, Vx, Vy, Vz, c);
+            vertex_consts(rs, Vx, Vy, Vz, c);
             float* u = vu + lane * VU_FLOATS;
             u[0] = c.Nx; u[1] = c.Ny; u[2] = c.Nz; u[3] = c.c;
             u[4] = c.a2; u[5] = c.k; u[6] = c.nom1; u[7] = c.NoV;
+            u[23] = rs.rough;
         }
-        float met_l = 0.f, base_l = 0.f, Gp = 0.f, Gdi = 0.f, Gin = 0.f, Gs = 0.f;
         if (lane < 12) {
             const int v = lane & 3, ch = lane >> 2;
             const size_t og = (size_t)n * g.g_row_stride + lane;
-            base_l = a.base_color[(size_t)n * 12 + lane];
-            met_l = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
-            const float fd = (1.f - met_l) * base_l / PI_F;
-            Gp = g.g_pbr ? g.g_pbr[og] : 0.f;
+            const float base_l = a.base_color[(size_t)n * 12 + lane];
+            const float met_l = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
+            const float fd = (1.f - met_l) * base_l * (1.f / PI_F);
+            const float Gp = g.g_pbr ? g.g_pbr[og] : 0.f;
             const float Gd = g.g_diffuse ? g.g_diffuse[og] : 0.f;
-            Gs = g.g_specular ? g.g_specular[og] : 0.f;
-            Gdi = g.g_direct ? g.g_direct[og] : 0.f;
-            Gin = g.g_indirect ? g.g_indirect[og] : 0.f;
+            const float Gs = g.g_specular ? g.g_specular[og] : 0.f;
+            const float Gdi = g.g_direct ? g.g_direct[og] : 0.f;
+            const float Gin = g.g_indirect ? g.g_indirect[og] : 0.f;
             float* u = vu + v * VU_FLOATS;
             u[8 + ch] = (Gd + (Gp + Gdi) * fd) * inv;
             u[12 + ch] = (Gd + (Gp + Gin) * fd) * inv;
@@ -434,6 +518,9 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
             u[11 + 4 * ch] = MET ? 0.04f * (1.f - met_l) + base_l * met_l : 0.04f;
         }
         __syncwarp();
+        const int n_next = n + stride;
+        if (n_next < a.N) fetch_surfel<MET>(a, n_next, lane, rs);
+
         float gmv = 0.f, gml[3] = {0, 0, 0}, gmg[3] = {0, 0, 0};
         {
             const size_t om = (size_t)n * g.g_mean_stride;
@@ -446,21 +533,23 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
             }
         }
 
-        // per-vertex partial sums of this lane: 0..2 dN, 3 d_c, 4 d_a2, 5 d_k, 6 d_nom1, 7..9 sum ndi*Ag,
-        // 10..12 sum ndi*Al, 13..15 dF0 (metallic only)
-        float acc[4][16];
+        // per-vertex partial sums of this lane: 0..2 dN, 3 d_c, 4 d_a2, 5 d_k, 6 d_nom1, 7..9 dF0 (metallic only)
+        float acc[4][NACC];
 #pragma unroll
         for (int v = 0; v < 4; v++)
 #pragma unroll
-            for (int i = 0; i < 16; i++) acc[v][i] = 0.f;
+            for (int i = 0; i < NACC; i++) acc[v][i] = 0.f;
         float dV[3] = {0, 0, 0};
 
         for (int s0 = 0; s0 < Ns; s0 += 32) {
+            const RawSample cur = raw;
+            if (s0 + 32 < Ns) fetch_raw(a, n, s0 + 32, lane, raw);
+            else if (n_next < a.N) fetch_raw(a, n_next, 0, lane, raw);
             const int s = s0 + lane;
             const bool ok = s < Ns;
             const size_t is = (size_t)n * Ns + (ok ? s : Ns - 1);
             Sample sm;
-            load_sample(a, env, is, ok, Vx, Vy, Vz, sm);
+            make_sample(a, env, cur, Vx, Vy, Vz, sm);
             float dAg[3] = {0, 0, 0}, dAl[3] = {0, 0, 0}, dp_acc = 0.f, dhN[3] = {0, 0, 0};
 #pragma unroll
             for (int v = 0; v < 4; v++) {
@@ -489,26 +578,32 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
                 const float nom = fminf(fmaxf(nom_raw, 1e-6f), 4.f * PI_F);
                 const float rn = __fdividef(1.f, nom);
                 const float Dt = a2 * rn;
+                const float dn = Dt * ndi;
 
                 float qD = 0.f, Fq = 0.f, Gq = 0.f;   // sum gD*A ; sum F[ch]*qs[ch] ; sum (1-F0[ch])*qs[ch]
                 float* ac = acc[v];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-                    const float F = F0[ch] + (1.f - F0[ch]) * sm.p;
                     const float qs = gSg[ch] * sm.ag[ch] + gSl[ch] * sm.al[ch];
                     qD = fmaf(gDg[ch], sm.ag[ch], fmaf(gDl[ch], sm.al[ch], qD));
-                    Fq = fmaf(F, qs, Fq);
-                    Gq = fmaf(1.f - F0[ch], qs, Gq);
-                    const float fsn = F * Dt * ndi;
+                    float F;
+                    if (MET) {
+                        F = F0[ch] + (1.f - F0[ch]) * sm.p;
+                        Fq = fmaf(F, qs, Fq);
+                        Gq = fmaf(1.f - F0[ch], qs, Gq);
+                        ac[7 + ch] = fmaf(dn * (1.f - sm.p), qs, ac[7 + ch]);
+                    } else {
+                        F = 0.04f + 0.96f * sm.p;
+                        Fq += qs;     // scaled by F / 0.96 after the loop
+                    }
+                    const float fsn = F * dn;
                     dAg[ch] += ndi * gDg[ch] + fsn * gSg[ch];
                     dAl[ch] += ndi * gDl[ch] + fsn * gSl[ch];
-                    ac[7 + ch] = fmaf(ndi, sm.ag[ch], ac[7 + ch]);
-                    ac[10 + ch] = fmaf(ndi, sm.al[ch], ac[10 + ch]);
-                    if (MET) ac[13 + ch] = fmaf(ndi * Dt * (1.f - sm.p), qs, ac[13 + ch]);
                 }
+                if (!MET) { Gq = 0.96f * Fq; Fq *= 0.04f + 0.96f * sm.p; }
                 const float d_ndi = qD + Dt * Fq;
                 const float d_Dt = ndi * Fq;
-                dp_acc = fmaf(ndi * Dt, Gq, dp_acc);
+                dp_acc = fmaf(dn, Gq, dp_acc);
                 // Dt = a2 / clamp(nom_raw)
                 const bool nom_in = nom_raw >= 1e-6f && nom_raw <= 4.f * PI_F;
                 float d_a2 = d_Dt * rn;
@@ -541,113 +636,127 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
                 const float d_voh = voh_in ? dp_acc * sm.p * 0.6931471805599453f * (2.f * -5.55473f * voh - 6.98316f) : 0.f;
                 const float dH[3] = {dhN[0] + d_voh * Vx, dhN[1] + d_voh * Vy, dhN[2] + d_voh * Vz};
                 const float hd = sm.hx * dH[0] + sm.hy * dH[1] + sm.hz * dH[2];
-                const float ih = 0.5f / sm.hlen;
+                const float ih = 0.5f * sm.ih;
                 dV[0] += d_voh * sm.hx + (dH[0] - sm.hx * hd) * ih;
                 dV[1] += d_voh * sm.hy + (dH[1] - sm.hy * hd) * ih;
                 dV[2] += d_voh * sm.hz + (dH[2] - sm.hz * hd) * ih;
             }
-            if (ok) {
-                if (want_rad) {
+            if (want_rad && ok) {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++) g.d_radiance[is * 3 + ch] = dAl[ch] * sm.area + gml[ch];
-                }
-                float dvis = gmv, draw[3];
+                for (int ch = 0; ch < 3; ch++) g.d_radiance[is * 3 + ch] = dAl[ch] * cur.area + gml[ch];
+            }
+            float dvis = gmv, draw[3];
 #pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    const float x = sm.raw[ch] * a.env_scale;
-                    const float dLg = dAg[ch] * sm.area + gmg[ch];
-                    dvis = fmaf(dLg, sm.lg[ch], dvis);
-                    draw[ch] = (x >= 0.f && x <= 64.f) ? dLg * sm.vis * a.env_scale : 0.f;
-                }
-                if (g.d_visibility) g.d_visibility[is] = dvis;
-                if (g.d_env) {
-                    const float wx0 = 1.f - sm.tap.wx1, wy0 = 1.f - sm.tap.wy1;
+            for (int ch = 0; ch < 3; ch++) {
+                const float x = sm.raw[ch] * a.env_scale;
+                const float dLg = dAg[ch] * cur.area + gmg[ch];
+                dvis = fmaf(dLg, sm.lg[ch], dvis);
+                draw[ch] = (ok && x >= 0.f && x <= 64.f) ? dLg * cur.vis * a.env_scale : 0.f;
+            }
+            if (g.d_visibility && ok) g.d_visibility[is] = dvis;
+            if (g.d_env_acc && (draw[0] != 0.f || draw[1] != 0.f || draw[2] != 0.f)) {
+                const float wx0 = 1.f - sm.tap.wx1, wy0 = 1.f - sm.tap.wy1;
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const int x = sm.tap.x0 + (kk & 1), y = sm.tap.y0 + (kk >> 1);
-                        if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
-                        const float w = ((kk & 1) ? sm.tap.wx1 : wx0) * ((kk >> 1) ? sm.tap.wy1 : wy0);
-                        const int base_i = (y * a.We + x) * 3;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) {
-                            const float val = draw[ch] * w;
-                            if (val != 0.f) {
-                                if (ENV_SMEM) atomicAdd(&denv_s[base_i + ch], val);
-                                else atomicAdd(&g.d_env[base_i + ch], env_mode == 0 ? val / (1.f + expf(-g.env_param[base_i + ch])) : val);
-                            }
-                        }
-                    }
+                for (int kk = 0; kk < 4; kk++) {
+                    const int x = sm.tap.x0 + (kk & 1), y = sm.tap.y0 + (kk >> 1);
+                    if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
+                    const float w = ((kk & 1) ? sm.tap.wx1 : wx0) * ((kk >> 1) ? sm.tap.wy1 : wy0);
+                    red_add_v4(g.d_env_acc + (size_t)(y * a.We + x) * 4, draw[0] * w, draw[1] * w, draw[2] * w);
                 }
             }
         }
 
-        // ---- per-vertex epilogue --------------------------------------------------------------------
-        // after the reduction slot i lives on lanes 2i, 2i+1
-        float dVu[3] = {0, 0, 0};   // uniform (vertex-level) view-direction terms, added once below
+        // ---- per-vertex epilogue ----------------------------------------------------------------------
+        // One 32-slot transposed reduction for all four vertices: afterwards lane L holds the total of
+        // slot (L & 7) of vertex (L >> 3); the metallic-only dF0 sums take a second, 16-slot reduction.
+        float r[32];
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            const float tot = warp_reduce_slots<16>(acc[v], lane);
+#pragma unroll
+            for (int i = 0; i < 7; i++) r[8 * v + i] = acc[v][i];
+            r[8 * v + 7] = 0.f;
+        }
+        const float tot = warp_reduce_slots<32>(r, lane);
+        float totF = 0.f;   // lanes 2*(4*ch+v), +1: dF0[v][ch]
+        if (MET) {
+            float rf[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) rf[i] = 0.f;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) rf[4 * ch + v] = acc[v][MET ? 7 + ch : 0];
+            totF = warp_reduce_slots<16>(rf, lane);
+        }
+        {
+            const int hb = lane & 24, slot = lane & 7, v = lane >> 3;
             const float* u = vu + v * VU_FLOATS;
-            const float Nx = u[0], Ny = u[1], Nz = u[2], cc = u[3];
-            const float k = u[5], NoVc = u[7];
-            const float d_c = __shfl_sync(full, tot, 6), d_a2 = __shfl_sync(full, tot, 8);
-            const float d_k = __shfl_sync(full, tot, 10), d_nom1 = __shfl_sync(full, tot, 12);
-            // recompute the un-clamped N~.V and |N| (uniform)
-            const float nvr = (Nx * Vx + Ny * Vy + Nz * Vz);
+            const float4 u0 = *reinterpret_cast<const float4*>(u);
+            const float Nx = u0.x, Ny = u0.y, Nz = u0.z, cc = u0.w;
+            const float k = u[5], rgh = u[23];
+            const float d_c = __shfl_sync(full, tot, hb + 3), d_a2 = __shfl_sync(full, tot, hb + 4);
+            const float d_k = __shfl_sync(full, tot, hb + 5), d_nom1 = __shfl_sync(full, tot, hb + 6);
+            const float nvr = Nx * Vx + Ny * Vy + Nz * Vz;
             const float nv_raw = nvr * cc;
             const float d_nov = (nv_raw >= 1e-6f && nv_raw <= 1.f) ? d_nom1 * (1.f - k) : 0.f;
-            (void)NoVc;
-            const float nl2 = fmaxf(Nx * Nx + Ny * Ny + Nz * Nz, 1e-24f);
-            const float d_c_tot = d_c + d_nov * nvr;
-            dVu[0] += d_nov * cc * Nx; dVu[1] += d_nov * cc * Ny; dVu[2] += d_nov * cc * Nz;
-            const float rgh = a.roughness[(size_t)n * 4 + v];
-            if ((lane & 1) == 0) {
-                const int slot = lane >> 1;
-                if (slot < 3) {
-                    const float Nk = slot == 0 ? Nx : (slot == 1 ? Ny : Nz);
-                    const float Vk = slot == 0 ? Vx : (slot == 1 ? Vy : Vz);
-                    // c = sgn/|N|  ->  dc/dN = -c N/|N|^2
-                    float val = tot + d_nov * cc * Vk - d_c_tot * cc * Nk / nl2;
-                    if (g.g_pack) {  // packed view-space normals: n_view[v][j] = sum_i N[v][i] R[i][j]
-                        const float* gp = g.g_pack + (size_t)n * g.g_row_stride + 12;
-                        val += gp[v] * a.view3x3[3 * slot] + gp[4 + v] * a.view3x3[3 * slot + 1] + gp[8 + v] * a.view3x3[3 * slot + 2];
-                    }
-                    g.d_normals[((size_t)n * 4 + v) * 3 + slot] = val;
-                } else if (slot == 4) {
-                    float val = d_a2 * 4.f * rgh * rgh * rgh + d_k * (2.f * rgh + 2.f) / 8.0f;
-                    if (g.g_pack) val += g.g_pack[(size_t)n * g.g_row_stride + 24 + v];
-                    g.d_roughness[(size_t)n * 4 + v] = val;
+            float dvu = 0.f;
+            if (slot < 3) {
+                const float Nk = slot == 0 ? Nx : (slot == 1 ? Ny : Nz);
+                const float Vk = slot == 0 ? Vx : (slot == 1 ? Vy : Vz);
+                const float nl2 = fmaxf(Nx * Nx + Ny * Ny + Nz * Nz, 1e-24f);
+                // c = sgn/|N|  ->  dc/dN = -c N/|N|^2
+                float val = tot + d_nov * cc * Vk - (d_c + d_nov * nvr) * cc * Nk / nl2;
+                if (g.g_pack) {  // packed view-space normals: n_view[v][j] = sum_i N[v][i] R[i][j]
+                    const float* gp = g.g_pack + (size_t)n * g.g_row_stride + 12;
+                    val += gp[v] * a.view3x3[3 * slot] + gp[4 + v] * a.view3x3[3 * slot + 1] + gp[8 + v] * a.view3x3[3 * slot + 2];
                 }
+                g.d_normals[((size_t)n * 4 + v) * 3 + slot] = val;
+                dvu = d_nov * cc * Nk;     // vertex-level N~.V term of dV component `slot`
+            } else if (slot == 4) {
+                float val = d_a2 * 4.f * rgh * rgh * rgh + d_k * (2.f * rgh + 2.f) * 0.125f;
+                if (g.g_pack) val += g.g_pack[(size_t)n * g.g_row_stride + 24 + v];
+                g.d_roughness[(size_t)n * 4 + v] = val;
             }
-            // base colour / metallic: lanes 14,16,18 hold sum ndi*Ag per channel; 20,22,24 the Al sums; 26,28,30 dF0
-            const float sumL = __shfl_down_sync(full, tot, 6);
-            const float dF0 = __shfl_down_sync(full, tot, 12);
+            // fold the vertex-level view terms into the per-sample ones: component = slot (0..2)
+            dV[0] += slot == 0 ? dvu : 0.f;
+            dV[1] += slot == 1 ? dvu : 0.f;
+            dV[2] += slot == 2 ? dvu : 0.f;
+        }
+        // base colour / metallic through f_d = (1-m) base/pi and F0 = 0.04(1-m) + base m; lane = 4*ch + v
+        {
+            const float dF0 = __shfl_sync(full, totF, (2 * lane) & 31);
             float dm = 0.f;
-            if (lane >= 14 && lane < 20 && (lane & 1) == 0) {
-                const int ch = (lane - 14) >> 1;
-                const size_t o12 = (size_t)n * 12 + 4 * ch + v;
-                const size_t og = (size_t)n * g.g_row_stride + 4 * ch + v;
+            if (lane < 12) {
+                const int v = lane & 3;
+                const size_t o12 = (size_t)n * 12 + lane;
+                const size_t og = (size_t)n * g.g_row_stride + lane;
                 const float base = a.base_color[o12];
                 const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
                 const float gp = g.g_pbr ? g.g_pbr[og] : 0.f;
-                const float gdi = g.g_direct ? g.g_direct[og] : 0.f;
-                const float gin = g.g_indirect ? g.g_indirect[og] : 0.f;
-                const float dgm = tot * inv, dlm = sumL * inv;
-                const float dfd = gp * (dgm + dlm) + gdi * dgm + gin * dlm;
-                float db = dfd * (1.f - met) / PI_F;
-                dm = dfd * (-base / PI_F);
-                if (MET) { db += dF0 * met; dm += dF0 * (base - 0.04f); }
+                const float dgm = g.sum_direct[o12];
+                float dfd;
+                if (g.sum_indirect) {
+                    const float dlm = g.sum_indirect[o12];
+                    const float gdi = g.g_direct ? g.g_direct[og] : 0.f;
+                    const float gin = g.g_indirect ? g.g_indirect[og] : 0.f;
+                    dfd = gp * (dgm + dlm) + gdi * dgm + gin * dlm;
+                } else {
+                    dfd = gp * dgm;
+                }
+                float db = dfd * (1.f - met) * (1.f / PI_F);
+                dm = dfd * (-base * (1.f / PI_F));
+                if (MET) { db += dF0 * met; dm += dF0 * (base - 0.04f); }   // dF0 already carries the 1/Ns of the upstream
                 if (g.g_pack) db += g.g_pack[og];
                 g.d_base_color[o12] = db;
             }
-            if (MET && g.d_metallic) {  // uniform branch: all lanes shuffle
-                const float t = __shfl_sync(full, dm, 14) + __shfl_sync(full, dm, 16) + __shfl_sync(full, dm, 18);
-                if (lane == 0) g.d_metallic[(size_t)n * 4 + v] = t;
+            if (MET && g.d_metallic) {  // uniform branch: all lanes shuffle; lanes v, 4+v, 8+v hold the 3 channels
+                const float t = dm + __shfl_down_sync(full, dm, 4) + __shfl_down_sync(full, dm, 8);
+                if (lane < 4) g.d_metallic[(size_t)n * 4 + lane] = t;
             }
         }
-        // view direction: per-sample terms summed over the warp + the uniform N~.V terms, then normalisation
+        // view direction: summed over the warp, then through the normalisation V = vd/|vd|
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) dV[ch] = warp_sum(dV[ch]) + dVu[ch];
+        for (int ch = 0; ch < 3; ch++) dV[ch] = warp_sum(dV[ch]);
         if (lane == 0) {
             const float vdot = Vx * dV[0] + Vy * dV[1] + Vz * dV[2];
             float* o = g.d_viewdirs + (size_t)n * 3;
@@ -655,16 +764,7 @@ __global__ void __launch_bounds__(SHB_THREADS) shade_bwd_kernel(const ShadeArgs 
             o[1] = (dV[1] - Vy * vdot) * inv_vlen;
             o[2] = (dV[2] - Vz * vdot) * inv_vlen;
         }
-    }
-    if (ENV_SMEM && g.d_env) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) {
-            float val = denv_s[i];
-            if (val != 0.f) {
-                if (env_mode == 0) val = val / (1.f + expf(-g.env_param[i]));  // softplus'
-                atomicAdd(&g.d_env[i], val);
-            }
-        }
+        n = n_next;
     }
 }
 
@@ -735,28 +835,26 @@ static int shade_grid(int N, int threads, int ctas_per_sm) {
 template <bool SPLIT, bool MET>
 static void launch_shade_fwd(const ShadeArgs& a, const ShadeOutK& so, cudaStream_t s) {
     const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
+    const size_t vu_bytes = (size_t)(SH_THREADS / 32) * 4 * VUF_FLOATS * sizeof(float);
     const int grid = shade_grid(a.N, SH_THREADS, 2);
-    if (env_bytes <= 96 * 1024) {
-        if (env_bytes > 48 * 1024)
-            cudaFuncSetAttribute(shade_fwd_kernel<SPLIT, MET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_bytes);
-        shade_fwd_kernel<SPLIT, MET, true><<<grid, SH_THREADS, env_bytes, s>>>(a, so);
+    if (env_bytes + vu_bytes <= 96 * 1024) {
+        if (env_bytes + vu_bytes > 48 * 1024)
+            cudaFuncSetAttribute(shade_fwd_kernel<SPLIT, MET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(env_bytes + vu_bytes));
+        shade_fwd_kernel<SPLIT, MET, true><<<grid, SH_THREADS, env_bytes + vu_bytes, s>>>(a, so);
     } else {
-        shade_fwd_kernel<SPLIT, MET, false><<<grid, SH_THREADS, 0, s>>>(a, so);
+        shade_fwd_kernel<SPLIT, MET, false><<<grid, SH_THREADS, vu_bytes, s>>>(a, so);
     }
 }
 
 template <bool MET>
-static void launch_shade_bwd(const ShadeArgs& a, const ShadeGradsK& g, int env_mode, cudaStream_t s) {
+static void launch_shade_bwd(const ShadeArgs& a, const ShadeGradsK& g, cudaStream_t s) {
     const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
     const size_t vu_bytes = (size_t)(SHB_THREADS / 32) * 4 * VU_FLOATS * sizeof(float);
-    const int grid = shade_grid(a.N, SHB_THREADS, 3);
-    if (2 * env_bytes + vu_bytes <= 96 * 1024) {
-        const size_t smem = 2 * env_bytes + vu_bytes;
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(shade_bwd_kernel<MET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        shade_bwd_kernel<MET, true><<<grid, SHB_THREADS, smem, s>>>(a, g, env_mode);
+    const int grid = shade_grid(a.N, SHB_THREADS, SHB_MIN_CTAS);
+    if (env_bytes + vu_bytes <= 48 * 1024) {
+        shade_bwd_kernel<MET, true><<<grid, SHB_THREADS, env_bytes + vu_bytes, s>>>(a, g);
     } else {
-        shade_bwd_kernel<MET, false><<<grid, SHB_THREADS, vu_bytes, s>>>(a, g, env_mode);
+        shade_bwd_kernel<MET, false><<<grid, SHB_THREADS, vu_bytes, s>>>(a, g);
     }
 }
 
@@ -789,10 +887,10 @@ int svgir_shade_forward(const svgir_shade_cfg* c, const svgir_shade_in* in, cons
     if (o->pack && !in->view3x3) { set_error("shade: packed pass-through columns need view3x3"); return SVGIR_ERR_INVALID; }
     if (c->N == 0) return SVGIR_OK;
     ShadeOutK so{o->pbr, o->diffuse_light, o->specular, o->direct, o->indirect, o->mean_visibility,
-                 o->mean_local, o->mean_incident, o->mean_global, o->pack,
+                 o->mean_local, o->mean_incident, o->mean_global, o->pack, o->sum_direct, o->sum_indirect,
                  o->row_stride > 0 ? o->row_stride : 12, o->mean_vis_stride > 0 ? o->mean_vis_stride : 1,
                  o->mean_stride > 0 ? o->mean_stride : 3};
-    const bool split = o->direct || o->indirect;
+    const bool split = o->direct || o->indirect || o->sum_indirect;
     const bool met = in->metallic != nullptr;
     {
         TimedScope ts_("shade_fwd", s);
@@ -809,16 +907,27 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
     if (rc) return rc;
     if (!gr || !gr->d_base_color || !gr->d_roughness || !gr->d_normals || !gr->d_viewdirs) { set_error("shade_backward: missing buffers"); return SVGIR_ERR_INVALID; }
     if (gr->g_pack && !in->view3x3) { set_error("shade_backward: packed pass-through columns need view3x3"); return SVGIR_ERR_INVALID; }
+    if (!gr->sum_direct) { set_error("shade_backward: sum_direct (saved by svgir_shade_forward) is required"); return SVGIR_ERR_INVALID; }
+    if ((gr->g_direct || gr->g_indirect) && !gr->sum_indirect) { set_error("shade_backward: g_direct/g_indirect need the split sums (sum_indirect)"); return SVGIR_ERR_INVALID; }
     if (c->N == 0) return SVGIR_OK;
     ShadeGradsK g{gr->g_pbr, gr->g_diffuse_light, gr->g_specular, gr->g_direct, gr->g_indirect, gr->g_mean_visibility,
-                  gr->g_mean_local, gr->g_mean_incident, gr->g_mean_global, gr->g_pack,
+                  gr->g_mean_local, gr->g_mean_incident, gr->g_mean_global, gr->g_pack, gr->sum_direct, gr->sum_indirect,
                   gr->g_row_stride > 0 ? gr->g_row_stride : 12, gr->g_mean_vis_stride > 0 ? gr->g_mean_vis_stride : 1,
                   gr->g_mean_stride > 0 ? gr->g_mean_stride : 3, in->env,
                   gr->d_base_color, gr->d_roughness, gr->d_metallic, gr->d_normals, gr->d_viewdirs,
-                  gr->d_radiance, gr->d_visibility, gr->d_env};
+                  gr->d_radiance, gr->d_visibility, gr->d_env ? gr->d_env_scratch : nullptr};
+    const int ntex = a.He * a.We;
+    if (gr->d_env) {
+        if (!gr->d_env_scratch) { set_error("shade_backward: d_env needs d_env_scratch [env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
+        if (cudaMemsetAsync(gr->d_env_scratch, 0, (size_t)ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+    }
     {
         TimedScope ts_("shade_bwd", s);
-        if (in->metallic) launch_shade_bwd<true>(a, g, c->env_mode, s); else launch_shade_bwd<false>(a, g, c->env_mode, s);
+        if (in->metallic) launch_shade_bwd<true>(a, g, s); else launch_shade_bwd<false>(a, g, s);
+    }
+    if (gr->d_env) {
+        TimedScope ts_("env_grad_finalize", s);
+        env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, c->env_mode, gr->d_env_scratch, in->env, gr->d_env);
     }
     return check_launch("shade_backward", c->debug, s);
 }

@@ -37,7 +37,8 @@ class ShadeIn(C.Structure):
 
 class ShadeOut(C.Structure):
     _fields_ = [(n, c_fp) for n in ("pbr", "diffuse_light", "specular", "direct", "indirect",
-                                    "mean_visibility", "mean_local", "mean_incident", "mean_global", "pack")] + \
+                                    "mean_visibility", "mean_local", "mean_incident", "mean_global", "pack",
+                                    "sum_direct", "sum_indirect")] + \
                [(n, C.c_int32) for n in ("row_stride", "mean_vis_stride", "mean_stride", "reserved_")]
 
 
@@ -45,7 +46,8 @@ class ShadeGrads(C.Structure):
     _fields_ = [(n, c_fp) for n in ("g_pbr", "g_diffuse_light", "g_specular", "g_direct", "g_indirect",
                                     "g_mean_visibility", "g_mean_local", "g_mean_incident", "g_mean_global",
                                     "d_base_color", "d_roughness", "d_metallic", "d_normals", "d_viewdirs",
-                                    "d_radiance", "d_visibility", "d_env", "g_pack")] + \
+                                    "d_radiance", "d_visibility", "d_env", "g_pack", "sum_direct", "sum_indirect",
+                                    "d_env_scratch")] + \
                [(n, C.c_int32) for n in ("g_row_stride", "g_mean_vis_stride", "g_mean_stride", "reserved_")]
 
 
@@ -129,14 +131,15 @@ class _ShadeFn(torch.autograd.Function):
         cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
                       _p(t["env"]), _p(t["transform"]), _p(scratch), None)
-        cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg), None, 0, 0, 0, 0)
+        sums = torch.empty((2, N, 12), **f32)
+        cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg), None, _p(sums[0]), _p(sums[1]), 0, 0, 0, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
         ctx.cfg = (N, Ns, He, We, int(env_mode), int(bool(debug)))
         ctx.has = (metallic is not None, transform is not None)
         ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
-                                            t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
+                                            t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"], sums,
                                             t["metallic"], t["transform"]) if x is not None])
         return (*outs, mv, ml, mi, mg)
 
@@ -144,8 +147,8 @@ class _ShadeFn(torch.autograd.Function):
     def backward(ctx, g_pbr, g_diff, g_spec, g_dir, g_ind, g_mv, g_ml, g_mi, g_mg):
         L = _L()
         saved = list(ctx.saved_tensors)
-        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env = saved[:9]
-        rest = saved[9:]
+        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env, sums = saved[:10]
+        rest = saved[10:]
         metallic = rest.pop(0) if ctx.has[0] else None
         transform = rest.pop(0) if ctx.has[1] else None
         N, Ns, He, We, env_mode, debug = ctx.cfg
@@ -166,7 +169,8 @@ class _ShadeFn(torch.autograd.Function):
         cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
                       _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), None)
         cg = ShadeGrads(*[_p(x) for x in gs], _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad),
-                        _p(d_vis), _p(d_env), None, 0, 0, 0, 0)
+                        _p(d_vis), _p(d_env), None, _p(sums[0]), _p(sums[1]),
+                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, 0, 0, 0, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
@@ -220,11 +224,14 @@ class _ShadePackedFn(torch.autograd.Function):
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
                       _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]))
         vp, fp = vfeats.data_ptr(), feats.data_ptr()
+        # sums saved for backward: un-split total in training (only pbr / diffuse carry gradients there)
+        sums = torch.empty((1 if is_training else 2, N, 12), **f32)
         if is_training:
-            cout = ShadeOut(vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None, vp + 4 * 12, VS, S, S, 0)
+            cout = ShadeOut(vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None, vp + 4 * 12, _p(sums[0]), None,
+                            VS, S, S, 0)
         else:
             cout = ShadeOut(vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None, vp + 4 * 12,
-                            VS, S, S, 0)
+                            _p(sums[0]), _p(sums[1]), VS, S, S, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
@@ -232,15 +239,15 @@ class _ShadePackedFn(torch.autograd.Function):
         ctx.has = (metallic is not None, transform is not None)
         ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
                                             t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
-                                            t["view3x3"], t["metallic"], t["transform"]) if x is not None])
+                                            t["view3x3"], sums, t["metallic"], t["transform"]) if x is not None])
         return feats, vfeats
 
     @staticmethod
     def backward(ctx, g_feats, g_vfeats):
         L = _L()
         saved = list(ctx.saved_tensors)
-        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env, view3x3 = saved[:10]
-        rest = saved[10:]
+        base_color, roughness, normals, viewdirs, radiance, visibility, dirs, areas, env, view3x3, sums = saved[:11]
+        rest = saved[11:]
         metallic = rest.pop(0) if ctx.has[0] else None
         transform = rest.pop(0) if ctx.has[1] else None
         N, Ns, He, We, env_mode, debug, is_training = ctx.cfg
@@ -268,7 +275,8 @@ class _ShadePackedFn(torch.autograd.Function):
         else:
             gin = (vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None)
         cg = ShadeGrads(*gin, _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad), _p(d_vis),
-                        _p(d_env), vp + 4 * 12, VS, S, S, 0)
+                        _p(d_env), vp + 4 * 12, _p(sums[0]), _p(sums[1]) if sums.shape[0] > 1 else None,
+                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, VS, S, S, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")

@@ -36,8 +36,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.RasterGrads) == 20 * 8
     assert C.sizeof(shading.ShadeCfg) == 6 * 4
     assert C.sizeof(shading.ShadeIn) == 13 * 8
-    assert C.sizeof(shading.ShadeOut) == 10 * 8 + 16
-    assert C.sizeof(shading.ShadeGrads) == 18 * 8 + 16
+    assert C.sizeof(shading.ShadeOut) == 12 * 8 + 16
+    assert C.sizeof(shading.ShadeGrads) == 21 * 8 + 16
 
 
 def test_settings_tuples_have_reference_field_order():

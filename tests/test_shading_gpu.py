@@ -32,16 +32,18 @@ def test_shade_matches_reference_golden(tag):
     # reference evaluated in fp32 is itself only 1e-4..3e-4 relative on some specular peaks (measured
     # against the same reference code run in float64, stored as out64_* by make_golden_shading.py);
     # (ii) acos(d.z) in the lat-long lookup (direct_light_map.py:76) is ill-conditioned at the poles.
-    # So the kernel is held to the float64 truth with the fp32 reference's own error as the yardstick:
-    # relative L2 error <= 3x the reference's, fraction of elements outside 1e-5 abs + 3e-5 rel <= 3x the
-    # reference's + 0.2 %, and every element within 1e-3 rel of the fp32 reference.
+    # So the kernel is held to the float64 truth with the fp32 reference's own error as the yardstick, in
+    # units of the north-star tolerance e = |x - x64| / (1e-5 + 3e-5 |x64|): relative L2 error, the 99th
+    # percentile of e and max e all <= 3x the reference's (floors: 2e-6, 1, 3), and every element within
+    # 1e-3 rel of the fp32 reference.
     for k in ("pbr", "diffuse_light", "specular", "direct", "indirect"):
         a, b, b64 = r[k].detach().cpu().numpy(), g["out_" + k], g["out64_" + k]
         ref_err = _rel(b, b64)
         assert _rel(a, b64) <= max(3.0 * ref_err, 2e-6), (k, _rel(a, b64), ref_err)
         tol = 1e-5 + 3e-5 * np.abs(b64)
-        bad, ref_bad = np.abs(a - b64) > tol, np.abs(b - b64) > tol
-        assert bad.mean() <= 3.0 * ref_bad.mean() + 2e-3, (k, float(bad.mean()), float(ref_bad.mean()))
+        e, e_ref = np.abs(a - b64) / tol, np.abs(b - b64) / tol
+        assert np.quantile(e, 0.99) <= max(3.0 * np.quantile(e_ref, 0.99), 1.0), (k, np.quantile(e, 0.99), np.quantile(e_ref, 0.99))
+        assert e.max() <= max(3.0 * e_ref.max(), 3.0), (k, e.max(), e_ref.max())
         np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-4, err_msg=k)
     np.testing.assert_allclose(r["mean_incident_lights"].detach().cpu().numpy(), g["out_incident_lights"].mean(-2),
                                rtol=1e-3, atol=1e-4)
