@@ -148,19 +148,23 @@ struct RawSample { float wx, wy, wz, r0, r1, r2, vis, area; };
 
 __device__ __forceinline__ void fetch_raw(const ShadeArgs& a, int n, int s0, int lane, RawSample& r) {
     const int s = s0 + lane;
-    const bool ok = s < a.Ns;
-    const size_t is = (size_t)n * a.Ns + (ok ? s : a.Ns - 1);
+    const size_t is = (size_t)n * a.Ns + (s < a.Ns ? s : a.Ns - 1);
     const float* d = a.dirs + is * 3;
     r.wx = __ldg(d); r.wy = __ldg(d + 1); r.wz = __ldg(d + 2);
     const float* rad = a.radiance + is * 3;
-    const float r0 = __ldg(rad), r1 = __ldg(rad + 1), r2 = __ldg(rad + 2);
-    const float vis = __ldg(a.visibility + is), area = __ldg(a.areas + is);
-    r.r0 = ok ? r0 : 0.f; r.r1 = ok ? r1 : 0.f; r.r2 = ok ? r2 : 0.f;
-    r.vis = ok ? vis : 0.f; r.area = ok ? area : 0.f;   // a padded lane contributes nothing
+    r.r0 = __ldg(rad); r.r1 = __ldg(rad + 1); r.r2 = __ldg(rad + 2);
+    r.vis = __ldg(a.visibility + is); r.area = __ldg(a.areas + is);
+    // nothing here may consume the loaded values: the point is to leave them in flight
+}
+// a padded lane (sample index >= Ns) contributes nothing
+__device__ __forceinline__ RawSample mask_raw(const RawSample& r, bool ok) {
+    RawSample o = r;
+    if (!ok) { o.r0 = o.r1 = o.r2 = 0.f; o.vis = 0.f; o.area = 0.f; }
+    return o;
 }
 
 // Raw per-surfel inputs: view direction (all lanes) and, on lanes 0..3, that vertex's normal/roughness.
-struct RawSurfel { float vx, vy, vz, nx, ny, nz, rough, met; };
+struct RawSurfel { float vx, vy, vz, nx, ny, nz, rough, met, base; };
 
 template <bool MET>
 __device__ __forceinline__ void fetch_surfel(const ShadeArgs& a, int n, int lane, RawSurfel& r) {
@@ -171,6 +175,7 @@ __device__ __forceinline__ void fetch_surfel(const ShadeArgs& a, int n, int lane
     r.nx = __ldg(nn); r.ny = __ldg(nn + 1); r.nz = __ldg(nn + 2);
     r.rough = __ldg(a.roughness + (size_t)n * 4 + v);
     r.met = MET ? __ldg(a.metallic + (size_t)n * 4 + v) : 0.f;
+    r.base = __ldg(a.base_color + (size_t)n * 12 + (lane < 12 ? lane : 0));   // lane = 4*ch + v
 }
 
 // Per-sample, vertex-independent quantities (one lane = one light sample of the warp's surfel).
@@ -279,6 +284,8 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         const float Vx = rs.vx * inv_vlen, Vy = rs.vy * inv_vlen, Vz = rs.vz * inv_vlen;
         // per-vertex uniforms, computed by lanes 0..3 and read back as broadcast LDS.128:
         //   [0..3] N, c | [4..7] a2, k, nom1, F0.r | [8..11] F0.g, F0.b, -, -
+        const float base_g = MET ? __shfl_down_sync(full, rs.base, 4) : 0.f;   // lane v: base colour g, b of vertex v
+        const float base_b = MET ? __shfl_down_sync(full, rs.base, 8) : 0.f;
         __syncwarp();
         if (lane < 4) {
             VertexConst c;
@@ -288,12 +295,13 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
             u[4] = c.a2; u[5] = c.k; u[6] = c.nom1;
             if (MET) {
                 const float m = rs.met;
-                u[7] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + lane] * m;
-                u[8] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 4 + lane] * m;
-                u[9] = 0.04f * (1.f - m) + a.base_color[(size_t)n * 12 + 8 + lane] * m;
+                u[7] = 0.04f * (1.f - m) + rs.base * m;
+                u[8] = 0.04f * (1.f - m) + base_g * m;
+                u[9] = 0.04f * (1.f - m) + base_b * m;
             }
         }
         __syncwarp();
+        const RawSurfel sc = rs;   // this surfel's per-lane raw values (normal/roughness of vertex lane&3, base of lane)
         const int n_next = n + stride;
         if (n_next < a.N) fetch_surfel<MET>(a, n_next, lane, rs);
 
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         float m_vis = 0.f, m_g[3] = {0, 0, 0}, m_l[3] = {0, 0, 0};
 
         for (int s0 = 0; s0 < Ns; s0 += 32) {
-            const RawSample cur = raw;
+            const RawSample cur = mask_raw(raw, s0 + lane < Ns);
             if (s0 + 32 < Ns) fetch_raw(a, n, s0 + 32, lane, raw);
             else if (n_next < a.N) fetch_raw(a, n_next, 0, lane, raw);
             Sample sm;
@@ -380,10 +388,10 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         const float s1v = __shfl_down_sync(full, t1, 12);
         const float gl = __shfl_down_sync(full, t0, 3);     // lanes 25..27: global light of the same channel
         if (lane < 12) {
-            const int v = lane & 3;
+            (void)0;
             const size_t o = (size_t)n * out.row_stride + lane;
-            const float base = a.base_color[(size_t)n * 12 + lane];
-            const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
+            const float base = sc.base;
+            const float met = MET ? sc.met : 0.f;
             const float fd = (1.f - met) * base * (1.f / PI_F);
             if (out.sum_direct) out.sum_direct[(size_t)n * 12 + lane] = t0;
             if (!SPLIT) {
@@ -403,9 +411,8 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
                 float* pk = out.pack + (size_t)n * out.row_stride;
                 pk[lane] = base;
                 const int j = lane >> 2;  // view-space axis; n_view[v][j] = sum_i N[v][i] R[i][j], R row-major [3,3]
-                const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
-                pk[12 + lane] = nn[0] * a.view3x3[j] + nn[1] * a.view3x3[3 + j] + nn[2] * a.view3x3[6 + j];
-                if (lane < 4) pk[24 + lane] = a.roughness[(size_t)n * 4 + lane];
+                pk[12 + lane] = sc.nx * a.view3x3[j] + sc.ny * a.view3x3[3 + j] + sc.nz * a.view3x3[6 + j];
+                if (lane < 4) pk[24 + lane] = sc.rough;
             }
         } else if (lane == 24) {
             if (out.mean_vis) out.mean_vis[(size_t)n * out.mean_vis_stride] = t0;
@@ -456,6 +463,31 @@ __global__ void env_grad_finalize_kernel(int ntex, int env_mode, const float* __
     d_env[i] += val;
 }
 
+// Upstream gradients and saved sums of one surfel, on lanes 0..11 (lane = 4*ch + v) plus the uniform
+// mean gradients; fetched one surfel ahead like the other inputs.
+struct RawGrad { float gp, gd, gs, gdi, gin, pk_base, sd, si, gmv, gml[3], gmg[3]; };
+
+__device__ __forceinline__ void fetch_grad(const ShadeGradsK& g, int n, int lane, RawGrad& r) {
+    const int l12 = lane < 12 ? lane : 0;
+    const size_t og = (size_t)n * g.g_row_stride + l12;
+    r.gp = g.g_pbr ? __ldg(g.g_pbr + og) : 0.f;
+    r.gd = g.g_diffuse ? __ldg(g.g_diffuse + og) : 0.f;
+    r.gs = g.g_specular ? __ldg(g.g_specular + og) : 0.f;
+    r.gdi = g.g_direct ? __ldg(g.g_direct + og) : 0.f;
+    r.gin = g.g_indirect ? __ldg(g.g_indirect + og) : 0.f;
+    r.pk_base = g.g_pack ? __ldg(g.g_pack + og) : 0.f;
+    r.sd = __ldg(g.sum_direct + (size_t)n * 12 + l12);
+    r.si = g.sum_indirect ? __ldg(g.sum_indirect + (size_t)n * 12 + l12) : 0.f;
+    const size_t om = (size_t)n * g.g_mean_stride;
+    r.gmv = g.g_mean_vis ? __ldg(g.g_mean_vis + (size_t)n * g.g_mean_vis_stride) : 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        const float gi = g.g_mean_incident ? __ldg(g.g_mean_incident + om + ch) : 0.f;
+        r.gml[ch] = (g.g_mean_local ? __ldg(g.g_mean_local + om + ch) : 0.f) + gi;
+        r.gmg[ch] = (g.g_mean_global ? __ldg(g.g_mean_global + om + ch) : 0.f) + gi;
+    }
+}
+
 template <bool MET, bool ENV_SMEM>
 __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(const ShadeArgs a, const ShadeGradsK g) {
     extern __shared__ __align__(16) float smem_b[];
@@ -481,8 +513,10 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
 
     RawSample raw;
     RawSurfel rs;
+    RawGrad rg;
     if (n < a.N) {
         fetch_surfel<MET>(a, n, lane, rs);
+        fetch_grad(g, n, lane, rg);
         fetch_raw(a, n, 0, lane, raw);
     }
     while (n < a.N) {
@@ -499,39 +533,28 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
             u[4] = c.a2; u[5] = c.k; u[6] = c.nom1; u[7] = c.NoV;
             u[23] = rs.rough;
         }
+        const RawSurfel sc = rs;
+        const RawGrad gc = rg;
         if (lane < 12) {
             const int v = lane & 3, ch = lane >> 2;
-            const size_t og = (size_t)n * g.g_row_stride + lane;
-            const float base_l = a.base_color[(size_t)n * 12 + lane];
-            const float met_l = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
-            const float fd = (1.f - met_l) * base_l * (1.f / PI_F);
-            const float Gp = g.g_pbr ? g.g_pbr[og] : 0.f;
-            const float Gd = g.g_diffuse ? g.g_diffuse[og] : 0.f;
-            const float Gs = g.g_specular ? g.g_specular[og] : 0.f;
-            const float Gdi = g.g_direct ? g.g_direct[og] : 0.f;
-            const float Gin = g.g_indirect ? g.g_indirect[og] : 0.f;
+            const float met_l = MET ? sc.met : 0.f;
+            const float fd = (1.f - met_l) * sc.base * (1.f / PI_F);
             float* u = vu + v * VU_FLOATS;
-            u[8 + ch] = (Gd + (Gp + Gdi) * fd) * inv;
-            u[12 + ch] = (Gd + (Gp + Gin) * fd) * inv;
-            u[16 + ch] = (Gs + Gp + Gdi) * inv;
-            u[20 + ch] = (Gs + Gp + Gin) * inv;
-            u[11 + 4 * ch] = MET ? 0.04f * (1.f - met_l) + base_l * met_l : 0.04f;
+            u[8 + ch] = (gc.gd + (gc.gp + gc.gdi) * fd) * inv;
+            u[12 + ch] = (gc.gd + (gc.gp + gc.gin) * fd) * inv;
+            u[16 + ch] = (gc.gs + gc.gp + gc.gdi) * inv;
+            u[20 + ch] = (gc.gs + gc.gp + gc.gin) * inv;
+            u[11 + 4 * ch] = MET ? 0.04f * (1.f - met_l) + sc.base * met_l : 0.04f;
         }
         __syncwarp();
         const int n_next = n + stride;
-        if (n_next < a.N) fetch_surfel<MET>(a, n_next, lane, rs);
-
-        float gmv = 0.f, gml[3] = {0, 0, 0}, gmg[3] = {0, 0, 0};
-        {
-            const size_t om = (size_t)n * g.g_mean_stride;
-            if (g.g_mean_vis) gmv = g.g_mean_vis[(size_t)n * g.g_mean_vis_stride] * inv;
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float gi = g.g_mean_incident ? g.g_mean_incident[om + ch] : 0.f;
-                gml[ch] = ((g.g_mean_local ? g.g_mean_local[om + ch] : 0.f) + gi) * inv;
-                gmg[ch] = ((g.g_mean_global ? g.g_mean_global[om + ch] : 0.f) + gi) * inv;
-            }
+        if (n_next < a.N) {
+            fetch_surfel<MET>(a, n_next, lane, rs);
+            fetch_grad(g, n_next, lane, rg);
         }
+        const float gmv = gc.gmv * inv;
+        const float gml[3] = {gc.gml[0] * inv, gc.gml[1] * inv, gc.gml[2] * inv};
+        const float gmg[3] = {gc.gmg[0] * inv, gc.gmg[1] * inv, gc.gmg[2] * inv};
 
         // per-vertex partial sums of this lane: 0..2 dN, 3 d_c, 4 d_a2, 5 d_k, 6 d_nom1, 7..9 dF0 (metallic only)
         float acc[4][NACC];
@@ -542,7 +565,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
         float dV[3] = {0, 0, 0};
 
         for (int s0 = 0; s0 < Ns; s0 += 32) {
-            const RawSample cur = raw;
+            const RawSample cur = mask_raw(raw, s0 + lane < Ns);
             if (s0 + 32 < Ns) fetch_raw(a, n, s0 + 32, lane, raw);
             else if (n_next < a.N) fetch_raw(a, n_next, 0, lane, raw);
             const int s = s0 + lane;
@@ -727,27 +750,14 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
             const float dF0 = __shfl_sync(full, totF, (2 * lane) & 31);
             float dm = 0.f;
             if (lane < 12) {
-                const int v = lane & 3;
-                const size_t o12 = (size_t)n * 12 + lane;
-                const size_t og = (size_t)n * g.g_row_stride + lane;
-                const float base = a.base_color[o12];
-                const float met = MET ? a.metallic[(size_t)n * 4 + v] : 0.f;
-                const float gp = g.g_pbr ? g.g_pbr[og] : 0.f;
-                const float dgm = g.sum_direct[o12];
-                float dfd;
-                if (g.sum_indirect) {
-                    const float dlm = g.sum_indirect[o12];
-                    const float gdi = g.g_direct ? g.g_direct[og] : 0.f;
-                    const float gin = g.g_indirect ? g.g_indirect[og] : 0.f;
-                    dfd = gp * (dgm + dlm) + gdi * dgm + gin * dlm;
-                } else {
-                    dfd = gp * dgm;
-                }
+                const float base = sc.base;
+                const float met = MET ? sc.met : 0.f;
+                const float dfd = g.sum_indirect ? gc.gp * (gc.sd + gc.si) + gc.gdi * gc.sd + gc.gin * gc.si : gc.gp * gc.sd;
                 float db = dfd * (1.f - met) * (1.f / PI_F);
                 dm = dfd * (-base * (1.f / PI_F));
                 if (MET) { db += dF0 * met; dm += dF0 * (base - 0.04f); }   // dF0 already carries the 1/Ns of the upstream
-                if (g.g_pack) db += g.g_pack[og];
-                g.d_base_color[o12] = db;
+                db += gc.pk_base;
+                g.d_base_color[(size_t)n * 12 + lane] = db;
             }
             if (MET && g.d_metallic) {  // uniform branch: all lanes shuffle; lanes v, 4+v, 8+v hold the 3 channels
                 const float t = dm + __shfl_down_sync(full, dm, 4) + __shfl_down_sync(full, dm, 8);
