@@ -50,6 +50,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// 128-bit fire-and-forget fp32 vector reduction into global memory (REDG.E.ADD.F32x4, sm_90+);
+// addr must be 16-byte aligned
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // 128-bit read-only streaming load
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 

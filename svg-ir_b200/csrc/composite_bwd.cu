@@ -268,23 +268,312 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
             __syncwarp();
         }
         __syncthreads();
-        // combine the warp-private partial sums; one global atomic per (tile, instance, component)
-        for (int q = tid; q < nb * NCOMP; q += TILE_PIX) {
-            float v = 0.f;
+        // combine the warp-private partial sums; one 128-bit vector reduction (REDG.E.ADD.F32x4) per
+        // (tile, instance, 4 components) -- 18 per instance at the training shape instead of 69 scalar atomics
+        for (int q4 = tid; q4 < nb * (NCOMP / 4); q4 += TILE_PIX) {
+            const int q = q4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int wv = 0; wv < NWARP; wv++) v += acc[wv * BWD_BATCH * NCOMP + q];
-            if (v == 0.f) continue;
+            for (int wv = 0; wv < NWARP; wv++) {
+                const float4 t = *reinterpret_cast<const float4*>(acc + wv * BWD_BATCH * NCOMP + q);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
             const int j = q / NCOMP, k = q - j * NCOMP;
             const int id = ids[j];
             if (k < SVGIR_GEO_GRAD_FLOATS) {
-                if (k >= 9 && k < 12) v *= 10.f;  // dL_dnormal x10 (backward.cu:804)
-                atomicAdd(&geo_grad[(size_t)id * SVGIR_GEO_GRAD_FLOATS + k], v);
+                if (k == 8) { v.y *= 10.f; v.z *= 10.f; v.w *= 10.f; }  // dL_dnormal x10 (backward.cu:804): comps 9..11
+                red_add_f32x4(geo_grad + (size_t)id * SVGIR_GEO_GRAD_FLOATS + k, v);
+            } else if (k < SVGIR_GEO_GRAD_FLOATS + SP) {
+                const int f0 = k - SVGIR_GEO_GRAD_FLOATS;
+                float* dst = dL_dfeatures + (size_t)id * S + f0;
+                if ((S & 3) == 0) red_add_f32x4(dst, v);
+                else {
+                    if (f0 + 0 < S && v.x != 0.f) atomicAdd(dst + 0, v.x);
+                    if (f0 + 1 < S && v.y != 0.f) atomicAdd(dst + 1, v.y);
+                    if (f0 + 2 < S && v.z != 0.f) atomicAdd(dst + 2, v.z);
+                    if (f0 + 3 < S && v.w != 0.f) atomicAdd(dst + 3, v.w);
+                }
+            } else {
+                red_add_f32x4(dL_dvfeatures + (size_t)id * (4 * NV) + (k - SVGIR_GEO_GRAD_FLOATS - SP), v);
             }
-            else if (k < SVGIR_GEO_GRAD_FLOATS + SP) {
-                if (k - SVGIR_GEO_GRAD_FLOATS < S) atomicAdd(&dL_dfeatures[(size_t)id * S + (k - SVGIR_GEO_GRAD_FLOATS)], v);
-            } else atomicAdd(&dL_dvfeatures[(size_t)id * (4 * NV) + (k - SVGIR_GEO_GRAD_FLOATS - SP)], v);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lane-mode backward compositor, used when 8+S+NV+5 <= 32 (stage-2 training S=4/VS=52, stage 1 S=5).
+// Same per-hit math as the kernel above; the reduction is organised so that LANE L OWNS PIXEL-GRADIENT
+// CHANNEL L: for every hit of its warp it reads G[pixel][L] once and accumulates
+//     a0      += h[sel0(L)] * G     (colour / normal / depth / feature gradient, or a geo scalar with G = 1)
+//     a1..a4  += (w*w0..w3) * G     (the four vertex gradients of SV channel L)
+// i.e. 5 FMAs for 3 shared-memory loads.  A warp's result for an instance is complete in registers,
+// so it goes straight to L2 as one scalar and one 128-bit fire-and-forget reduction instruction per
+// (warp, instance) -- no warp-private accumulators, no flush pass, one barrier pair per 32 instances, and
+// 46 KB instead of 81 KB of shared memory per CTA (4 resident CTAs per SM instead of 2).
+#define LBATCH 32
+#define HIT_STRIDE_L 12   // 3 float4 per hit: 128-bit stores/loads are conflict-free at this stride
+
+template <int S_T, int NV_T, bool RGSS>
+__global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
+    const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
+    const float4* __restrict__ rec, const uint2* __restrict__ ranges,
+    const uint32_t* __restrict__ point_list, const float* __restrict__ final_T,
+    const float* __restrict__ final_D, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ gpix_color, const float* __restrict__ gpix_normal,
+    const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
+    const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
+    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures) {
+    constexpr int S = S_T, NV = NV_T;
+    constexpr int SP = (S + 3) & ~3;
+    constexpr int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;
+    constexpr int CH = STRIDE / 4;
+    constexpr int NG = 8 + S + NV;          // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
+    constexpr int GS = NG | 1;              // odd stride
+    static_assert(NG + 5 <= 32, "lane mode needs one lane per gradient channel plus 5 geo lanes");
+
+    extern __shared__ __align__(16) float smem[];
+    float* stage = smem;                                   // [LBATCH][STRIDE]
+    float* G = stage + LBATCH * STRIDE;                    // [256][GS]
+    float* hits = G + TILE_PIX * GS + 3;                   // [NWARP][32][HIT_STRIDE_L] (+3: 256*GS is 0 mod 4 only if GS%4==0... keep 16-B alignment below)
+    hits = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(hits) + 15) & ~uintptr_t(15));
+    int* ids = reinterpret_cast<int*>(hits + NWARP * 32 * HIT_STRIDE_L);  // [LBATCH]
+    __shared__ int tile_max_s;
+
+    const int W = c.W, H = c.H;
+    const int gx = (W + TILE - 1) / TILE;
+    const int tile = blockIdx.x;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    if (total == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int px = (tile % gx) * TILE + (tid & 15), py = (tile / gx) * TILE + (tid >> 4);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix_id = (size_t)W * py + px;
+    const float pxf = (float)px, pyf = (float)py;
+
+    bool surface = true, ppd = true, normalize_depth = true;
+    if (!RGSS) {
+        surface = c.n_config > 0 && c.config[0] > 0;
+        normalize_depth = c.n_config > 1 && c.config[1] > 0;
+        ppd = c.n_config > 2 && c.config[2] > 0;
+    }
+    const bool sv = surface && ppd;
+    const bool feat_to_alpha = !RGSS || c.backward_geometry != 0;
+
+    const float T_final = inside ? final_T[pix_id] : 0.f;
+    const float D_final = (inside && normalize_depth) ? final_D[pix_id] : 0.f;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    // ---- pixel-gradient row (shared: read by the channel lanes; registers: this pixel's own copy) ----
+    float* Grow = G + tid * GS;
+    float gD = 0.f, gDn = 0.f, Kpix = 0.f;
+    float gC[3] = {0, 0, 0}, gN[3] = {0, 0, 0}, gF[S > 0 ? S : 1], gV[NV > 0 ? NV : 1];
+    {
+        float gO = 0.f;
+        if (inside) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) gC[i] = gpix_color[i * HW + pix_id];
+#pragma unroll
+            for (int i = 0; i < 3; i++) gN[i] = surface ? gpix_normal[i * HW + pix_id] : 0.f;
+            gD = gpix_depth[pix_id];
+            gO = gpix_opac[pix_id];
+        }
+        const float omT = 1.f - T_final;
+        gDn = normalize_depth ? gD / omT : gD;
+        Grow[0] = 1.0f;
+        Grow[1] = gC[0]; Grow[2] = gC[1]; Grow[3] = gC[2];
+        Grow[4] = gN[0]; Grow[5] = gN[1]; Grow[6] = gN[2];   // the x10 of backward.cu:804 is applied at the reduction
+        Grow[7] = gDn;
+#pragma unroll
+        for (int i = 0; i < S; i++) { gF[i] = inside ? gpix_feature[i * HW + pix_id] : 0.f; Grow[8 + i] = gF[i]; }
+#pragma unroll
+        for (int i = 0; i < NV; i++) { gV[i] = inside ? gpix_vfeature[i * HW + pix_id] : 0.f; Grow[8 + S + i] = gV[i]; }
+        const float* bg = c.bg;
+        const float bgdot = bg[0] * gC[0] + bg[1] * gC[1] + bg[2] * gC[2];
+        Kpix = gO * T_final - T_final * bgdot;
+        if (normalize_depth) Kpix += gD * D_final / omT / omT * -T_final;
+        else Kpix += -T_final * (10.f * gD);
+    }
+
+    // ---- lane roles ---------------------------------------------------------------------------------
+    //   hit record: [0..3] w*w0..w3 | [4] w | [5,6] dmean | [7,8,9] dconic | [10] dopacity | [11] pixel
+    //   scalar target of a0: geo_grad component (>=0), feature index (encoded as 16+i), or none (-1)
+    int l_gch = 0, l_sel0 = 4, l_k0 = -1;
+    bool l_vf = false;
+    float l_scale = 1.f;
+    if (lane == 0) { l_sel0 = 5; l_k0 = 0; }                                    // dmean.x (G = 1)
+    else if (lane < 4) { l_gch = lane; l_k0 = 6 + (lane - 1); }                // colour
+    else if (lane < 7) { l_gch = lane; l_k0 = 9 + (lane - 4); l_scale = 10.f; }  // normal, x10 (backward.cu:804)
+    else if (lane == 7) { l_gch = 7; l_k0 = 12; }                              // depth
+    else if (lane < 8 + S) { l_gch = lane; l_k0 = 16 + (lane - 8); }           // flat features
+    else if (lane < NG) { l_gch = lane; l_vf = true; }                         // SV channel lane-8-S
+    else if (lane < NG + 5) { l_sel0 = 6 + (lane - NG); l_k0 = 1 + (lane - NG); }  // dmean.y, dconic xyw, dopacity
+
+    // ---- tile-wide traversal start --------------------------------------------------------------
+    if (tid == 0) tile_max_s = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) atomicMax(&tile_max_s, m);
+    }
+    __syncthreads();
+    const int tile_max = min(tile_max_s, total);
+    if (tile_max == 0) return;
+
+    float* my_hits = hits + wid * 32 * HIT_STRIDE_L;
+    float T = T_final, A = 0.f, last_alpha = 0.f, V_last = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    for (int top = tile_max; top > 0; top -= LBATCH) {
+        const int nb = min(LBATCH, top);
+        __syncthreads();  // every warp is done with the previous batch's staged records
+        for (int q = tid; q < nb * CH; q += TILE_PIX) {
+            const int i = q / CH, ch = q - i * CH;
+            const int id = (int)point_list[range.x + top - 1 - i];
+            float4 v;
+            if (ch < REC_F4) {
+                v = __ldg(rec + (size_t)id * REC_F4 + ch);
+                if (ch == 0) ids[i] = id;
+            } else if (ch < REC_F4 + SP / 4) {
+                const int f0 = (ch - REC_F4) * 4;
+                const float* src = features + (size_t)id * S + f0;
+                if ((S & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    v.x = f0 + 0 < S ? __ldg(src + 0) : 0.f;
+                    v.y = f0 + 1 < S ? __ldg(src + 1) : 0.f;
+                    v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
+                    v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
+                }
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + (ch - REC_F4 - SP / 4));
+            }
+            reinterpret_cast<float4*>(stage)[q] = v;
+        }
+        __syncthreads();
+
+        for (int j = 0; j < nb; j++) {
+            const int pos = top - 1 - j;  // 0-based position in the tile's sorted list
+            const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+            const float4 q0 = r[0];
+            const float4 q1 = r[1];
+            PairEval e;
+            bool hit = false;
+            if (pos < last_contributor) hit = eval_alpha<RGSS>(pxf, pyf, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e);
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            if (ballot == 0) continue;
+            if (hit) {
+                const float inv1ma = __frcp_rn(1.f - e.alpha);
+                T = T * inv1ma;
+                const float w = e.alpha * T;
+                float depth_k = q1.z;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                float gzx = 0.f, gzy = 0.f;
+                if (sv) {
+                    const float4 q2 = r[2];
+                    const float4 q3 = r[3];
+                    const float u0 = fma_(e.dx, q2.x, mul_(e.dy, q2.y));
+                    const float u1 = fma_(e.dx, q2.z, mul_(e.dy, q2.w));
+                    depth_k = sub_(q1.z, fma_(q3.x, u0, mul_(q3.y, u1)));
+                    gzx = q3.x * q2.x + q3.y * q2.z;   // J6*J0 + J9*J2 (backward.cu:915)
+                    gzy = q3.x * q2.y + q3.y * q2.w;   // J6*J1 + J9*J3
+                    if (!RGSS) {
+                        float u = fmaf(u0, q1.w, 0.5f), v = fmaf(u1, q3.z, 0.5f);
+                        u = fminf(0.999f, fmaxf(0.001f, u));
+                        v = fminf(0.999f, fmaxf(0.001f, v));
+                        w0 = (1.0f - u) * (1.0f - v);
+                        w1 = u * (1.0f - v);
+                        w2 = (1.0f - u) * v;
+                        w3 = u * v;
+                    }
+                }
+                // V = sum_c value_c * g_c over all blended channels (normal uses the plain gN)
+                const float4 q4 = r[4];
+                float V = q4.x * gC[0] + q4.y * gC[1] + q4.z * gC[2];
+                if (surface) {
+                    const float4 q5 = r[5];
+                    V += q4.w * gN[0] + q5.x * gN[1] + q5.y * gN[2];
+                }
+                V = fmaf(depth_k, gDn, V);
+                const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+                if (feat_to_alpha) {
+#pragma unroll
+                    for (int ch = 0; ch < S; ch++) V = fmaf(f[ch], gF[ch], V);
+                }
+                const float4* vf = reinterpret_cast<const float4*>(f + SP);
+#pragma unroll
+                for (int cidx = 0; cidx < NV; cidx++) {
+                    const float4 t = vf[cidx];
+                    const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
+                    V = fmaf(s4, gV[cidx], V);
+                }
+                A = last_alpha * V_last + (1.f - last_alpha) * A;
+                V_last = V;
+                last_alpha = e.alpha;
+                const float dL_dalpha = (V - A) * T + Kpix * inv1ma;
+                const float dL_ddist = dL_dalpha * q1.y * -0.5f * e.G;
+                float dmx = dL_ddist * 2.f * (q0.z * e.dx + q0.w * e.dy) * ddelx_dx;
+                float dmy = dL_ddist * 2.f * (q1.x * e.dy + q0.w * e.dx) * ddely_dy;
+                if (sv) { dmx -= gD * gzx; dmy -= gD * gzy; }
+                const int rank = __popc(ballot & ((1u << lane) - 1u));
+                float4* h4 = reinterpret_cast<float4*>(my_hits + rank * HIT_STRIDE_L);
+                h4[0] = make_float4(w * w0, w * w1, w * w2, w * w3);
+                h4[1] = make_float4(w, dmx, dmy, dL_ddist * (e.dx * e.dx));
+                h4[2] = make_float4(dL_ddist * (e.dx * e.dy), dL_ddist * (e.dy * e.dy), e.G * dL_dalpha, __int_as_float(tid));
+            }
+            __syncwarp();
+            const int nh = __popc(ballot);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll 2
+            for (int hh = 0; hh < nh; hh++) {
+                const float* h = my_hits + hh * HIT_STRIDE_L;
+                const int pix = __float_as_int(h[11]);
+                const float Gv = G[pix * GS + l_gch];
+                a0 = fmaf(h[l_sel0], Gv, a0);
+                if (NV > 0) {
+                    const float4 hw = *reinterpret_cast<const float4*>(h);
+                    a1 = fmaf(hw.x, Gv, a1); a2 = fmaf(hw.y, Gv, a2);
+                    a3 = fmaf(hw.z, Gv, a3); a4 = fmaf(hw.w, Gv, a4);
+                }
+            }
+            __syncwarp();
+            // this warp's complete contribution to instance j: straight to L2
+            const int id = ids[j];
+            if (l_k0 >= 16) {
+                if (a0 != 0.f) atomicAdd(dL_dfeatures + (size_t)id * S + (l_k0 - 16), a0);
+            } else if (l_k0 >= 0) {
+                if (a0 != 0.f) atomicAdd(geo_grad + (size_t)id * SVGIR_GEO_GRAD_FLOATS + l_k0, a0 * l_scale);
+            } else if (l_vf) {
+                red_add_f32x4(dL_dvfeatures + (size_t)id * (4 * NV) + 4 * (lane - 8 - S), make_float4(a1, a2, a3, a4));
+            }
+        }
+    }
+}
+
+template <int S_T, int NV_T, bool RGSS>
+static int launch_lane_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
+                           const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s) {
+    const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
+    constexpr int SP = (S_T + 3) & ~3;
+    constexpr int stride = SVGIR_REC_FLOATS + SP + 4 * NV_T;
+    constexpr int gs = (8 + S_T + NV_T) | 1;
+    const size_t smem = sizeof(float) * ((size_t)LBATCH * stride + (size_t)TILE_PIX * gs + 8 +
+                                         (size_t)NWARP * 32 * HIT_STRIDE_L + LBATCH);
+    auto k = composite_bwd_lane_kernel<S_T, NV_T, RGSS>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("composite_bwd: cannot reserve %zu B of shared memory", smem);
+        return SVGIR_ERR_CUDA;
+    }
+    { TimedScope ts_("composite_bwd", s); k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
+                                      (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
+                                      st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
+                                      g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
+                                      g.dL_dfeatures, g.dL_dvfeatures); }
+    return check_launch("composite_bwd", c.debug, s);
 }
 
 template <int S_T, int NV_T, bool RGSS>
@@ -321,12 +610,13 @@ int launch_composite_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                          const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s) {
     const int NV = c.VS / 4;
     if (c.variant == SVGIR_VARIANT_RGSS) {
-        if (c.S == 5) return launch_one_bwd<5, 0, true>(c, in, st, g, s);
+        if (c.S == 5) return launch_lane_bwd<5, 0, true>(c, in, st, g, s);
         return launch_one_bwd<-1, -1, true>(c, in, st, g, s);
     }
-    if (c.S == 4 && NV == 13) return launch_one_bwd<4, 13, false>(c, in, st, g, s);
+    // lane mode needs 8+S+NV+5 <= 32 lanes; the eval shape (7,16) and generic shapes use the component-owner kernel
+    if (c.S == 4 && NV == 13) return launch_lane_bwd<4, 13, false>(c, in, st, g, s);
     if (c.S == 7 && NV == 16) return launch_one_bwd<7, 16, false>(c, in, st, g, s);
-    if (c.S == 0 && NV == 0) return launch_one_bwd<0, 0, false>(c, in, st, g, s);
+    if (c.S == 0 && NV == 0) return launch_lane_bwd<0, 0, false>(c, in, st, g, s);
     return launch_one_bwd<-1, -1, false>(c, in, st, g, s);
 }
 

@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
 
     extern __shared__ __align__(16) float smem[];
     float* stage = smem;                                  // [FWD_BATCH][STRIDE]
-    float* wsum = smem + FWD_BATCH * STRIDE;              // [2][FWD_BATCH]
-    int* ids = reinterpret_cast<int*>(wsum + 2 * FWD_BATCH);  // [2][FWD_BATCH]
+    float* wsum = smem + FWD_BATCH * STRIDE;              // [2][8 warps][FWD_BATCH] warp-private blend-weight sums
+    int* ids = reinterpret_cast<int*>(wsum + 2 * 8 * FWD_BATCH);  // [2][FWD_BATCH]
 
     if (num_rendered[1]) return;  // binning overflowed: nothing valid to render
     const int W = c.W, H = c.H;
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
     uint32_t last_contributor = 0;
     bool done = !inside;
 
-    if (tid < 2 * FWD_BATCH) wsum[tid] = 0.f;
+    for (int i = tid; i < 2 * 8 * FWD_BATCH; i += TILE_PIX) wsum[i] = 0.f;
+    const int wid = tid >> 5;
 
     int nbatch = 0;
     for (int base = 0; base < total; base += FWD_BATCH, nbatch++) {
@@ -86,11 +87,11 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
         const int ndone = __syncthreads_count(done);
         // flush the previous batch's per-instance weight sums (one atomic per tile x instance)
         if (nbatch > 0 && tid < FWD_BATCH) {
-            const float wv = wsum[(par ^ 1) * FWD_BATCH + tid];
-            if (wv != 0.f) {
-                atomicAdd(&out_weights[ids[(par ^ 1) * FWD_BATCH + tid]], wv);
-                wsum[(par ^ 1) * FWD_BATCH + tid] = 0.f;
-            }
+            float* ws = wsum + (par ^ 1) * 8 * FWD_BATCH + tid;
+            float wv = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { wv += ws[k * FWD_BATCH]; ws[k * FWD_BATCH] = 0.f; }
+            if (wv != 0.f) atomicAdd(&out_weights[ids[(par ^ 1) * FWD_BATCH + tid]], wv);
         }
         if (ndone == TILE_PIX) break;
         const int nb = min(FWD_BATCH, total - base);
@@ -183,14 +184,16 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
                 last_contributor = (uint32_t)(base + j + 1);
             }
             const float wt = warp_sum(w);
-            if (lane == 0) atomicAdd(&wsum[par * FWD_BATCH + j], wt);
+            if (lane == 0) wsum[(par * 8 + wid) * FWD_BATCH + j] = wt;
         }
     }
     // flush the last computed batch's weight sums
     __syncthreads();
     if (nbatch > 0 && tid < FWD_BATCH) {
         const int par = (nbatch - 1) & 1;
-        const float wv = wsum[par * FWD_BATCH + tid];
+        float wv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) wv += wsum[(par * 8 + k) * FWD_BATCH + tid];
         if (wv != 0.f) atomicAdd(&out_weights[ids[par * FWD_BATCH + tid]], wv);
     }
 
@@ -223,7 +226,7 @@ static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
     const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
     const int SP = (c.S + 3) & ~3;
     const int stride = SVGIR_REC_FLOATS + SP + c.VS;
-    const size_t smem = sizeof(float) * ((size_t)FWD_BATCH * stride + 4 * FWD_BATCH);
+    const size_t smem = sizeof(float) * ((size_t)FWD_BATCH * stride + 2 * 8 * FWD_BATCH + 2 * FWD_BATCH);
     auto k = composite_fwd_kernel<S_T, NV_T, RGSS>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
