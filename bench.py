@@ -99,6 +99,7 @@ def flat_grads(params):
 def run_ours(args):
     import torch.distributed as dist
     from svgir_b200 import _lib, pipeline, shading
+    from svgir_b200 import dist as svdist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -117,13 +118,17 @@ def run_ours(args):
     cam_dev = [pipeline.camera_from_scene(c, dev) for c in cams]
     gt_dev = [torch.from_numpy(g).to(dev) for g in gts]
     params = pc.trainable() + [env]
+    # N>1: .grad of every parameter is a view into one flat buffer, reduced with ONE NCCL all-reduce
+    # per step (svgir_b200/dist.py); N=1 lets autograd hand over its gradient tensors.
+    bucket = svdist.FlatGradBucket(params) if world > 1 else None
 
     def step(i):
         v = (i * world + rank) % N_VIEWS
-        loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
-        if world > 1:
-            fg = flat_grads(params)
-            dist.all_reduce(fg)  # per-surfel gradient exchange over NVLink
+        if bucket is None:
+            return pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
+        bucket.zero()
+        loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)], zero_grad=False)
+        bucket.all_reduce()  # per-surfel gradient exchange over NVLink
         return loss, res
 
     def sync_all():

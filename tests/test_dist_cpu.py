@@ -1,0 +1,101 @@
+"""View-sharded data parallel host logic on CPU: gloo, world_size 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from svgir_b200 import dist as D
+
+
+def test_view_partition_covers_every_view_once():
+    for n_views in (1, 7, 8, 200):
+        for world in (1, 2, 4, 8):
+            got = sorted(v for r in range(world) for v in D.views_for_rank(n_views, r, world))
+            assert got == list(range(n_views))
+            sizes = [len(D.views_for_rank(n_views, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_relight_grid_partition():
+    # C5 shape: 200 views x 5 env maps over 8 ranks (eval_relighting_tensoIR.py:138-143, 303-331)
+    items = [D.relight_grid_for_rank(200, 5, r, 8) for r in range(8)]
+    flat = sorted(x for it in items for x in it)
+    assert flat == [(e, v) for e in range(5) for v in range(200)]
+    assert {len(it) for it in items} == {125}
+    with pytest.raises(ValueError):
+        D.relight_grid_for_rank(4, 2, 3, 2)
+
+
+def test_flat_bucket_views_single_process():
+    a = torch.randn(5, 3, requires_grad=True)
+    b = torch.randn(7, requires_grad=True)
+    bk = D.FlatGradBucket([a, b])
+    assert bk.numel == 16 + 8 and bk.attached()
+    (a.sum() * 2 + (b * b).sum()).backward()
+    assert bk.attached(), "autograd must accumulate into the bucket views in place"
+    assert torch.allclose(bk.view(0), torch.full((5, 3), 2.0))
+    assert torch.allclose(bk.view(1), 2 * b.detach())
+    bk.zero()
+    assert float(bk.flat.abs().sum()) == 0.0
+    a.grad = None  # something dropped the view: all_reduce() re-gathers and re-attaches
+    (a.sum() * 3).backward()
+    bk.all_reduce()
+    assert bk.attached() and torch.allclose(a.grad, torch.full((5, 3), 3.0))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, dev = D.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world) and dev.type == "cpu"
+    torch.manual_seed(0)  # replicas: identical parameters on every rank
+    base = torch.randn(50, 12, requires_grad=True)
+    rough = torch.randn(50, 4, requires_grad=True)
+    env = torch.randn(8, 16, 3, requires_grad=True)
+    bk = D.FlatGradBucket([base, rough, env])
+    targets = [torch.full((50, 12), float(v)) for v in range(5)]
+
+    def render_and_backward(v):  # stands in for pipeline.training_step(view v): per-view loss
+        loss = ((base - targets[v]) ** 2).sum() * (v + 1) + (rough * (v + 1)).sum() + (env * env).sum()
+        loss.backward()
+        return loss
+
+    total, mine = D.data_parallel_step(list(range(5)), render_and_backward, bk)
+    assert mine == D.views_for_rank(5, rank, world)
+    # the expected gradient is the sum over ALL five views, whichever rank rendered them
+    exp_base = sum(2 * (base.detach() - targets[v]) * (v + 1) for v in range(5))
+    exp_rough = torch.full((50, 4), float(sum(v + 1 for v in range(5))))
+    exp_env = 5 * 2 * env.detach()
+    ok = (torch.allclose(base.grad, exp_base, rtol=1e-5, atol=1e-5) and torch.allclose(rough.grad, exp_rough)
+          and torch.allclose(env.grad, exp_env, rtol=1e-5, atol=1e-5) and bk.attached())
+    t = D.max_over_ranks(float(rank + 1), dev)
+    q.put((rank, bool(ok), t, len(mine)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [2.0, 2.0]          # max over ranks
+    assert sorted(r[3] for r in res) == [2, 3]        # 5 views dealt 3 + 2
