@@ -11,6 +11,7 @@
 #ifndef SVGIR_B200_H_
 #define SVGIR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -256,6 +257,48 @@ int svgir_direct_light_forward(int n, int env_h, int env_w, int env_mode, const 
 int svgir_direct_light_backward(int n, int env_h, int env_w, int env_mode, const float* env,
                                 const float* transform, const float* dirs, const float* g_out,
                                 float* d_env, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LBVH over the surfels + visibility trace.  Replaces bvh_tracing._C (submodules/bvh/src/bindings.cpp:9-11):
+ * create_bvh (src/bvh.cu:9-27 -> construct_bvh, src/construct.cu:147-265) and trace_bvh_opacity
+ * (src/bvh.cu:89-116 -> trace_bvh_opacity_cuda, src/trace.cu:196-286), plus the torch code of
+ * RayTracer.__init__ that prepares the leaf boxes (submodules/bvh/__init__.py:29-57). */
+typedef struct svgir_bvh {
+    int32_t P;               /* leaves (surfels) */
+    int32_t reserved_;
+    int32_t* nodes;          /* [2P-1,5] (parent, left, right, object, count) -- the reference layout */
+    float* aabbs;            /* [2P-1,6] (lower xyz, upper xyz); rows P-1.. hold the leaf boxes on entry to
+                                svgir_bvh_build and the Morton-sorted leaf boxes on return */
+    uint64_t* morton;        /* [P] (code30 << 31) | object, ascending */
+    float* packed;           /* [max(P-1,1),16] traversal records written by svgir_bvh_build (16-B aligned) */
+    void* workspace;         /* svgir_bvh_workspace_bytes(P) bytes, 256-B aligned; scratch of the build only */
+    size_t workspace_bytes;
+} svgir_bvh;
+
+size_t svgir_bvh_workspace_bytes(int P);
+
+/* RayTracer.__init__ (submodules/bvh/__init__.py:31-57): initialises nodes (-1, counts 0/1) and aabbs
+ * (+-100000) and writes the 8-corner leaf boxes mu +- 3 s R e_k into rows P-1.. ; bit-identical to the
+ * reference's torch evaluation. rotations [P,4] un-normalised quaternions (r,x,y,z), 16-B aligned. */
+int svgir_bvh_leaf_aabbs(int P, const float* means3D, const float* scales, const float* rotations,
+                         int32_t* nodes, float* aabbs, void* stream);
+
+/* construct_bvh: Morton codes of the leaf-box centroids, stable sort, Karras hierarchy, bottom-up boxes.
+ * nodes / aabbs / morton come out bit-identical to the reference. */
+int svgir_bvh_build(const svgir_bvh* bvh, void* stream);
+
+/* Packs the per-surfel arguments of trace_bvh_opacity (means3D [P,3], symm_inv [P,6] = upper triangle of
+ * Sigma^-1, opacity [P], normals [P,3]) into one 64-byte record per surfel (leaf_records [P,16]). */
+int svgir_bvh_pack_leaves(int P, const float* means3D, const float* symm_inv, const float* opacity,
+                          const float* normals, float* leaf_records, void* stream);
+
+/* trace_bvh_opacity: ray r has direction rays_d[r] and origin rays_o[r / rays_per_origin] + origin_offset *
+ * rays_d[r] (rays_per_origin = 1 and origin_offset = 0 give the reference call; RayTracer.trace_visibility
+ * adds 0.05 d, submodules/bvh/__init__.py:63). Writes contributes [n_rays] int32 (0 for early-out rays) and
+ * visibility [n_rays] (transmittance, or 0 once it drops below 0.9). */
+int svgir_bvh_trace_opacity(const svgir_bvh* bvh, long long n_rays, const float* rays_o, const float* rays_d,
+                            int rays_per_origin, float origin_offset, const float* leaf_records,
+                            int32_t* contributes, float* visibility, void* stream);
 
 #ifdef __cplusplus
 }

@@ -125,3 +125,30 @@ class RefSvgss:
         if rc != 0:
             raise RuntimeError("reference backward failed")
         return g
+
+
+class RefBvh:
+    """The reference LBVH (submodules/bvh construct.cu / trace.cu, unmodified) behind
+    oracle/ref_harness_bvh.cu; mirrors RayTracer (submodules/bvh/__init__.py:28-71)."""
+
+    def __init__(self, nodes: torch.Tensor, aabbs: torch.Tensor, means3D, scales, rotations):
+        self.L = C.CDLL(os.path.join(_HERE, "_ref", "libbvh_ref.so"))
+        P = means3D.shape[0]
+        self.nodes, self.aabbs = nodes.contiguous().clone(), aabbs.contiguous().clone()
+        self.morton = torch.zeros((P,), dtype=torch.int64, device=means3D.device)
+        rc = self.L.ref_bvh_build(P, _p(means3D.contiguous()), _p(scales.contiguous()), _p(rotations.contiguous()),
+                                  _p(self.nodes), _p(self.aabbs), _p(self.morton))
+        if rc != 0:
+            raise RuntimeError(f"ref_bvh_build failed ({rc})")
+
+    def trace_opacity(self, rays_o, rays_d, means3D, cov_inv, opacity, normals):
+        rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+        shape = rays_o.shape[:-1]
+        contrib = torch.zeros(shape, dtype=torch.int32, device=rays_o.device)
+        vis = torch.ones(shape, dtype=torch.float32, device=rays_o.device)
+        rc = self.L.ref_bvh_trace_opacity(rays_o.numel() // 3, _p(self.nodes), _p(self.aabbs), _p(rays_o), _p(rays_d),
+                                          _p(means3D.contiguous()), _p(cov_inv.contiguous()), _p(opacity.contiguous()),
+                                          _p(normals.contiguous()), _p(contrib), _p(vis))
+        if rc != 0:
+            raise RuntimeError(f"ref_bvh_trace_opacity failed ({rc})")
+        return contrib, vis

@@ -129,5 +129,6 @@ EXPORTED_SYMBOLS = [
     "svgir_last_error", "svgir_version", "svgir_raster_preprocess", "svgir_raster_render",
     "svgir_raster_backward", "svgir_mark_visible", "svgir_shade_forward", "svgir_shade_backward",
     "svgir_direct_light_forward", "svgir_direct_light_backward", "svgir_timing_enable",
-    "svgir_timing_collect", "svgir_launch_count",
+    "svgir_timing_collect", "svgir_launch_count", "svgir_bvh_workspace_bytes", "svgir_bvh_leaf_aabbs",
+    "svgir_bvh_build", "svgir_bvh_pack_leaves", "svgir_bvh_trace_opacity",
 ]

@@ -102,3 +102,22 @@ def rel_l2(a, b):
     d = np.linalg.norm(a - b)
     n = max(np.linalg.norm(b), 1e-30)
     return d / n
+
+
+def make_bvh_case(P, n_rays, seed=11, surfel=True, size=0.08):
+    """Random occluder cloud + random rays for the LBVH / visibility tests: centres uniform in the unit
+    cube, random orientations, disc-like scales (tiny z when `surfel`), rays from random points."""
+    rng = np.random.default_rng(seed)
+    means = rng.uniform(-1, 1, (P, 3)).astype(np.float32)
+    q = rng.standard_normal((P, 4)).astype(np.float32)  # un-normalised on purpose (build_rotation normalises)
+    sxy = np.exp(rng.normal(np.log(size), 0.4, (P, 2)))
+    sz = np.full((P, 1), 1e-4) if surfel else np.exp(rng.normal(np.log(0.03), 0.3, (P, 1)))
+    scales = np.concatenate([sxy, sz], 1).astype(np.float32)
+    opacity = (1 / (1 + np.exp(-rng.normal(0.5, 2.0, (P,))))).astype(np.float32)
+    qn = q / np.linalg.norm(q, axis=1, keepdims=True)
+    r, x, y, z = qn.T
+    normals = np.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], 1).astype(np.float32)
+    ro = rng.uniform(-1, 1, (n_rays, 3)).astype(np.float32)
+    rd = rng.standard_normal((n_rays, 3))
+    rd = (rd / np.linalg.norm(rd, axis=1, keepdims=True)).astype(np.float32)
+    return dict(means=means, scales=scales, rotations=q, opacity=opacity, normals=normals, rays_o=ro, rays_d=rd)
