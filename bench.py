@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -198,18 +198,20 @@ def run_ours(args):
             dist.all_reduce(flat_grads(m.trainable() + [envp]))
         return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
 
-    for i in range(max(1, min(args.warmup, 2))):
-        e2e_step(i)
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    e1.record()
-    sync_all()
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(t_ms.item()) / 1e3)
+    e2e_value = None
+    if not args.no_e2e:
+        for i in range(max(1, min(args.warmup, 2))):
+            e2e_step(i)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        sync_all()
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        e2e_value = world * args.steps / (float(t_ms.item()) / 1e3)
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -238,7 +240,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "views_per_step": world, "parallelism": f"view-dp{world}",
                        "l2": "working set > L2 (per-sample light buffers 614 MB/iter)", "R": R, "P_vis": Pv},
             "clocks": clk,
-            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+            "e2e": {"value": round(e2e_value, 3) if e2e_value else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
@@ -249,6 +251,92 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(1, 0)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def run_relight(args):
+    """C3-eval (BASELINE.json configs[2]): relighting frame = render_equation over all 300k surfels with
+    Ns=384 samples under a fixed HDR env map (EnvLight semantics, scene/envmap.py:54-72) + svgss forward
+    with the eval G-buffer (S=7, VS=64) at 800x800. Forward only; reports ms/frame. Under torchrun the
+    view x envmap grid is sharded round-robin with no collective."""
+    import torch.distributed as dist
+    from svgir_b200 import _lib, pipeline, scene, shading
+    from svgir_b200 import dist as svdist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    ns, n_env = 384, 5
+    cloud = scene.make_surfels(P_SURFELS, seed=1236)
+    mats = scene.make_materials(cloud, ns, seed=1237)
+    pc = pipeline.model_from_scene(cloud, mats, dev, requires_grad=False)
+    cams = [pipeline.camera_from_scene(scene.look_at_camera(WIDTH, HEIGHT, v, N_VIEWS), dev) for v in range(N_VIEWS)]
+    rng = np.random.default_rng(7)
+    envs = [torch.from_numpy(rng.uniform(0, 4, (32, 64, 3)).astype(np.float32)).to(dev) for _ in range(n_env)]
+    bg = torch.zeros(3, device=dev)
+    grid = svdist.relight_grid_for_rank(N_VIEWS, n_env, rank, world)
+
+    def frame(i):
+        e, v = grid[i % len(grid)]  # (env, view), env-major
+        with torch.no_grad():
+            return pipeline.render_view(cams[v], pc, (envs[e], shading.MODE_FIXED), bg, is_training=False)
+
+    for i in range(args.warmup):
+        res = frame(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.launch_count(reset=True)
+    _lib.timing_collect(reset=True)
+    _lib.timing_enable(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        res = frame(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    _lib.timing_enable(False)
+    launches = _lib.launch_count()
+    kt = {}
+    for k in ("shade_fwd", "composite_fwd", "preprocess", "emit", "sort_small", "tile_scan"):
+        t, n = _lib.timing_collect(k)
+        kt[k] = t / max(n, 1)
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_frame = float(t_ms.item()) / args.steps
+    if rank == 0:
+        pk, pk_src = peaks()
+        alg = P_SURFELS * (ns * 32 + 124) + P_SURFELS * 4 * (12 * 5 + 7)
+        ach = alg / (kt["shade_fwd"] * 1e-3) / 1e9 if kt["shade_fwd"] > 0 else 0.0
+        print(json.dumps({
+            "metric": "relight ms/frame", "value": round(ms_frame / world, 4), "unit": "ms/frame", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_frame, 4), "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3-eval: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
+                                   "S=7/VS=64 at %dx%d, fixed HDR env map" % (ns, P_SURFELS // 1000, WIDTH, HEIGHT),
+                       "grid": "%d views x %d env maps, round-robin over ranks" % (N_VIEWS, n_env),
+                       "l2": "working set > L2 (light buffers 3.7 GB/frame)", "R": int(res["num_rendered"])},
+            "clocks": clk, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "shade_fwd", "achieved": round(ach, 1), "peak": pk["hbm_gbs"],
+                         "peak_source": pk_src, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
+                         "algorithmic_bytes": int(alg), "avg_ms": round(kt["shade_fwd"], 4)},
+            "kernels_ms": {k: round(v, 4) for k, v in kt.items()}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -392,12 +480,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--workload", default="train", choices=["train", "relight"],
+                    help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference_cuda":
         run_reference_cuda(args)
+    elif args.workload == "relight":
+        run_relight(args)
     else:
         run_ours(args)
 

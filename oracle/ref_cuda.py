@@ -127,6 +127,91 @@ class RefSvgss:
         return g
 
 
+class RefRgss:
+    """One forward (+ optional backward) of the reference stage-1 rasteriser
+    (rgss-rasterization/cuda_rasterizer, harness oracle/ref_harness_rgss.cu)."""
+
+    def __init__(self):
+        self.L = _lib("rgss")
+        self.h = C.c_void_p(self.L.ref_rgss_create())
+
+    def close(self):
+        if self.h:
+            self.L.ref_rgss_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, *, bg, means3D, features, colors, opacity, scales, rotations, scale_modifier, viewmatrix,
+                projmatrix, tanfovx, tanfovy, cx, cy, H, W, sh, degree, campos, computer_pseudo_normal=False,
+                debug=False):
+        dev = means3D.device
+        P, S = means3D.shape[0], features.shape[1]
+        M = sh.shape[1] if sh is not None and sh.numel() else 0
+        f = dict(dtype=torch.float32, device=dev)
+        o = dict(color=torch.zeros((3, H, W), **f), normal=torch.zeros((3, H, W), **f),
+                 opacity=torch.zeros((1, H, W), **f), depth=torch.zeros((1, H, W), **f),
+                 feature=torch.zeros((S, H, W), **f), pseudo_normal=torch.zeros((3, H, W), **f),
+                 surface_xyz=torch.zeros((3, H, W), **f), weights=torch.zeros((P, 1), **f),
+                 radii=torch.zeros((P,), dtype=torch.int32, device=dev))
+        self.args = dict(bg=bg, means3D=means3D, features=features, colors=colors, opacity=opacity, scales=scales,
+                         rotations=rotations, scale_modifier=scale_modifier, viewmatrix=viewmatrix,
+                         projmatrix=projmatrix, tanfovx=tanfovx, tanfovy=tanfovy, H=H, W=W, sh=sh, degree=degree,
+                         campos=campos, P=P, S=S, M=M)
+        torch.cuda.synchronize()
+        R = self.L.ref_rgss_forward(
+            self.h, P, S, degree, M, _p(bg), W, H, _p(means3D), _p(sh), _p(colors), _p(features), _p(opacity),
+            _p(scales), C.c_float(scale_modifier), _p(rotations), _p(None), _p(viewmatrix), _p(projmatrix),
+            _p(campos), C.c_float(tanfovx), C.c_float(tanfovy), C.c_float(cx), C.c_float(cy), 0,
+            int(computer_pseudo_normal), _p(o["color"]), _p(o["normal"]), _p(o["opacity"]), _p(o["depth"]),
+            _p(o["feature"]), _p(o["pseudo_normal"]), _p(o["surface_xyz"]), _p(o["weights"]), _p(o["radii"]),
+            int(debug))
+        if R < 0:
+            raise RuntimeError("reference rgss forward failed")
+        o["num_rendered"] = R
+        self.out = o
+        return o
+
+    def state(self, name, shape, dtype):
+        ptr = self.L.ref_rgss_state(self.h, name.encode())
+        if not ptr:
+            raise KeyError(name)
+        out = torch.empty(shape, dtype=dtype, device="cuda")
+        if out.numel():
+            rt = C.CDLL("libcudart.so")
+            rt.cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(ptr), C.c_size_t(out.numel() * out.element_size()), 3)
+        torch.cuda.synchronize()
+        return out
+
+    def backward(self, dL_dcolor, dL_dnormal, dL_dopac, dL_ddepth, dL_dfeature, backward_geometry=True):
+        a = self.args
+        P, S, M = a["P"], a["S"], a["M"]
+        f = dict(dtype=torch.float32, device=a["means3D"].device)
+        g = dict(dL_dmeans2D=torch.zeros((P, 3), **f), dL_dconic=torch.zeros((P, 2, 2), **f),
+                 dL_dopacity=torch.zeros((P, 1), **f), dL_dcolors=torch.zeros((P, 3), **f),
+                 dL_dnormal=torch.zeros((P, 3), **f), dL_ddepth=torch.zeros((P, 1), **f),
+                 dL_dfeatures=torch.zeros((P, S), **f), dL_dmeans3D=torch.zeros((P, 3), **f),
+                 dL_dcov3D=torch.zeros((P, 6), **f), dL_dsh=torch.zeros((P, M, 3), **f),
+                 dL_dscales=torch.zeros((P, 3), **f), dL_drotations=torch.zeros((P, 4), **f))
+        torch.cuda.synchronize()
+        rc = self.L.ref_rgss_backward(
+            self.h, P, S, a["degree"], M, _p(a["bg"]), a["W"], a["H"], _p(a["means3D"]), _p(a["sh"]),
+            _p(a["features"]), _p(a["colors"]), _p(a["scales"]), C.c_float(a["scale_modifier"]), _p(a["rotations"]),
+            _p(None), _p(a["viewmatrix"]), _p(a["projmatrix"]), _p(a["campos"]), C.c_float(a["tanfovx"]),
+            C.c_float(a["tanfovy"]), _p(self.out["radii"]), _p(dL_dcolor), _p(dL_dnormal), _p(dL_dopac),
+            _p(dL_ddepth), _p(dL_dfeature), _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]), _p(g["dL_dopacity"]),
+            _p(g["dL_dcolors"]), _p(g["dL_dnormal"]), _p(g["dL_ddepth"]), _p(g["dL_dfeatures"]),
+            _p(g["dL_dmeans3D"]), _p(g["dL_dcov3D"]), _p(g["dL_dsh"]), _p(g["dL_dscales"]), _p(g["dL_drotations"]),
+            int(backward_geometry), 0)
+        if rc != 0:
+            raise RuntimeError("reference rgss backward failed")
+        return g
+
+
 class RefBvh:
     """The reference LBVH (submodules/bvh construct.cu / trace.cu, unmodified) behind
     oracle/ref_harness_bvh.cu; mirrors RayTracer (submodules/bvh/__init__.py:28-71)."""
