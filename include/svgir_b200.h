@@ -300,6 +300,62 @@ int svgir_bvh_trace_opacity(const svgir_bvh* bvh, long long n_rays, const float*
                             int rays_per_origin, float origin_offset, const float* leaf_records,
                             int32_t* contributes, float* visibility, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Incident-ray sampling.  Replaces sample_incident_rays (scene/gaussian_model.py:23-31) ->
+ * fibonacci_sphere_sampling (utils/graphics_utils.py:9-37) + rotation_between_z (utils/sh_utils.py:36-68).
+ * normals [N,3]; rand_u [N] = the per-surfel torch.rand offset in [0,1) used when training, or NULL
+ * (random_rotate=False); incident_dirs [N,Ns,3]; incident_areas [N,Ns,1] (= 2*pi) or NULL. */
+int svgir_sample_incident_rays(int N, int Ns, const float* normals, const float* rand_u, float* incident_dirs,
+                               float* incident_areas, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SH-lit render_equation with per-surfel scalar materials (metallic workflow).  Replaces the R3DG-style
+ * operators the reference declares in rgss-rasterization/render_equation.h:7-46 and defines in
+ * rgss-rasterization/render_equation.cu (RenderEquationForwardCUDA :555-729, _complex :55-277,
+ * RenderEquationBackwardCUDA :280-550).  base_color/normals/viewdirs [P,3], roughness/metallic [P,1],
+ * incidents_shs [P,S_incident,3], direct_shs [1,S_direct,3], visibility_shs [P,S_vis,1]; S_* <= 16. */
+typedef struct svgir_req_sh_cfg {
+    int32_t P, S_incident, S_direct, S_vis, sample_num;
+    int32_t is_training;   /* simple forward only: add rand_float*2*pi to the sample azimuth (:583) */
+    int32_t legacy_exact;  /* backward: 1 = the reference's arithmetic including its known slips (dL_dn_d_i
+                              overwritten :406, incident-SH loop over S_direct :453, no clamp masks);
+                              0 = analytic gradient of the forward */
+    int32_t debug;
+} svgir_req_sh_cfg;
+
+typedef struct svgir_req_sh_in {
+    const float* base_color; const float* roughness; const float* metallic; const float* normals;
+    const float* viewdirs; const float* incidents_shs; const float* direct_shs; const float* visibility_shs;
+    const float* rand_float;  /* [P,sample_num,1] uniform randoms (torch::rand in the reference, :705) or NULL */
+} svgir_req_sh_in;
+
+typedef struct svgir_req_sh_out {
+    float* pbr;            /* [P,3] */
+    float* incident_dirs;  /* [P,sample_num,3] */
+    float* diffuse_light;  /* [P,3] */
+    /* the eight extra results of RenderEquationForwardCUDA_complex: all NULL (simple forward) or all set */
+    float* incident_lights; float* local_incident_lights; float* global_incident_lights; /* [P,sample_num,3] */
+    float* incident_visibility;   /* [P,sample_num,1] */
+    float* local_diffuse_light;   /* [P,3] */
+    float* accum;                 /* [P,1] */
+    float* rgb_d; float* rgb_s;   /* [P,3] */
+} svgir_req_sh_out;
+
+typedef struct svgir_req_sh_grads {
+    const float* incident_dirs;      /* [P,sample_num,3] as returned by the forward */
+    const float* dL_dpbr;            /* [P,3] */
+    const float* dL_ddiffuse_light;  /* [P,3] */
+    float* dL_dbase_color; float* dL_droughness; float* dL_dmetallic; float* dL_dnormals; float* dL_dviewdirs;
+    float* dL_dincidents_shs;        /* [P,S_incident,3] */
+    float* dL_ddirect_shs;           /* [1,S_direct,3]; zeroed by the library, exact sum (the reference races here) */
+    float* dL_dvisibility_shs;       /* [P,S_vis,1] */
+} svgir_req_sh_grads;
+
+int svgir_render_equation_sh_forward(const svgir_req_sh_cfg* cfg, const svgir_req_sh_in* in,
+                                     const svgir_req_sh_out* out, void* stream);
+int svgir_render_equation_sh_backward(const svgir_req_sh_cfg* cfg, const svgir_req_sh_in* in,
+                                      const svgir_req_sh_grads* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

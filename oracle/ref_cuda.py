@@ -212,6 +212,63 @@ class RefRgss:
         return g
 
 
+class RefReq:
+    """The reference's SH render_equation kernels (rgss-rasterization/render_equation.cu) behind
+    oracle/ref_harness_req.cu. Inputs: dict from oracle.render_equation_sh_oracle.make_inputs (CUDA tensors)."""
+    ORDER = ("base_color", "roughness", "metallic", "normals", "viewdirs", "incidents_shs", "direct_shs", "visibility_shs")
+
+    def __init__(self):
+        import torch  # noqa: F401  (libtorch must be loaded before the harness)
+        self.L = C.CDLL(os.path.join(_HERE, "_ref", "libreq_ref.so"))
+
+    def _sizes(self, t):
+        return t["base_color"].shape[0], t["incidents_shs"].shape[1], t["direct_shs"].shape[1], t["visibility_shs"].shape[1]
+
+    def forward(self, t, sample_num, is_training=False, rand_float=None):
+        P, Si, Sd, Sv = self._sizes(t)
+        f = dict(dtype=torch.float32, device=t["base_color"].device)
+        o = dict(incident_dirs=torch.zeros((P, sample_num, 3), **f), pbr=torch.zeros((P, 3), **f),
+                 diffuse_light=torch.zeros((P, 3), **f))
+        torch.cuda.synchronize()
+        rc = self.L.ref_req_forward(P, Si, Sd, Sv, *[_p(t[k]) for k in self.ORDER], sample_num, int(is_training),
+                                    _p(rand_float), _p(o["incident_dirs"]), _p(o["pbr"]), _p(o["diffuse_light"]))
+        if rc != 0:
+            raise RuntimeError("reference render_equation forward failed")
+        return o
+
+    def forward_complex(self, t, sample_num):
+        P, Si, Sd, Sv = self._sizes(t)
+        f = dict(dtype=torch.float32, device=t["base_color"].device)
+        z = lambda *s: torch.zeros(s, **f)
+        o = dict(incident_dirs=z(P, sample_num, 3), pbr=z(P, 3), incident_lights=z(P, sample_num, 3),
+                 local_incident_lights=z(P, sample_num, 3), global_incident_lights=z(P, sample_num, 3),
+                 incident_visibility=z(P, sample_num, 1), diffuse_light=z(P, 3), local_diffuse_light=z(P, 3),
+                 accum=z(P, 1), rgb_d=z(P, 3), rgb_s=z(P, 3))
+        torch.cuda.synchronize()
+        rc = self.L.ref_req_forward_complex(P, Si, Sd, Sv, *[_p(t[k]) for k in self.ORDER], sample_num,
+                                            *[_p(o[k]) for k in ("incident_dirs", "pbr", "incident_lights",
+                                                                 "local_incident_lights", "global_incident_lights",
+                                                                 "incident_visibility", "diffuse_light",
+                                                                 "local_diffuse_light", "accum", "rgb_d", "rgb_s")])
+        if rc != 0:
+            raise RuntimeError("reference render_equation forward_complex failed")
+        return o
+
+    def backward(self, t, sample_num, incident_dirs, g_pbr, g_dl):
+        P, Si, Sd, Sv = self._sizes(t)
+        f = dict(dtype=torch.float32, device=t["base_color"].device)
+        z = lambda *s: torch.zeros(s, **f)
+        g = dict(dL_dbase_color=z(P, 3), dL_droughness=z(P, 1), dL_dmetallic=z(P, 1), dL_dnormals=z(P, 3),
+                 dL_dviewdirs=z(P, 3), dL_dincidents_shs=z(P, Si, 3), dL_ddirect_shs=z(1, Sd, 3),
+                 dL_dvisibility_shs=z(P, Sv, 1))
+        torch.cuda.synchronize()
+        rc = self.L.ref_req_backward(P, Si, Sd, Sv, *[_p(t[k]) for k in self.ORDER], sample_num, _p(incident_dirs),
+                                     _p(g_pbr), _p(g_dl), *[_p(v) for v in g.values()])
+        if rc != 0:
+            raise RuntimeError("reference render_equation backward failed")
+        return g
+
+
 class RefBvh:
     """The reference LBVH (submodules/bvh construct.cu / trace.cu, unmodified) behind
     oracle/ref_harness_bvh.cu; mirrors RayTracer (submodules/bvh/__init__.py:28-71)."""
