@@ -110,6 +110,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the extension is missing
+    # default: shade only the surfels that survive the rasteriser's culling (identical images and gradients,
+    # tests/test_culled_shading_gpu.py); --shade-all shades every surfel in the reference's order
+    pipeline.SHADE_CULLED = bool(args.shade_all)
 
     cloud, mats, cams, gts = build_host_workload()
     pc = pipeline.model_from_scene(cloud, mats, dev)
@@ -121,14 +124,27 @@ def run_ours(args):
     # N>1: .grad of every parameter is a view into one flat buffer, reduced with ONE NCCL all-reduce
     # per step (svgir_b200/dist.py); N=1 lets autograd hand over its gradient tensors.
     bucket = svdist.FlatGradBucket(params) if world > 1 else None
+    # The step is captured once into a CUDA graph (pipeline.GraphedTrainingStep) and replayed: one
+    # cudaGraphLaunch per iteration, camera + ground truth copied into static buffers, binning capacity
+    # checked after every replay. --eager runs the same step launch by launch instead.
+    runner = None if args.eager else pipeline.GraphedTrainingStep(pc, env, bg, cam_dev[0], gt_dev[0], bucket=bucket)
 
-    def step(i):
+    def eager_step(i):
         v = (i * world + rank) % N_VIEWS
         if bucket is None:
             return pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
         bucket.zero()
         loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)], zero_grad=False)
         bucket.all_reduce()  # per-surfel gradient exchange over NVLink
+        return loss, res
+
+    def step(i):
+        if runner is None:
+            return eager_step(i)
+        v = (i * world + rank) % N_VIEWS
+        loss, res = runner(cam_dev[v], gt_dev[i % len(gt_dev)])
+        if bucket is not None:
+            bucket.all_reduce()
         return loss, res
 
     def sync_all():
@@ -144,7 +160,8 @@ def run_ours(args):
     stats = {"R": int(res["num_rendered"]), "P_vis": int(res["visibility_filter"].sum())}
     _lib.launch_count(reset=True)
     _lib.timing_collect(reset=True)
-    _lib.timing_enable(True)
+    if runner is None:
+        _lib.timing_enable(True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -157,8 +174,15 @@ def run_ours(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
+    launches = _lib.launch_count() if runner is None else runner.launches_per_step * args.steps
+    if runner is not None:
+        # per-kernel device times: the same kernels on the same inputs launched one by one, each bracketed
+        # by CUDA events on the launching stream (events cannot be timed inside a replayed graph)
+        _lib.timing_enable(True)
+        for i in range(min(args.steps, 8)):
+            eager_step(args.warmup + i)
+        torch.cuda.synchronize()
     _lib.timing_enable(False)
-    launches = _lib.launch_count()
     ktimes = {k: _lib.timing_collect(k) for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess",
                                                   "preprocess_bwd", "emit", "sort_small", "tile_scan")}
     _lib.timing_collect(reset=True)
@@ -169,6 +193,33 @@ def run_ours(args):
     value = world * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ----------------------------
+    # A training iteration's INPUTS are the camera and the ground-truth image (the surfel parameters and the
+    # per-surfel light buffers are optimiser state resident on the GPU, exactly as in the reference, whose
+    # rasteriser API takes CUDA tensors): every step copies them from pinned host memory, runs the step
+    # through the public call and reads the loss and num_rendered back. `e2e_cold` additionally re-uploads
+    # ALL parameters and light buffers every step (the worst case: nothing resident).
+    gt_host = [torch.from_numpy(g).pin_memory() for g in gts]
+    cam_host = [pipeline.ViewCamera(HEIGHT, WIDTH, c.tanfovx, c.tanfovy, *[torch.from_numpy(getattr(c, k)).pin_memory()
+                for k in ("viewmatrix", "projmatrix", "campos", "patch_bbox", "prcppoint")]) for c in cams]
+    h2d_bytes = gt_host[0].numel() * 4 + sum(getattr(cam_host[0], k).numel() * 4 for k in
+                                             ("world_view_transform", "full_proj_transform", "camera_center", "patch_bbox", "prcppoint"))
+
+    def e2e_step(i):
+        v = (i * world + rank) % N_VIEWS
+        if runner is not None:
+            loss, res = runner(cam_host[v], gt_host[i % len(gt_host)])   # H2D into the graph's static inputs
+        else:
+            c = cam_host[v]
+            cam = pipeline.ViewCamera(HEIGHT, WIDTH, c.tanfovx, c.tanfovy, *[getattr(c, k).to(dev, non_blocking=True) for k in
+                                      ("world_view_transform", "full_proj_transform", "camera_center", "patch_bbox", "prcppoint")])
+            if bucket is not None:
+                bucket.zero()
+            loss, res = pipeline.training_step(cam, pc, env, bg, gt_host[i % len(gt_host)].to(dev, non_blocking=True),
+                                               zero_grad=bucket is None)
+        if bucket is not None:
+            bucket.all_reduce()
+        return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
+
     host = {}
     for name, arr in (("xyz", cloud.means3D), ("opacity", cloud.opacity), ("scaling", cloud.scales),
                       ("rotation", cloud.rotations), ("shs", cloud.shs), ("base_color", mats["base_color"]),
@@ -177,52 +228,55 @@ def run_ours(args):
                       ("incident_dirs", mats["incident_dirs"]), ("incident_areas", mats["incident_areas"]),
                       ("env", mats["env_param"]), ("gt", gts[0])):
         host[name] = torch.from_numpy(arr).pin_memory()
-    cam_host = [{k: torch.from_numpy(getattr(c, k)).pin_memory() for k in ("viewmatrix", "projmatrix", "campos",
-                                                                           "patch_bbox", "prcppoint")} for c in cams]
-    h2d_bytes = sum(t.numel() * 4 for t in host.values()) + sum(t.numel() * 4 for t in cam_host[0].values())
+    cold_bytes = sum(t.numel() * 4 for t in host.values()) + h2d_bytes - gt_host[0].numel() * 4
 
-    def e2e_step(i):
+    def cold_step(i):
         v = (i * world + rank) % N_VIEWS
         d = {k: t.to(dev, non_blocking=True) for k, t in host.items()}
-        c = {k: t.to(dev, non_blocking=True) for k, t in cam_host[v].items()}
+        c = cam_host[v]
+        cam = pipeline.ViewCamera(HEIGHT, WIDTH, c.tanfovx, c.tanfovy, *[getattr(c, k).to(dev, non_blocking=True) for k in
+                                  ("world_view_transform", "full_proj_transform", "camera_center", "patch_bbox", "prcppoint")])
         m = pipeline.SurfelModel(d["xyz"], d["opacity"], d["scaling"], d["rotation"], d["shs"], d["base_color"],
                                  d["roughness"], d["shading_normal"], d["radiance"], d["visibility"],
                                  d["incident_dirs"], d["incident_areas"])
         for t in m.trainable():
             t.requires_grad_(True)
         envp = d["env"].requires_grad_(True)
-        cam = pipeline.ViewCamera(HEIGHT, WIDTH, cams[v].tanfovx, cams[v].tanfovy, c["viewmatrix"], c["projmatrix"],
-                                  c["campos"], c["patch_bbox"], c["prcppoint"])
         loss, res = pipeline.training_step(cam, m, envp, bg, d["gt"], zero_grad=False)
         if world > 1:
             dist.all_reduce(flat_grads(m.trainable() + [envp]))
-        return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
+        return float(loss.item()), int(res["num_rendered"])
 
-    e2e_value = None
-    if not args.no_e2e:
-        for i in range(max(1, min(args.warmup, 2))):
-            e2e_step(i)
+    def timed(fn, n):
+        for i in range(2):
+            fn(i)
         sync_all()
         e0.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        for i in range(n):
+            fn(2 + i)
         e1.record()
         sync_all()
-        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        e2e_value = world * args.steps / (float(t_ms.item()) / 1e3)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n / (float(t.item()) / 1e3)
+
+    e2e_value = e2e_cold = None
+    if not args.no_e2e:
+        e2e_value = timed(e2e_step, args.steps)
+        e2e_cold = timed(cold_step, min(args.steps, 5))
 
     if rank == 0:
         pk, pk_src = peaks()
         R, Pv = stats["R"], stats["P_vis"]
         b_rec = 104 + 4 * S_FEAT + 4 * VS_FEAT
         b_pix = 4 * (3 + 3 + 1 + 1 + S_FEAT + VS_FEAT // 4)
+        n_sh = P_SURFELS if args.shade_all else Pv
         alg = {  # SURVEY.md 8(d) algorithmic bytes per launch, at this view's measured R / P_vis
             "composite_bwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12) + Pv * 4 * (15 + S_FEAT + VS_FEAT),
             "composite_fwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12),
-            "shade_fwd": P_SURFELS * (NS * 32 + 124) + P_SURFELS * 4 * (12 * 5 + S_FEAT),
-            "shade_bwd": P_SURFELS * (NS * 32 + 124) + P_SURFELS * 4 * (12 * 5 + S_FEAT) + P_SURFELS * 4 * (12 + 4 + 12 + 3),
+            "shade_fwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT),
+            "shade_bwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT) + n_sh * 4 * (12 + 4 + 12 + 3),
         }
         kt = {k: (v[0] / max(v[1], 1)) for k, v in ktimes.items()}  # avg ms per launch
         dom = max(("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd"), key=lambda k: kt[k])
@@ -238,10 +292,18 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "views_per_step": world, "parallelism": f"view-dp{world}",
-                       "l2": "working set > L2 (per-sample light buffers 614 MB/iter)", "R": R, "P_vis": Pv},
+                       "l2": "working set > L2 (per-sample light buffers 614 MB/iter)", "R": R, "P_vis": Pv,
+                       "shading": "all %d surfels (reference order)" % P_SURFELS if args.shade_all else
+                                  "the %d surfels that survive culling (preprocess runs first; images and gradients identical)" % Pv},
             "clocks": clk,
             "e2e": {"value": round(e2e_value, 3) if e2e_value else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": 12},
+                    "d2h_bytes_per_step": 12, "inputs": "camera matrices + ground-truth image from pinned host memory; loss + "
+                    "num_rendered read back; parameters / light buffers resident (optimiser state)"},
+            "e2e_cold": {"value": round(e2e_cold, 3) if e2e_cold else None, "unit": UNIT, "h2d_bytes_per_step": int(cold_bytes),
+                         "note": "worst case: every parameter and light buffer re-uploaded each step (eager path)"},
+            "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/step)" % runner.launches_per_step,
+            "kernel_timing": "CUDA events around each launch on the launching stream" + ("" if runner is None else
+                             ", separate eager pass of the same kernels/inputs right after the timed region"),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
                          "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
@@ -274,6 +336,7 @@ def run_relight(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    pipeline.SHADE_CULLED = bool(args.shade_all)
     ns, n_env = 384, 5
     cloud = scene.make_surfels(P_SURFELS, seed=1236)
     mats = scene.make_materials(cloud, ns, seed=1237)
@@ -481,6 +544,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
+    ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "relight"],
                     help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")
     args = ap.parse_args()

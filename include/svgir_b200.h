@@ -101,6 +101,8 @@ typedef struct svgir_raster_state {
     float* final_T;           /* [H*W] */
     float* final_D;           /* [H*W] */
     uint32_t* n_contrib;      /* [H*W] */
+    int32_t* vis_list;        /* [P] optional: indices of the surfels with radii > 0 (unordered), or NULL */
+    int32_t* vis_count;       /* [1] optional: length of vis_list (device) */
 } svgir_raster_state;
 
 /* Outputs of the forward pass; caller zero-fills out_weights, everything else is fully written.
@@ -120,7 +122,9 @@ typedef struct svgir_raster_out {
 
 /* Forward, part 1: per-surfel preprocess (forward.cu:230-396), per-tile counting and the tile
  * scan (replaces InclusiveSum + D2H, rasterizer_impl.cu:307-311). Leaves R in
- * state->num_rendered[0]; needs rec..num_rendered of `state`. */
+ * state->num_rendered[0]; needs rec..num_rendered of `state`. Does not read in->features / in->vfeatures
+ * (they may still be NULL: the shading that produces them can run between part 1 and part 2, restricted
+ * to state->vis_list, which this call fills when the pointer is set). */
 int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
                             svgir_raster_state* state, svgir_raster_out* out, void* stream);
 
@@ -196,6 +200,12 @@ typedef struct svgir_shade_in {
     const float* env_transform;  /* [3,3] or NULL (envmap.py:58-61) */
     float* env_act_scratch;      /* [env_h,env_w,3] scratch for the activated map */
     const float* view3x3;        /* [3,3] = viewmatrix[:3,:3] (row-vector convention), only for `pack` */
+    /* Optional work list (device): only surfels surfel_list[0 .. *surfel_count) are shaded / differentiated;
+     * the rows of every other surfel are left untouched in all outputs (the caller zero-fills them).
+     * svgir_raster_preprocess produces the list of surfels that survive culling (state.vis_list), so
+     * that culled surfels -- which no pixel reads and whose gradients are zero -- cost nothing. */
+    const int32_t* surfel_list;  /* [<=N] surfel indices, or NULL = all N surfels */
+    const int32_t* surfel_count; /* [1] device-side length of surfel_list */
 } svgir_shade_in;
 
 typedef struct svgir_shade_out {

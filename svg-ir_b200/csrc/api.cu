@@ -38,6 +38,8 @@ static long long g_launches = 0;
 void timing_begin(const char* name, cudaStream_t s) {
     g_launches++;
     if (!g_timing || g_nrec >= 4096) { g_open = -1; return; }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { g_open = -1; return; }  // no timing events inside a graph capture
     TimingRec& r = g_recs[g_nrec];
     r.name = name;
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { g_open = -1; return; }
@@ -49,7 +51,7 @@ void timing_end(cudaStream_t s) {
     g_open = -1;
 }
 
-static int validate(const svgir_raster_cfg* c, const svgir_raster_in* in) {
+static int validate(const svgir_raster_cfg* c, const svgir_raster_in* in, bool need_features = true) {
     if (!c || !in) { set_error("null cfg/in"); return SVGIR_ERR_INVALID; }
     if (c->P < 0 || c->W <= 0 || c->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", c->P, c->W, c->H); return SVGIR_ERR_INVALID; }
     if (c->S < 0 || c->S > SVGIR_MAX_S) { set_error("S=%d outside [0,%d]", c->S, SVGIR_MAX_S); return SVGIR_ERR_INVALID; }
@@ -61,8 +63,8 @@ static int validate(const svgir_raster_cfg* c, const svgir_raster_in* in) {
     if (in->shs && c->M < (c->sh_degree + 1) * (c->sh_degree + 1)) { set_error("M=%d too small for SH degree %d", c->M, c->sh_degree); return SVGIR_ERR_INVALID; }
     if (!in->cov3D_precomp && (!in->scales || !in->rotations)) { set_error("provide scales+rotations or cov3D_precomp"); return SVGIR_ERR_INVALID; }
     if (!in->rotations) { set_error("rotations are required (surfel normals)"); return SVGIR_ERR_INVALID; }
-    if (c->S > 0 && !in->features) { set_error("features missing"); return SVGIR_ERR_INVALID; }
-    if (c->VS > 0 && !in->vfeatures) { set_error("vfeatures missing"); return SVGIR_ERR_INVALID; }
+    if (need_features && c->S > 0 && !in->features) { set_error("features missing"); return SVGIR_ERR_INVALID; }
+    if (need_features && c->VS > 0 && !in->vfeatures) { set_error("vfeatures missing"); return SVGIR_ERR_INVALID; }
     if (((uintptr_t)in->rotations & 15) || (c->VS > 0 && ((uintptr_t)in->vfeatures & 15)) ||
         (c->S > 0 && (c->S & 3) == 0 && ((uintptr_t)in->features & 15))) {
         set_error("rotations/features/vfeatures must be 16-byte aligned");
@@ -80,6 +82,27 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
     const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
     const float pz = V[2] * x + V[6] * y + V[10] * z + V[14];
     present[idx] = pz > 0.2f;
+}
+
+// Work list of the surfels that survived culling (radii > 0): block-local ballot scan, ONE global atomic
+// per block. Order across blocks is arbitrary -- consumers treat it as a set.
+__global__ void __launch_bounds__(256) compact_visible_kernel(int P, const int32_t* __restrict__ radii,
+                                                              int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    __shared__ int wsum[8];
+    __shared__ int base_s;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool v = idx < P && radii[idx] > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) wsum[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) { const int c = wsum[w]; wsum[w] = t; t += c; }
+        base_s = t ? atomicAdd(count, t) : 0;
+    }
+    __syncthreads();
+    if (v) list[base_s + wsum[wid] + __popc(m & ((1u << lane) - 1u))] = idx;
 }
 
 }  // namespace svgir
@@ -123,7 +146,7 @@ long long svgir_launch_count(int reset) {
 
 int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
                             svgir_raster_state* st, svgir_raster_out* out, void* stream) {
-    int rc = validate(cfg, in);
+    int rc = validate(cfg, in, false);  // the per-surfel preprocess does not read features / vfeatures
     if (rc) return rc;
     if (!st || !out || !st->rec || !st->tile_count || !st->num_rendered || !out->radii) {
         set_error("state/out buffers missing");
@@ -133,6 +156,14 @@ int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* 
     if (cfg->P == 0) return SVGIR_OK;
     rc = launch_preprocess(*cfg, *in, *st, *out, s);
     if (rc) return rc;
+    if (st->vis_list) {
+        if (!st->vis_count) { set_error("vis_list needs vis_count"); return SVGIR_ERR_INVALID; }
+        if (cudaMemsetAsync(st->vis_count, 0, sizeof(int32_t), s) != cudaSuccess) { set_error("memset vis_count failed"); return SVGIR_ERR_CUDA; }
+        { TimedScope ts_("compact_visible", s);
+          compact_visible_kernel<<<(cfg->P + 255) / 256, 256, 0, s>>>(cfg->P, out->radii, st->vis_list, st->vis_count); }
+        rc = check_launch("compact_visible", cfg->debug, s);
+        if (rc) return rc;
+    }
     return launch_tile_scan(*cfg, *st, s);
 }
 

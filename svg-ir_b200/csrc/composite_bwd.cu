@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
     const float* __restrict__ gpix_color, const float* __restrict__ gpix_normal,
     const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
     const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
-    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures) {
+    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures,
+    const int32_t* __restrict__ num_rendered) {
     constexpr bool GENERIC = S_T < 0;
     const int S = GENERIC ? c.S : S_T;
     const int NV = GENERIC ? c.VS / 4 : NV_T;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
     const int tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
-    if (total == 0) return;
+    if (total == 0 || num_rendered[1]) return;  // empty tile, or the forward's bins overflowed (nothing valid)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int px = (tile % gx) * TILE + (tid & 15), py = (tile / gx) * TILE + (tid >> 4);
     const bool inside = px < W && py < H;
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const float* __restrict__ gpix_color, const float* __restrict__ gpix_normal,
     const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
     const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
-    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures) {
+    float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures,
+    const int32_t* __restrict__ num_rendered) {
     constexpr int S = S_T, NV = NV_T;
     constexpr int SP = (S + 3) & ~3;
     constexpr int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const int tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
-    if (total == 0) return;
+    if (total == 0 || num_rendered[1]) return;  // empty tile, or the forward's bins overflowed (nothing valid)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int px = (tile % gx) * TILE + (tid & 15), py = (tile / gx) * TILE + (tid >> 4);
     const bool inside = px < W && py < H;
@@ -572,7 +574,7 @@ static int launch_lane_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                                       (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
                                       st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
                                       g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
-                                      g.dL_dfeatures, g.dL_dvfeatures); }
+                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered); }
     return check_launch("composite_bwd", c.debug, s);
 }
 
@@ -602,7 +604,7 @@ static int launch_one_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                                       (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
                                       st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
                                       g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
-                                      g.dL_dfeatures, g.dL_dvfeatures); }
+                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered); }
     return check_launch("composite_bwd", c.debug, s);
 }
 

@@ -102,7 +102,14 @@ struct ShadeArgs {
     const float* visibility;  // [N,Ns]
     const float* dirs;        // [N,Ns,3]
     const float* areas;       // [N,Ns]
+    const int32_t* list;       // optional work list: shade only surfels list[0 .. *list_count)
+    const int32_t* list_count;
 };
+
+// Surfel handled by work slot `slot` (identity without a work list); a.N once the work is exhausted.
+__device__ __forceinline__ int surfel_at(const ShadeArgs& a, int slot, int count) {
+    return slot < count ? (a.list ? __ldg(a.list + slot) : slot) : a.N;
+}
 
 // Sum over the warp of NP (a power of two <= 32) per-lane values, "transposed": instead of 5 shuffles
 // per value, each step exchanges half of the remaining slots, so the whole reduction costs ~NP
@@ -271,8 +278,11 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
     const int Ns = a.Ns;
     const float inv = 1.f / (float)Ns;
     const int stride = gridDim.x * WPC;
-    int n = blockIdx.x * WPC + (threadIdx.x >> 5);
+    const int count = a.list_count ? min(__ldg(a.list_count), a.N) : a.N;
+    int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
+    int n = surfel_at(a, slot, count);
     if (n >= a.N) return;
+    int n_next = surfel_at(a, slot + stride, count);
 
     RawSample raw;
     RawSurfel rs;
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         }
         __syncwarp();
         const RawSurfel sc = rs;   // this surfel's per-lane raw values (normal/roughness of vertex lane&3, base of lane)
-        const int n_next = n + stride;
+        const int n_next2 = surfel_at(a, slot + 2 * stride, count);   // work-list entry two ahead (the one-ahead surfel is fetched now)
         if (n_next < a.N) fetch_surfel<MET>(a, n_next, lane, rs);
 
         // D = sum ndi*A, S = sum f_s*ndi*A; [0]: env ("direct") light or the total when !SPLIT, [1]: cached radiance
@@ -423,7 +433,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
         } else if (lane >= 28 && lane < 31) {
             if (out.mean_global) out.mean_global[(size_t)n * out.mean_stride + (lane - 28)] = t0;
         }
-        n = n_next;
+        n = n_next; n_next = n_next2; slot += stride;
     }
 }
 
@@ -509,7 +519,10 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
     const float inv = 1.f / (float)Ns;
     const bool want_rad = g.d_radiance != nullptr;
     const int stride = gridDim.x * WPC;
-    int n = blockIdx.x * WPC + (threadIdx.x >> 5);
+    const int count = a.list_count ? min(__ldg(a.list_count), a.N) : a.N;
+    int slot = blockIdx.x * WPC + (threadIdx.x >> 5);
+    int n = surfel_at(a, slot, count);
+    int n_next = surfel_at(a, slot + stride, count);
 
     RawSample raw;
     RawSurfel rs;
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
             u[11 + 4 * ch] = MET ? 0.04f * (1.f - met_l) + sc.base * met_l : 0.04f;
         }
         __syncwarp();
-        const int n_next = n + stride;
+        const int n_next2 = surfel_at(a, slot + 2 * stride, count);
         if (n_next < a.N) {
             fetch_surfel<MET>(a, n_next, lane, rs);
             fetch_grad(g, n_next, lane, rg);
@@ -774,7 +787,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
             o[1] = (dV[1] - Vy * vdot) * inv_vlen;
             o[2] = (dV[2] - Vz * vdot) * inv_vlen;
         }
-        n = n_next;
+        n = n_next; n_next = n_next2; slot += stride;
     }
 }
 
@@ -885,6 +898,8 @@ static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, Sha
     a.base_color = in->base_color; a.roughness = in->roughness; a.metallic = in->metallic;
     a.normals = in->normals; a.viewdirs = in->viewdirs; a.radiance = in->radiance;
     a.visibility = in->visibility; a.dirs = in->incident_dirs; a.areas = in->incident_areas;
+    a.list = in->surfel_list; a.list_count = in->surfel_list ? in->surfel_count : nullptr;
+    if (in->surfel_list && !in->surfel_count) { set_error("shade: surfel_list needs surfel_count"); return SVGIR_ERR_INVALID; }
     return SVGIR_OK;
 }
 

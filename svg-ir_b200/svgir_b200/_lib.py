@@ -47,6 +47,7 @@ class RasterState(C.Structure):
         ("tile_count", c_fp), ("tile_cursor", c_fp), ("ranges", c_fp), ("big_tiles", c_fp),
         ("num_rendered", c_fp), ("keys", c_fp), ("point_list", c_fp), ("sorted_keys", c_fp),
         ("cap_R", C.c_int64), ("final_T", c_fp), ("final_D", c_fp), ("n_contrib", c_fp),
+        ("vis_list", c_fp), ("vis_count", c_fp),
     ]
 
 

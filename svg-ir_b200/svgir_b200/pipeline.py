@@ -13,8 +13,23 @@ from typing import Optional
 
 import torch
 
-from . import shading
+from . import raster, shading
 from ._lib import launch_count
+
+_CONFIG_CACHE: dict = {}
+# render_view default: True = shade every surfel like the reference (svgss.py:116-135); False = shade only
+# the surfels that survive the rasteriser's culling (identical images and gradients, see render_view).
+SHADE_CULLED = True
+
+
+def _config_tensor(config, device) -> torch.Tensor:
+    """pc.config as a device tensor (svgss.py:66 builds it with torch.tensor(...).cuda() every call: a
+    pageable H2D copy per view; cached here, which also keeps render_view capturable into a CUDA graph)."""
+    key = (tuple(float(x) for x in config), str(device))
+    t = _CONFIG_CACHE.get(key)
+    if t is None:
+        t = _CONFIG_CACHE[key] = torch.tensor(key[0], dtype=torch.float32, device=device)
+    return t
 
 
 @dataclass
@@ -56,8 +71,7 @@ class ViewCamera:
 
 def rgb_to_srgb(img):
     """utils/graphics_utils.py:198-213."""
-    t = torch.tensor(0.0031308, device=img.device)
-    return torch.where(img > 0.0031308, torch.pow(torch.max(img, t), 1.0 / 2.4) * 1.055 - 0.055, 12.92 * img).clamp(0, 1)
+    return torch.where(img > 0.0031308, torch.pow(img.clamp_min(0.0031308), 1.0 / 2.4) * 1.055 - 0.055, 12.92 * img).clamp(0, 1)
 
 
 def camera_from_scene(cam, device) -> ViewCamera:
@@ -78,10 +92,18 @@ def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
 
 
 def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier=1.0,
-                is_training=True, debug=False) -> dict:
+                is_training=True, debug=False, shade_culled: Optional[bool] = None) -> dict:
     """svgss.py:15-262 without the application objects. Returns the same result keys the hot path
-    produces (render, depth, pbr, normal, opacity, base_color, roughness, diffuse, ...)."""
-    from svgss_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    produces (render, depth, pbr, normal, opacity, base_color, roughness, diffuse, ...).
+
+    shade_culled=False runs the rasteriser's per-surfel preprocess FIRST and shades only the surfels that
+    survive culling (radii > 0): the compositor never reads the others and their gradients are zero, so
+    every image and every gradient is unchanged; only the per-surfel by-product `diffuse_light` is zero
+    for culled surfels (it feeds the optional lambda_light regulariser, svgss.py:359-364, which the TensoIR
+    recipe disables: script/run_tensoir.sh:37-38). Default: the module switch SHADE_CULLED."""
+    from svgss_rasterization import GaussianRasterizationSettings, GaussianRasterizer, preprocess_geometry
+    if shade_culled is None:
+        shade_culled = SHADE_CULLED
     means3D = pc.xyz
     screenspace_points = torch.zeros_like(means3D, requires_grad=True) + 0
     try:
@@ -93,14 +115,20 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
         tanfovy=cam.tanfovy, bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=cam.world_view_transform,
         projmatrix=cam.full_proj_transform, patch_bbox=cam.patch_bbox, prcppoint=cam.prcppoint,
         sh_degree=pc.active_sh_degree, campos=cam.camera_center, prefiltered=False, debug=debug,
-        config=torch.tensor(pc.config, dtype=torch.float32, device=means3D.device))
+        config=_config_tensor(pc.config, means3D.device))
+    work = None
+    if not shade_culled:
+        prestate, work = preprocess_geometry(raster_settings, means3D, pc.opacity, pc.scaling, pc.rotation, None,
+                                             pc.shs, None)
+        raster_settings = raster_settings._replace(prestate=prestate)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
 
     viewdirs = torch.nn.functional.normalize(cam.camera_center - means3D, dim=-1)
     # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel
     features, vfeatures = shading.shade_and_pack(
         pc.base_color, pc.roughness, pc.shading_normal, viewdirs, pc.radiance, env_light, pc.visibility,
-        pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug)
+        pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
+        work=work)
 
     (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
      rendered_vfeature, weights, radii) = rasterizer(
@@ -132,7 +160,8 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
         "base_color": opacity_filter(rgb_to_srgb(base)), "roughness": opacity_filter(rough),
         "local_lights": opacity_filter(rgb_to_srgb(local)), "visibility": opacity_filter(vis),
         "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
-        "num_rendered": num_rendered, "weights": weights, "diffuse_light": vfeatures[:, 40:52] if is_training else None})
+        "num_rendered": num_rendered, "weights": weights,
+        "raster_state": num_rendered._st if isinstance(num_rendered, raster.LazyCount) else None, "diffuse_light": vfeatures[:, 40:52] if is_training else None})
     return res
 
 
@@ -153,6 +182,119 @@ def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg,
     loss = image_loss(res, gt_image)
     loss.backward()
     return loss, res
+
+
+class GraphedTrainingStep:
+    """`training_step` captured ONCE into a CUDA graph and replayed: one cudaGraphLaunch per iteration
+    instead of ~150 host-side launches and tensor allocations, and no mid-step device->host read
+    (the reference blocks on num_rendered inside every forward, rasterizer_impl.cu:311, and again at
+    svgss.py:186). The rasteriser runs in its "async" count mode inside the graph: the binning buffers
+    have a fixed capacity (2x the largest num_rendered seen), the (num_rendered, overflow) pair lands
+    in pinned host memory, and __call__ checks it after the replay -- on overflow the capacity is
+    raised, the graph re-captured and the SAME step re-run, so the results are always those of a
+    complete render. Per-step inputs (camera matrices, ground-truth image) are copied into static
+    device buffers; results and .grad tensors are static buffers overwritten by the next call.
+
+    The camera intrinsics (H, W, tan_fov) are baked into the graph; a different value re-captures.
+    With `bucket` (dist.FlatGradBucket) the .grad views are zeroed inside the graph and accumulated
+    in place, ready for bucket.all_reduce() after the call.
+    """
+
+    def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
+                 gt_image: torch.Tensor, bucket=None, warmup: int = 2):
+        self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
+        dev = pc.xyz.device
+        self.dev = dev
+        self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                              cam.world_view_transform.clone(), cam.full_proj_transform.clone(),
+                              cam.camera_center.clone(), cam.patch_bbox.clone(), cam.prcppoint.clone())
+        self.gt = gt_image.clone()
+        self.graph = None
+        self.loss = None
+        self.res = None
+        self.captures = 0
+        self.launches_per_step = 0
+        self.warmup = warmup
+
+    def _params(self):
+        return self.pc.trainable() + [self.env]
+
+    def _zero(self):
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            for t in self._params():
+                t.grad = None
+
+    def _capture(self):
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):  # eager: sizes the binning hint, warms allocators / lazy inits
+                self._zero()
+                with raster.count_mode("speculative"):
+                    _, r = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False)
+            R = int(r["num_rendered"])
+            raster.reserve(self.dev, self.pc.xyz.shape[0], self.cam.image_width, self.cam.image_height,
+                           int(R * raster.ASYNC_SLACK) + raster.ASYNC_MARGIN)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self._zero()
+        raster.prepare_capture(1)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(self.graph):
+            if self.bucket is not None:
+                self.bucket.zero()
+            with raster.count_mode("async", owner_resolves=True):
+                self.loss, self.res = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False)
+        self.launches_per_step = launch_count() - n0  # svgir kernels inside the graph
+        self.captures += 1
+
+    def load_inputs(self, cam: ViewCamera, gt_image: torch.Tensor):
+        c = self.cam
+        if (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy) != (c.image_height, c.image_width, c.tanfovx, c.tanfovy):
+            self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                                  c.world_view_transform, c.full_proj_transform, c.camera_center, c.patch_bbox,
+                                  c.prcppoint)
+            c = self.cam
+            self.graph = None
+        c.world_view_transform.copy_(cam.world_view_transform, non_blocking=True)
+        c.full_proj_transform.copy_(cam.full_proj_transform, non_blocking=True)
+        c.camera_center.copy_(cam.camera_center, non_blocking=True)
+        c.patch_bbox.copy_(cam.patch_bbox, non_blocking=True)
+        c.prcppoint.copy_(cam.prcppoint, non_blocking=True)
+        if gt_image is not self.gt:
+            self.gt.copy_(gt_image, non_blocking=True)
+
+    def __call__(self, cam: ViewCamera, gt_image: torch.Tensor, check: bool = True):
+        """Runs one step. With check=True (default) waits for the step and validates the binning
+        capacity (re-running on overflow); check=False returns right after the launch and leaves the
+        validation to a later `finish()`."""
+        self.load_inputs(cam, gt_image)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        if check:
+            self.finish()
+        return self.loss, self.res
+
+    def finish(self) -> int:
+        """Waits for the last replay and returns its num_rendered; on overflow re-captures with larger
+        bins and re-runs the step."""
+        st = self.res["raster_state"]
+        for _ in range(4):
+            torch.cuda.current_stream(self.dev).synchronize()
+            st.pending = True  # the graph re-wrote count_host
+            try:
+                return st.resolve()
+            except raster.CapacityOverflow:
+                self.graph = None
+                self._capture()
+                self.graph.replay()
+                st = self.res["raster_state"]
+        raise RuntimeError("GraphedTrainingStep: binning capacity did not converge")
 
 
 def smoke_step(P=3000, W=96, H=64, Ns=16) -> dict:

@@ -21,6 +21,109 @@ from ._lib import VARIANT_RGSS, VARIANT_SVGSS
 # rasterizer_impl.cu:311).
 _CAP_HINT: dict = {}
 SPECULATIVE = True
+# How forward() learns num_rendered (R), the size of the binning buffers:
+#   "exact"        read R after the preprocess, then bin (the reference's own order, one mid-pipeline sync)
+#   "speculative"  bin into a buffer sized from the previous call, read (R, overflow) once after every
+#                  kernel is enqueued, re-render on overflow -- always correct, one sync per forward (default)
+#   "async"        like speculative, but (R, overflow) is copied to pinned host memory asynchronously and
+#                  NOT awaited: forward() never blocks, so the whole step can be enqueued ahead of the GPU or
+#                  captured into a CUDA graph. The owner of the step must call RasterState.resolve() before
+#                  trusting the results (pipeline.training_step / GraphedTrainingStep do and redo the step
+#                  on overflow); LazyCount / backward() raise CapacityOverflow otherwise.
+COUNT_MODE = "speculative"
+OWNER_RESOLVES = False  # async: the caller of forward() promises to resolve() the state itself (no check in backward)
+ASYNC_MARGIN = 65536
+ASYNC_SLACK = 2.0      # async capacity = ASYNC_SLACK x the largest R seen for this (device, P, W, H)
+
+
+class CapacityOverflow(RuntimeError):
+    """Raised when an async forward binned more instances than its buffers hold."""
+
+    def __init__(self, needed: int, cap: int):
+        super().__init__("svgir_b200: binning capacity overflow (num_rendered=%d > capacity=%d); the images of "
+                         "this forward are incomplete -- re-run it (the capacity hint has been raised)" % (needed, cap))
+        self.needed, self.cap = needed, cap
+
+
+class count_mode:
+    """Context manager: `with raster.count_mode("async"): ...`"""
+
+    def __init__(self, mode: str, owner_resolves: bool = False):
+        assert mode in ("exact", "speculative", "async")
+        self.mode, self.owner = mode, owner_resolves
+
+    def __enter__(self):
+        global COUNT_MODE, OWNER_RESOLVES
+        self.prev, COUNT_MODE = (COUNT_MODE, OWNER_RESOLVES), self.mode
+        OWNER_RESOLVES = self.owner
+        return self
+
+    def __exit__(self, *a):
+        global COUNT_MODE, OWNER_RESOLVES
+        COUNT_MODE, OWNER_RESOLVES = self.prev
+        return False
+
+
+class LazyCount:
+    """num_rendered of an async forward: resolves (waits for the 8-byte D2H copy) on first use."""
+
+    def __init__(self, st: "RasterState"):
+        self._st = st
+
+    def __int__(self):
+        return self._st.resolve()
+
+    __index__ = __int__
+
+    def __repr__(self):
+        return str(int(self))
+
+    def __eq__(self, o):
+        return int(self) == o
+
+    def __hash__(self):
+        return hash(int(self))
+
+    def __gt__(self, o):
+        return int(self) > o
+
+    def __lt__(self, o):
+        return int(self) < o
+
+    def __add__(self, o):
+        return int(self) + o
+
+    __radd__ = __add__
+
+
+_PINNED_RING = None      # [256,2] int32 pinned: (R, overflow) landing slots of eager async forwards
+_PINNED_NEXT = 0
+_CAPTURE_SLOTS: list = []  # dedicated pinned slots for forwards captured into CUDA graphs (allocated before capture)
+
+
+def prepare_capture(n_forwards: int = 1):
+    """Call BEFORE capturing `n_forwards` async forwards into a CUDA graph: page-locked memory cannot be
+    allocated while a stream is capturing, and a graph's landing slot must never be recycled."""
+    for _ in range(n_forwards):
+        _CAPTURE_SLOTS.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+
+
+def _pinned_slot(capturing: bool) -> torch.Tensor:
+    global _PINNED_RING, _PINNED_NEXT
+    if capturing:
+        if not _CAPTURE_SLOTS:
+            raise RuntimeError("svgir_b200: call raster.prepare_capture() before capturing an async forward")
+        return _CAPTURE_SLOTS.pop()
+    if _PINNED_RING is None:
+        _PINNED_RING = torch.zeros((256, 2), dtype=torch.int32).pin_memory()
+    _PINNED_NEXT = (_PINNED_NEXT + 1) % 256
+    return _PINNED_RING[_PINNED_NEXT]
+
+
+def reserve(device, P: int, W: int, H: int, capacity: int):
+    """Pre-size the binning buffers for (device, P, W, H): lets the very first forward run without a sync."""
+    idx = torch.device(device).index
+    _CAP_HINT[(idx if idx is not None else torch.cuda.current_device(), P, W, H)] = int(capacity)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -77,6 +180,34 @@ class RasterState:
         self.cin = None
         self.cstate = None
         self.num_rendered = 0
+        self.count_host = None    # pinned [2] int32: (R, overflow) of an async forward
+        self.count_event = None
+        self.hint_key = None
+        self.pending = False
+        self.owner_resolves = False
+        self.cout = None
+        self.out = {}
+        self.settings = None
+        self.dims = None
+        self.src = None
+        self.rendered = False
+
+    def resolve(self) -> int:
+        """Wait for the (R, overflow) copy of an async forward; raises CapacityOverflow if the bins
+        were too small (after raising the capacity hint so that a re-run fits)."""
+        if self.pending:
+            if self.count_event is not None:
+                self.count_event.synchronize()
+            else:  # captured into a CUDA graph: the owner synchronises after the replay
+                torch.cuda.current_stream().synchronize()
+            R, overflow = self.count_host.tolist()
+            self.pending = False
+            self.num_rendered = int(R)
+            cap = int(self.cstate.cap_R)
+            _CAP_HINT[self.hint_key] = max(_CAP_HINT.get(self.hint_key, 0), int(R * ASYNC_SLACK) + ASYNC_MARGIN)
+            if overflow:
+                raise CapacityOverflow(int(R), cap)
+        return int(self.num_rendered)
 
 
 def _make_cfg(s: RasterSettings, P, S, VS, M, dev, keep) -> _lib.RasterCfg:
@@ -114,9 +245,12 @@ def _make_cfg(s: RasterSettings, P, S, VS, M, dev, keep) -> _lib.RasterCfg:
     return cfg
 
 
-def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
-            shs=None, colors_precomp=None, features=None, vfeatures=None, want_sorted_keys=False):
-    """Returns (outputs dict, RasterState). Mirrors Rasterizer::forward (rasterizer_impl.cu:209-382)."""
+def preprocess(s: RasterSettings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
+               shs=None, colors_precomp=None, want_vis_list=False) -> RasterState:
+    """Forward, part 1 (svgir_raster_preprocess): per-surfel projection / culling / tile counting, which
+    needs the geometry only. Returns the state that `forward(..., prestate=...)` completes. With
+    want_vis_list the state also carries st.t["vis_list"] / ["vis_count"]: the surfels that survive culling,
+    so that per-surfel work feeding `features` / `vfeatures` (the render_equation shading) can skip the rest."""
     L = _lib.lib()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:65-67
@@ -125,42 +259,31 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
     dev = means3D.device
     P = means3D.shape[0]
     H, W = int(s.image_height), int(s.image_width)
-    S = int(features.shape[1]) if features is not None and features.dim() == 2 else 0
-    VS = int(vfeatures.shape[1]) if vfeatures is not None and vfeatures.dim() == 2 else 0
     shs_p = _prep(shs, dev)
     M = int(shs_p.shape[1]) if shs_p is not None else 0
     f32 = dict(dtype=torch.float32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
-    out = dict(
-        color=torch.empty((3, H, W), **f32), normal=torch.empty((3, H, W), **f32),
-        depth=torch.empty((1, H, W), **f32), opacity=torch.empty((1, H, W), **f32),
-        feature=torch.empty((S, H, W), **f32), vfeature=torch.empty((VS // 4, H, W), **f32),
-        weights=torch.zeros((P, 1), **f32), radii=torch.zeros((P,), **i32))
-    if s.variant == VARIANT_RGSS:
-        out["pseudo_normal"] = torch.zeros((3, H, W), **f32)
-        out["surface_xyz"] = torch.zeros((3, H, W), **f32)
     st = RasterState()
-    if P == 0:  # rasterize_points.cu:100: outputs stay zero
-        for k in ("color", "normal", "depth", "opacity", "feature", "vfeature"):
-            out[k].zero_()
-        st.num_rendered = 0
-        out["n_contrib"] = torch.zeros((H, W), **i32)
-        return out, st
-
+    st.settings, st.dims, st.src = s, (P, H, W, M), means3D
+    st.out = dict(weights=torch.zeros((P, 1), **f32), radii=torch.zeros((P,), **i32))
+    t = st.t
+    if want_vis_list:
+        t["vis_list"] = torch.empty((max(P, 1),), **i32)
+        t["vis_count"] = torch.zeros((1,), **i32)
+    if P == 0:
+        return st
     keep = st.keep
     cin = _lib.RasterIn()
     tensors = dict(means3D=_prep(means3D, dev), opacities=_prep(opacities, dev), scales=_prep(scales, dev),
                    rotations=_prep(rotations, dev), cov3D_precomp=_prep(cov3D_precomp, dev), shs=shs_p,
-                   colors_precomp=_prep(colors_precomp, dev), features=_prep(features, dev),
-                   vfeatures=_prep(vfeatures, dev))
+                   colors_precomp=_prep(colors_precomp, dev))
     for k, v in tensors.items():
         setattr(cin, k, _ptr(v))
     keep.extend(v for v in tensors.values() if v is not None)
-    cfg = _make_cfg(s, P, S, VS, M, dev, keep)
+    cfg = _make_cfg(s, P, 0, 0, M, dev, keep)
 
     gx, gy = (W + 15) // 16, (H + 15) // 16
     T = gx * gy
-    t = st.t
     t["rec"] = torch.empty((P, _lib.REC_FLOATS), **f32)
     t["cov3D"] = torch.empty((P, 6), **f32)
     t["clamped"] = torch.empty((P,), dtype=torch.uint8, device=dev)
@@ -179,8 +302,60 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
     for k in ("rec", "cov3D", "clamped", "rect", "tiles_touched", "tile_count", "tile_cursor", "ranges",
               "big_tiles", "num_rendered", "final_T", "final_D", "n_contrib"):
         setattr(cst, k, t[k].data_ptr())
+    if want_vis_list:
+        cst.vis_list, cst.vis_count = t["vis_list"].data_ptr(), t["vis_count"].data_ptr()
     cout = _lib.RasterOut()
-    for k in ("color", "normal", "depth", "opacity", "feature", "vfeature", "weights", "radii"):
+    cout.weights, cout.radii = st.out["weights"].data_ptr(), st.out["radii"].data_ptr()
+    st.cfg, st.cin, st.cstate, st.cout = cfg, cin, cst, cout
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _lib.check(L.svgir_raster_preprocess(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
+                   "raster_preprocess")
+    return st
+
+
+def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
+            shs=None, colors_precomp=None, features=None, vfeatures=None, want_sorted_keys=False,
+            prestate: Optional[RasterState] = None):
+    """Returns (outputs dict, RasterState). Mirrors Rasterizer::forward (rasterizer_impl.cu:209-382).
+    `prestate` = the result of `preprocess()` on the same geometry and settings: only part 2 (binning,
+    sort, compositing) runs."""
+    L = _lib.lib()
+    if prestate is not None:
+        st = prestate
+        if st.src is not means3D or st.rendered:
+            raise RuntimeError("svgir_b200: prestate belongs to another forward call")
+    else:
+        st = preprocess(s, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp)
+    st.rendered = True
+    dev = means3D.device
+    P, H, W, M = st.dims
+    S = int(features.shape[1]) if features is not None and features.dim() == 2 else 0
+    VS = int(vfeatures.shape[1]) if vfeatures is not None and vfeatures.dim() == 2 else 0
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = st.out
+    out.update(
+        color=torch.empty((3, H, W), **f32), normal=torch.empty((3, H, W), **f32),
+        depth=torch.empty((1, H, W), **f32), opacity=torch.empty((1, H, W), **f32),
+        feature=torch.empty((S, H, W), **f32), vfeature=torch.empty((VS // 4, H, W), **f32))
+    if s.variant == VARIANT_RGSS:
+        out["pseudo_normal"] = torch.zeros((3, H, W), **f32)
+        out["surface_xyz"] = torch.zeros((3, H, W), **f32)
+    if P == 0:  # rasterize_points.cu:100: outputs stay zero
+        for k in ("color", "normal", "depth", "opacity", "feature", "vfeature"):
+            out[k].zero_()
+        st.num_rendered = 0
+        out["n_contrib"] = torch.zeros((H, W), **i32)
+        return out, st
+
+    t = st.t
+    cfg, cin, cst, cout = st.cfg, st.cin, st.cstate, st.cout
+    fe, vf = _prep(features, dev), _prep(vfeatures, dev)
+    st.keep.extend(x for x in (fe, vf) if x is not None)
+    cin.features, cin.vfeatures = _ptr(fe), _ptr(vf)
+    cfg.S, cfg.VS = S, VS
+    for k in ("color", "normal", "depth", "opacity", "feature", "vfeature"):
         setattr(cout, k, _ptr(out[k]))
     if s.variant == VARIANT_RGSS:
         cout.pseudo_normal = out["pseudo_normal"].data_ptr()
@@ -199,10 +374,26 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
         cst.cap_R = cap
 
     with torch.cuda.device(dev):
-        _lib.check(L.svgir_raster_preprocess(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
-                   "raster_preprocess")
         hint_key = (dev.index, P, W, H)
-        hint = _CAP_HINT.get(hint_key) if SPECULATIVE else None
+        mode = COUNT_MODE if SPECULATIVE else "exact"
+        hint = _CAP_HINT.get(hint_key) if mode != "exact" else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        if hint is None and capturing:
+            raise RuntimeError("svgir_b200: a forward captured into a CUDA graph needs a binning capacity "
+                               "(run one eager forward first, or raster.reserve())")
+        if hint is not None and mode == "async":
+            alloc_bins(hint)
+            _lib.check(L.svgir_raster_render(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
+                       "raster_render")
+            st.count_host = _pinned_slot(capturing)
+            st.count_host.copy_(t["num_rendered"], non_blocking=True)
+            if not capturing:
+                st.count_event = torch.cuda.Event()
+                st.count_event.record()
+            st.hint_key, st.pending, st.owner_resolves = hint_key, True, OWNER_RESOLVES
+            st.num_rendered = LazyCount(st)
+            out["n_contrib"] = t["n_contrib"].view(H, W)
+            return out, st
         if hint is None:
             R = int(t["num_rendered"][0].item())  # one 4-byte D2H, like rasterizer_impl.cu:311
             alloc_bins(R)
@@ -217,8 +408,8 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
                 alloc_bins(R)
                 _lib.check(L.svgir_raster_render(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
                            "raster_render")
-        _CAP_HINT[hint_key] = int(R * 1.25) + 4096
-    st.cfg, st.cin, st.cstate, st.num_rendered = cfg, cin, cst, R
+        _CAP_HINT[hint_key] = int(R * (ASYNC_SLACK if mode == "async" else 1.25)) + 4096
+    st.num_rendered = R
     out["n_contrib"] = t["n_contrib"].view(H, W)
     if R == 0:
         # nothing binned: the compositor still wrote background-only images
@@ -230,8 +421,13 @@ def backward(st: RasterState, radii, grads: dict, want_debug=False):
     """grads: dL_dcolor, dL_dnormal, dL_ddepth, dL_dopacity, dL_dfeature, dL_dvfeature (pixel space).
     Returns dict named like the reference's 13-tuple (rasterize_points.cu:264)."""
     L = _lib.lib()
+    if st.pending and not st.owner_resolves:
+        st.resolve()  # async forward whose count nobody checked yet: raises CapacityOverflow if it did not fit
     cfg = st.cfg
-    P, S, VS, M = cfg.P, cfg.S, cfg.VS, cfg.M
+    if cfg is None:  # P == 0: nothing was launched
+        P, S, VS, M = 0, int(st.out["feature"].shape[0]), 4 * int(st.out["vfeature"].shape[0]), st.dims[3]
+    else:
+        P, S, VS, M = cfg.P, cfg.S, cfg.VS, cfg.M
     dev = radii.device
     f32 = dict(dtype=torch.float32, device=dev)
     res = dict(

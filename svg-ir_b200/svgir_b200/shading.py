@@ -32,7 +32,7 @@ class ShadeCfg(C.Structure):
 class ShadeIn(C.Structure):
     _fields_ = [(n, c_fp) for n in ("base_color", "roughness", "metallic", "normals", "viewdirs", "radiance",
                                     "visibility", "incident_dirs", "incident_areas", "env", "env_transform",
-                                    "env_act_scratch", "view3x3")]
+                                    "env_act_scratch", "view3x3", "surfel_list", "surfel_count")]
 
 
 class ShadeOut(C.Structure):
@@ -203,12 +203,17 @@ class _ShadePackedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
-                incident_areas, env, metallic, view3x3, env_mode, transform, is_training, debug):
+                incident_areas, env, metallic, view3x3, env_mode, transform, is_training, debug, work=None):
         if not base_color.is_cuda:
             raise RuntimeError("svgir_b200 shading needs CUDA tensors (no CPU fallback)")
         L = _L()
         dev = base_color.device
         N, Ns = incident_dirs.shape[0], incident_dirs.shape[1]
+        if work is not None:
+            wl, wc = work
+            if wl.dtype != torch.int32 or wc.dtype != torch.int32 or wl.numel() < N or not wl.is_contiguous():
+                raise RuntimeError("shade_and_pack: work list must be contiguous int32 [N] plus an int32 [1] count")
+        alloc = torch.zeros if work is not None else torch.empty   # rows outside the work list stay zero
         t = dict(base_color=_c(base_color), roughness=_c(roughness), normals=_c(normals), viewdirs=_c(viewdirs),
                  radiance=_c(radiance), visibility=_c(visibility), incident_dirs=_c(incident_dirs),
                  incident_areas=_c(incident_areas), env=_c(env), metallic=_c(metallic), transform=_c(transform),
@@ -216,13 +221,14 @@ class _ShadePackedFn(torch.autograd.Function):
         He, We = t["env"].shape[0], t["env"].shape[1]
         f32 = dict(dtype=torch.float32, device=dev)
         S, VS = (4, 52) if is_training else (7, 64)
-        feats = torch.empty((N, S), **f32)
-        vfeats = torch.empty((N, VS), **f32)
+        feats = alloc((N, S), **f32)
+        vfeats = alloc((N, VS), **f32)
         scratch = torch.empty((He, We, 3), **f32)
         cfg = ShadeCfg(N, Ns, He, We, int(env_mode), int(bool(debug)))
         cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
-                      _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]))
+                      _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]),
+                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None)
         vp, fp = vfeats.data_ptr(), feats.data_ptr()
         # sums saved for backward: un-split total in training (only pbr / diffuse carry gradients there)
         sums = torch.empty((1 if is_training else 2, N, 12), **f32)
@@ -237,6 +243,7 @@ class _ShadePackedFn(torch.autograd.Function):
                 _lib.check(L.svgir_shade_forward(C.byref(cfg), C.byref(cin), C.byref(cout), _stream(dev)), "shade_forward")
         ctx.cfg = (N, Ns, He, We, int(env_mode), int(bool(debug)), bool(is_training))
         ctx.has = (metallic is not None, transform is not None)
+        ctx.work = work
         ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
                                             t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
                                             t["view3x3"], sums, t["metallic"], t["transform"]) if x is not None])
@@ -257,18 +264,21 @@ class _ShadePackedFn(torch.autograd.Function):
         S, VS = (4, 52) if is_training else (7, 64)
         g_feats = _c(g_feats) if g_feats is not None else torch.zeros((N, S), **f32)
         g_vfeats = _c(g_vfeats) if g_vfeats is not None else torch.zeros((N, VS), **f32)
-        d_base = torch.empty((N, 12), **f32)
-        d_rough = torch.empty((N, 4), **f32)
-        d_norm = torch.empty((N, 4, 3), **f32)
-        d_view = torch.empty((N, 3), **f32)
-        d_rad = torch.empty((N, Ns, 3), **f32) if need[4] else None
-        d_vis = torch.empty(tuple(visibility.shape), **f32) if need[5] else None
+        work = ctx.work
+        alloc = torch.zeros if work is not None else torch.empty   # surfels outside the work list: zero gradient
+        d_base = alloc((N, 12), **f32)
+        d_rough = alloc((N, 4), **f32)
+        d_norm = alloc((N, 4, 3), **f32)
+        d_view = alloc((N, 3), **f32)
+        d_rad = alloc((N, Ns, 3), **f32) if need[4] else None
+        d_vis = alloc(tuple(visibility.shape), **f32) if need[5] else None
         d_env = torch.zeros((He, We, 3), **f32) if need[8] else None
-        d_met = torch.empty((N, 4), **f32) if (metallic is not None and need[9]) else None
+        d_met = alloc((N, 4), **f32) if (metallic is not None and need[9]) else None
         scratch = torch.empty((He, We, 3), **f32)
         cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
         cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
-                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), _p(view3x3))
+                      _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), _p(view3x3),
+                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None)
         vp, fp = g_vfeats.data_ptr(), g_feats.data_ptr()
         if is_training:
             gin = (vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None)
@@ -282,16 +292,18 @@ class _ShadePackedFn(torch.autograd.Function):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
         if need[6] or need[7]:
             raise NotImplementedError("svgir_b200 shading: no gradients w.r.t. incident_dirs / incident_areas")
-        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None, None, None)
+        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None, None, None, None)
 
 
 def shade_and_pack(base_color, roughness, normals, viewdirs, radiance, env_light, visibility, incident_dirs,
-                   incident_areas, view3x3, is_training=True, metallic=None, debug=False):
+                   incident_areas, view3x3, is_training=True, metallic=None, debug=False, work=None):
     """(features [N,S], vfeatures [N,VS]) exactly as render_view packs them (svgss.py:141-166), computed by
-    one fused kernel. view3x3 = world_view_transform[:3,:3]."""
+    one fused kernel. view3x3 = world_view_transform[:3,:3].
+    work = (surfel_list int32 [N], count int32 [1]) restricts shading (and its backward) to the listed
+    surfels -- e.g. the rasteriser's list of surfels that survive culling; all other rows are zero."""
     env, mode, tr = env_of(env_light)
     return _ShadePackedFn.apply(base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
-                                incident_areas, env, metallic, view3x3, mode, tr, bool(is_training), debug)
+                                incident_areas, env, metallic, view3x3, mode, tr, bool(is_training), debug, work)
 
 
 class _DirectLightFn(torch.autograd.Function):

@@ -111,6 +111,28 @@ class GaussianRasterizationSettings(NamedTuple):
     prefiltered: bool
     debug: bool
     config: torch.Tensor
+    # Extension (keyword, optional -- the reference's 15 fields above are unchanged): the state returned by
+    # `preprocess_geometry()` for the same geometry, so that forward() runs only binning + compositing.
+    prestate: object = None
+
+
+def preprocess_geometry(raster_settings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
+                        shs=None, colors_precomp=None):
+    """Runs the rasteriser's per-surfel preprocess ahead of the forward call (it needs the geometry only) and
+    returns (prestate, (vis_list, vis_count)): the device-side list of the surfels that survive culling.
+    Shade only those (svgir_b200.shading.shade_and_pack(work=...)), then pass
+    `raster_settings._replace(prestate=prestate)` to GaussianRasterizer. Culled surfels are never read by
+    the compositor and receive zero gradients, so images and gradients are unchanged."""
+    rs = raster_settings
+    s = _raster.RasterSettings(
+        image_height=rs.image_height, image_width=rs.image_width, tanfovx=rs.tanfovx, tanfovy=rs.tanfovy,
+        bg=rs.bg, scale_modifier=rs.scale_modifier, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix,
+        sh_degree=rs.sh_degree, campos=rs.campos, prefiltered=rs.prefiltered, debug=rs.debug,
+        variant=VARIANT_SVGSS, patch_bbox=rs.patch_bbox, config=rs.config)
+    with torch.no_grad():
+        st = _raster.preprocess(s, means3D, opacities, scales, rotations, cov3D_precomp, shs, colors_precomp,
+                                want_vis_list=True)
+    return st, (st.t["vis_list"], st.t["vis_count"])
 
 
 def rasterize_gaussians(means3D, means2D, sh, features, vfeatures, colors_precomp, opacities, scales,
@@ -135,16 +157,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             sh_degree=rs.sh_degree, campos=campos, prefiltered=rs.prefiltered, debug=rs.debug,
             variant=VARIANT_SVGSS, patch_bbox=rs.patch_bbox, config=rs.config)
         args = (means3D, opacities, scales, rotations, cov3Ds_precomp, sh, colors_precomp, features, vfeatures)
+        pre = getattr(rs, "prestate", None)
         if rs.debug:
-            cpu_args = cpu_deep_copy_tuple(args + tuple(rs))  # copy before they can be corrupted
+            cpu_args = cpu_deep_copy_tuple(args + tuple(rs)[:15])  # copy before they can be corrupted
             try:
-                out, st = _raster.forward(s, *args)
+                out, st = _raster.forward(s, *args, prestate=pre)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out, st = _raster.forward(s, *args)
+            out, st = _raster.forward(s, *args, prestate=pre)
         ctx.raster_settings = rs
         ctx.num_rendered = st.num_rendered
         ctx.state = st

@@ -26,18 +26,32 @@ def test_library_exports_every_declared_symbol():
     assert L.svgir_version() >= 100
 
 
-def test_struct_layouts_match_header_sizes():
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """sizeof of every ctypes mirror == sizeof of the C struct, measured by compiling include/svgir_b200.h."""
     import ctypes as C
+    import subprocess
     from svgir_b200 import _lib, shading
-    assert C.sizeof(_lib.RasterCfg) == 18 * 4 + 6 * 8
-    assert C.sizeof(_lib.RasterIn) == 9 * 8
-    assert C.sizeof(_lib.RasterState) == 17 * 8
-    assert C.sizeof(_lib.RasterOut) == 10 * 8
-    assert C.sizeof(_lib.RasterGrads) == 20 * 8
-    assert C.sizeof(shading.ShadeCfg) == 6 * 4
-    assert C.sizeof(shading.ShadeIn) == 13 * 8
-    assert C.sizeof(shading.ShadeOut) == 12 * 8 + 16
-    assert C.sizeof(shading.ShadeGrads) == 21 * 8 + 16
+    pairs = [("svgir_raster_cfg", _lib.RasterCfg), ("svgir_raster_in", _lib.RasterIn),
+             ("svgir_raster_state", _lib.RasterState), ("svgir_raster_out", _lib.RasterOut),
+             ("svgir_raster_grads", _lib.RasterGrads), ("svgir_shade_cfg", shading.ShadeCfg),
+             ("svgir_shade_in", shading.ShadeIn), ("svgir_shade_out", shading.ShadeOut),
+             ("svgir_shade_grads", shading.ShadeGrads)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "svgir_b200.h"\nint main(void){' +
+                   "".join('printf("%%zu\\n", sizeof(%s));' % n for n, _ in pairs) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    for (name, ct), sz in zip(pairs, sizes):
+        assert C.sizeof(ct) == sz, (name, C.sizeof(ct), sz)
+    assert sv_fields_ok()
+
+
+def sv_fields_ok():
+    import svgss_rasterization as sv
+    # the optional trailing `prestate` extension must not disturb the reference's 15 positional fields
+    return sv.GaussianRasterizationSettings._fields[15:] == ("prestate",) and \
+        sv.GaussianRasterizationSettings._field_defaults == {"prestate": None}
 
 
 def test_settings_tuples_have_reference_field_order():
@@ -45,7 +59,7 @@ def test_settings_tuples_have_reference_field_order():
     import rgss_rasterization as rg
     assert sv.GaussianRasterizationSettings._fields == (
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
-        "patch_bbox", "prcppoint", "sh_degree", "campos", "prefiltered", "debug", "config")
+        "patch_bbox", "prcppoint", "sh_degree", "campos", "prefiltered", "debug", "config", "prestate")
     assert rg.GaussianRasterizationSettings._fields == (
         "image_height", "image_width", "tanfovx", "tanfovy", "cx", "cy", "bg", "scale_modifier", "viewmatrix",
         "projmatrix", "sh_degree", "campos", "prefiltered", "backward_geometry", "computer_pseudo_normal", "debug")
