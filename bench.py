@@ -113,6 +113,9 @@ def run_ours(args):
     # default: shade only the surfels that survive the rasteriser's culling (identical images and gradients,
     # tests/test_culled_shading_gpu.py); --shade-all shades every surfel in the reference's order
     pipeline.SHADE_CULLED = bool(args.shade_all)
+    # default: the resolve + loss tail is one fused kernel per direction (svgir_b200.losses); --torch-loss runs the torch
+    # mirror of the reference's tail instead (same loss and gradients, tests/test_fused_loss_gpu.py)
+    pipeline.FUSED_LOSS = not args.torch_loss
 
     cloud, mats, cams, gts = build_host_workload()
     pc = pipeline.model_from_scene(cloud, mats, dev)
@@ -184,7 +187,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     _lib.timing_enable(False)
     ktimes = {k: _lib.timing_collect(k) for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess",
-                                                  "preprocess_bwd", "emit", "sort_small", "tile_scan")}
+                                                  "preprocess_bwd", "emit", "sort_small", "tile_scan", "train_loss_fwd", "train_loss_bwd")}
     _lib.timing_collect(reset=True)
     t_ms = torch.tensor([ms], device=dev)
     if world > 1:
@@ -301,6 +304,8 @@ def run_ours(args):
                     "num_rendered read back; parameters / light buffers resident (optimiser state)"},
             "e2e_cold": {"value": round(e2e_cold, 3) if e2e_cold else None, "unit": UNIT, "h2d_bytes_per_step": int(cold_bytes),
                          "note": "worst case: every parameter and light buffer re-uploaded each step (eager path)"},
+            "loss_tail": "torch mirror of svgss.py:187-294 (~120 elementwise kernels)" if args.torch_loss else
+                         "fused resolve+loss kernels (csrc/resolve.cu), one per direction",
             "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/step)" % runner.launches_per_step,
             "kernel_timing": "CUDA events around each launch on the launching stream" + ("" if runner is None else
                              ", separate eager pass of the same kernels/inputs right after the timed region"),
@@ -337,6 +342,9 @@ def run_relight(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     pipeline.SHADE_CULLED = bool(args.shade_all)
+    # default: the resolve + loss tail is one fused kernel per direction (svgir_b200.losses); --torch-loss runs the torch
+    # mirror of the reference's tail instead (same loss and gradients, tests/test_fused_loss_gpu.py)
+    pipeline.FUSED_LOSS = not args.torch_loss
     ns, n_env = 384, 5
     cloud = scene.make_surfels(P_SURFELS, seed=1236)
     mats = scene.make_materials(cloud, ns, seed=1237)
@@ -545,6 +553,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
+    ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "relight"],
                     help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")

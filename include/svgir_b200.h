@@ -366,6 +366,46 @@ int svgir_render_equation_sh_forward(const svgir_req_sh_cfg* cfg, const svgir_re
 int svgir_render_equation_sh_backward(const svgir_req_sh_cfg* cfg, const svgir_req_sh_in* in,
                                       const svgir_req_sh_grads* g, void* stream);
 
+/* ---- fused G-buffer resolve + image loss (tail of a stage-2 training iteration) -----------------
+ * Replaces the torch code between the rasteriser's forward and backward: gaussian_renderer/svgss.py:187-233
+ * (divide feature/vfeature by opacity.clamp_min(1e-5), split, "pbr" = rgb_to_srgb(pbr*o + (1-o)*bg),
+ * utils/graphics_utils.py:198-213) and the L1 terms of calculate_loss (svgss.py:280-294,
+ * utils/loss_utils.py:33-34) plus the 0.02-weighted normal-consistency term (svgss.py:313):
+ *   loss = mean|color-gt| + lambda_pbr*mean|pbr_srgb-gt| + lambda_normal*mean(1 - <n_shade, geo_normal>).
+ * All images are channel-major [C,H,W] fp32 device pointers (the rasteriser's raw outputs). */
+typedef struct svgir_train_loss_cfg {
+    int32_t W, H, S, NV;            /* raw G-buffer: feature [S,H,W], vfeature [NV,H,W] (NV = VS/4) */
+    int32_t pbr_ch, normal_ch;      /* first vfeature channel of pbr (0) and of the shading normal (6), svgss.py:210-213 */
+    float lambda_pbr, lambda_normal;
+    const float* bg;                /* [3] device */
+} svgir_train_loss_cfg;
+
+typedef struct svgir_train_loss_in {
+    const float* color;       /* [3,H,W] "render" */
+    const float* geo_normal;  /* [3,H,W] rasteriser's normal output (raw) */
+    const float* opacity;     /* [1,H,W] */
+    const float* vfeature;    /* [NV,H,W] raw (opacity-premultiplied) */
+    const float* gt;          /* [3,H,W] */
+} svgir_train_loss_in;
+
+typedef struct svgir_train_loss_grads {   /* dL/d(rasteriser outputs); every element of a non-NULL image is written */
+    float* color;       /* [3,H,W] */
+    float* geo_normal;  /* [3,H,W] */
+    float* depth;       /* [1,H,W] (zeros; may be NULL) */
+    float* opacity;     /* [1,H,W] */
+    float* feature;     /* [S,H,W] (zeros; may be NULL) */
+    float* vfeature;    /* [NV,H,W] */
+} svgir_train_loss_grads;
+
+int svgir_train_loss_blocks(int W, int H);
+/* loss[4] = total, l1, l1_pbr, normal term; partials: 3*svgir_train_loss_blocks floats of scratch;
+ * counter: one zero-initialised u32 (left at zero on return). Deterministic summation order. */
+int svgir_train_loss_forward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in, float* loss,
+                             float* partials, unsigned int* counter, void* stream);
+/* grad_loss: device scalar dL/dloss (NULL = 1). */
+int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in,
+                              const float* grad_loss, const svgir_train_loss_grads* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,115 @@
+"""Fused tail of a stage-2 training iteration (G-buffer resolve + image loss), forward and backward.
+
+`fused_train_loss` computes, from the rasteriser's RAW outputs, exactly what
+`pipeline.image_loss(pipeline.render_view(...))` computes with ~120 torch kernels -- the
+un-premultiply / opacity filter / rgb_to_srgb of gaussian_renderer/svgss.py:187-233 followed by the L1
+terms of calculate_loss (svgss.py:280-294) and the 0.02-weighted normal-consistency term (svgss.py:313)
+-- with one CUDA kernel per direction (csrc/resolve.cu). No CPU / torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class TrainLossCfg(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("NV", C.c_int32),
+                ("pbr_ch", C.c_int32), ("normal_ch", C.c_int32),
+                ("lambda_pbr", C.c_float), ("lambda_normal", C.c_float), ("bg", C.c_void_p)]
+
+
+class TrainLossIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("color", "geo_normal", "opacity", "vfeature", "gt")]
+
+
+class TrainLossGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("color", "geo_normal", "depth", "opacity", "feature", "vfeature")]
+
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    L = _lib.lib()
+    if not _bound:
+        L.svgir_train_loss_blocks.argtypes = [C.c_int, C.c_int]
+        L.svgir_train_loss_blocks.restype = C.c_int
+        L.svgir_train_loss_forward.argtypes = [C.POINTER(TrainLossCfg), C.POINTER(TrainLossIn), C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+        L.svgir_train_loss_forward.restype = C.c_int
+        L.svgir_train_loss_backward.argtypes = [C.POINTER(TrainLossCfg), C.POINTER(TrainLossIn), C.c_void_p,
+                                                C.POINTER(TrainLossGrads), C.c_void_p]
+        L.svgir_train_loss_backward.restype = C.c_int
+        _bound = True
+    return L
+
+
+_SCRATCH: dict = {}
+
+
+def _scratch(dev, nblocks):
+    """(partials, counter) per device; the kernel leaves the counter at zero."""
+    key = (dev.index, nblocks)
+    s = _SCRATCH.get(key)
+    if s is None:
+        s = _SCRATCH[key] = (torch.empty(3 * nblocks, dtype=torch.float32, device=dev),
+                             torch.zeros(1, dtype=torch.int32, device=dev))
+    return s
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError("svgir_b200.losses: expected CUDA float32 tensors (no CPU fallback)")
+    return t.contiguous()
+
+
+class _FusedTrainLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, color, geo_normal, opacity, vfeature, gt, bg, lambda_pbr, lambda_normal, pbr_ch, normal_ch):
+        L = _bind()
+        color, geo_normal, opacity, vfeature, gt, bg = map(_f32c, (color, geo_normal, opacity, vfeature, gt, bg))
+        H, W = int(color.shape[-2]), int(color.shape[-1])
+        NV = int(vfeature.shape[0])
+        dev = color.device
+        cfg = TrainLossCfg(W, H, 0, NV, int(pbr_ch), int(normal_ch), float(lambda_pbr), float(lambda_normal), bg.data_ptr())
+        cin = TrainLossIn(color.data_ptr(), geo_normal.data_ptr(), opacity.data_ptr(), vfeature.data_ptr(), gt.data_ptr())
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        partials, counter = _scratch(dev, L.svgir_train_loss_blocks(W, H))
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(L.svgir_train_loss_forward(C.byref(cfg), C.byref(cin), out.data_ptr(), partials.data_ptr(),
+                                                  counter.data_ptr(), stream), "train_loss_forward")
+        ctx.save_for_backward(color, geo_normal, opacity, vfeature, gt, bg)
+        ctx.params = (W, H, NV, int(pbr_ch), int(normal_ch), float(lambda_pbr), float(lambda_normal))
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_terms):
+        L = _bind()
+        color, geo_normal, opacity, vfeature, gt, bg = ctx.saved_tensors
+        W, H, NV, pbr_ch, normal_ch, lp, ln = ctx.params
+        dev = color.device
+        cfg = TrainLossCfg(W, H, 0, NV, pbr_ch, normal_ch, lp, ln, bg.data_ptr())
+        cin = TrainLossIn(color.data_ptr(), geo_normal.data_ptr(), opacity.data_ptr(), vfeature.data_ptr(), gt.data_ptr())
+        g_color, g_normal = torch.empty_like(color), torch.empty_like(geo_normal)
+        g_opacity, g_vfeature = torch.empty_like(opacity), torch.empty_like(vfeature)
+        g = TrainLossGrads(g_color.data_ptr(), g_normal.data_ptr(), None, g_opacity.data_ptr(), None, g_vfeature.data_ptr())
+        grad_loss = _f32c(grad_loss.reshape(1))
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(L.svgir_train_loss_backward(C.byref(cfg), C.byref(cin), grad_loss.data_ptr(), C.byref(g), stream),
+                       "train_loss_backward")
+        return g_color, g_normal, g_opacity, g_vfeature, None, None, None, None, None, None
+
+
+def fused_train_loss(color, geo_normal, opacity, vfeature, gt_image, bg, lambda_pbr=1.0, lambda_normal=0.02,
+                     pbr_ch=0, normal_ch=6):
+    """Returns (loss, terms[4] = total, l1, l1_pbr, normal) from the rasteriser's raw outputs
+    (`rendered_image, rendered_normal, rendered_opacity, rendered_vfeature` of svgss.py:171-184)."""
+    return _FusedTrainLoss.apply(color, geo_normal, opacity, vfeature, gt_image, bg, lambda_pbr, lambda_normal,
+                                 pbr_ch, normal_ch)

@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from . import raster, shading
+from . import losses, raster, shading
 from ._lib import launch_count
 
 _CONFIG_CACHE: dict = {}
@@ -91,16 +91,10 @@ def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
     return m
 
 
-def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier=1.0,
-                is_training=True, debug=False, shade_culled: Optional[bool] = None) -> dict:
-    """svgss.py:15-262 without the application objects. Returns the same result keys the hot path
-    produces (render, depth, pbr, normal, opacity, base_color, roughness, diffuse, ...).
-
-    shade_culled=False runs the rasteriser's per-surfel preprocess FIRST and shades only the surfels that
-    survive culling (radii > 0): the compositor never reads the others and their gradients are zero, so
-    every image and every gradient is unchanged; only the per-surfel by-product `diffuse_light` is zero
-    for culled surfels (it feeds the optional lambda_light regulariser, svgss.py:359-364, which the TensoIR
-    recipe disables: script/run_tensoir.sh:37-38). Default: the module switch SHADE_CULLED."""
+def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier, is_training,
+                         debug, shade_culled):
+    """svgss.py:15-184: shading, feature packing and the rasteriser call; returns the rasteriser's raw 9-tuple
+    plus (screenspace_points, vfeatures)."""
     from svgss_rasterization import GaussianRasterizationSettings, GaussianRasterizer, preprocess_geometry
     if shade_culled is None:
         shade_culled = SHADE_CULLED
@@ -130,10 +124,26 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
         pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
         work=work)
 
-    (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
-     rendered_vfeature, weights, radii) = rasterizer(
+    raw = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=pc.shs, colors_precomp=None, opacities=pc.opacity,
         scales=pc.scaling, rotations=pc.rotation, cov3D_precomp=None, features=features, vfeatures=vfeatures)
+    return raw, screenspace_points, vfeatures
+
+
+def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier=1.0,
+                is_training=True, debug=False, shade_culled: Optional[bool] = None) -> dict:
+    """svgss.py:15-262 without the application objects. Returns the same result keys the hot path
+    produces (render, depth, pbr, normal, opacity, base_color, roughness, diffuse, ...).
+
+    shade_culled=False runs the rasteriser's per-surfel preprocess FIRST and shades only the surfels that
+    survive culling (radii > 0): the compositor never reads the others and their gradients are zero, so
+    every image and every gradient is unchanged; only the per-surfel by-product `diffuse_light` is zero
+    for culled surfels (it feeds the optional lambda_light regulariser, svgss.py:359-364, which the TensoIR
+    recipe disables: script/run_tensoir.sh:37-38). Default: the module switch SHADE_CULLED."""
+    raw, screenspace_points, vfeatures = _shade_and_rasterize(cam, pc, env_light, bg_color, scaling_modifier,
+                                                              is_training, debug, shade_culled)
+    (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
+     rendered_vfeature, weights, radii) = raw
 
     inv_o = 1.0 / rendered_opacity.clamp_min(1e-5)
     rendered_feature = rendered_feature * inv_o
@@ -172,14 +182,44 @@ def image_loss(res: dict, gt_image: torch.Tensor, lambda_pbr: float = 1.0) -> to
         0.02 * (1.0 - (res["normal"] * res["geo_normal"]).sum(0)).mean()
 
 
-def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg, gt_image, zero_grad=True):
+def render_raw(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier=1.0,
+               is_training=True, debug=False, shade_culled: Optional[bool] = None) -> dict:
+    """render_view up to and including the rasteriser (svgss.py:15-184): the raw, opacity-premultiplied G-buffer
+    that `losses.fused_train_loss` consumes directly."""
+    raw, screenspace_points, vfeatures = _shade_and_rasterize(cam, pc, env_light, bg_color, scaling_modifier,
+                                                              is_training, debug, shade_culled)
+    (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
+     rendered_vfeature, weights, radii) = raw
+    return {"render": rendered_image, "depth": rendered_depth, "geo_normal": rendered_normal, "opacity": rendered_opacity,
+            "raw_feature": rendered_feature, "raw_vfeature": rendered_vfeature, "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0, "radii": radii, "num_rendered": num_rendered, "weights": weights,
+            "raster_state": num_rendered._st if isinstance(num_rendered, raster.LazyCount) else None,
+            "diffuse_light": vfeatures[:, 40:52] if is_training else None}
+
+
+# training_step default: True = the resolve + loss tail runs as one fused CUDA kernel per direction
+# (losses.fused_train_loss); False = the torch mirror of the reference's tail (render_view + image_loss).
+FUSED_LOSS = True
+
+
+def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg, gt_image, zero_grad=True,
+                  fused_loss: Optional[bool] = None):
     """One stage-2 iteration of the hot path: shade + rasterise forward, loss, backward. Gradients
-    are left in .grad of pc.trainable() and env_param. Returns (loss tensor, result dict)."""
+    are left in .grad of pc.trainable() and env_param. Returns (loss tensor, result dict).
+    Both tails compute the same loss and gradients (tests/test_fused_loss_gpu.py)."""
     if zero_grad:
         for t in pc.trainable() + [env_param]:
             t.grad = None
-    res = render_view(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
-    loss = image_loss(res, gt_image)
+    if fused_loss is None:
+        fused_loss = FUSED_LOSS
+    if fused_loss:
+        res = render_raw(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
+        loss, terms = losses.fused_train_loss(res["render"], res["geo_normal"], res["opacity"], res["raw_vfeature"],
+                                              gt_image, bg, lambda_pbr=1.0, lambda_normal=0.02)
+        res["loss_terms"] = terms
+    else:
+        res = render_view(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
+        loss = image_loss(res, gt_image)
     loss.backward()
     return loss, res
 

