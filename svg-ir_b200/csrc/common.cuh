@@ -96,6 +96,46 @@ __device__ __forceinline__ bool eval_alpha(float px, float py, float mx, float m
     return e.alpha >= 1.0f / 255.0f;
 }
 
+// ---- packed fp32x2 FMA (FFMA2, sm_100+): two fused multiply-adds per issued instruction -----
+// Same FMA-pipe throughput as two FFMAs (profiles/r01e_ffma2_microbench.txt) but half the issue slots,
+// which is what the issue-bound compositors are short of.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// ---- per-warp footprint cull ------------------------------------------------------------------
+// A pixel can only be hit (alpha = min(0.99, o*exp(power)) >= 1/255, forward.cu:541-547) inside the
+// ellipse  cx dx^2 + 2 cy dx dy + cz dy^2 <= 2 ln(255 o).  Returns false only when the (slightly
+// inflated) bounding box of that ellipse misses the pixel rectangle [X0,X0+XW] x [Y0,Y0+YH]; any
+// non-finite or indefinite input returns true, so the exact per-pixel test still decides every hit.
+__device__ __forceinline__ bool footprint_overlaps(float mx, float my, float cx, float cy, float cz, float o,
+                                                   float X0, float Y0, float XW, float YH) {
+    if (o < 1.0f / 255.0f) return false;  // alpha <= o (exp(power) <= 1)
+    const float L = fmaf(2.0f * __logf(255.0f * o), 1.001f, 1e-3f);
+    const float det = cx * cz - cy * cy;
+    if (!(det > 0.f)) return true;
+    const float k = L / det;
+    const float ex = sqrtf(k * cz) * 1.0005f + 0.05f, ey = sqrtf(k * cx) * 1.0005f + 0.05f;
+    return !(mx + ex < X0) && !(mx - ex > X0 + XW) && !(my + ey < Y0) && !(my - ey > Y0 + YH);
+}
+
+// 16x16 tile, 8 warps: warp w owns the 8x4 pixel block at ((w&1)*8, (w>>1)*4) -- a compact footprint
+// (vs. 16x2 rows) means fewer warps touched per surfel and more hits per touched warp.
+#define WARP_PX_W 8
+#define WARP_PX_H 4
+
 // Launchers (one per translation unit)
 int launch_preprocess(const svgir_raster_cfg& c, const svgir_raster_in& in, svgir_raster_state& st,
                       svgir_raster_out& out, cudaStream_t s);

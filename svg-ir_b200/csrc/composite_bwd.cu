@@ -315,6 +315,21 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
 #define LBATCH 32
 #define HIT_STRIDE_L 12   // 3 float4 per hit: 128-bit stores/loads are conflict-free at this stride
 
+template <int S_T, int NV_T>
+struct LaneBwdLayout {
+    static constexpr int S = S_T, NV = NV_T;
+    static constexpr int SP = (S + 3) & ~3;
+    static constexpr int NVP = (NV + 3) & ~3;                 // transposed vfeature rows: [4 vertices][NVP channels]
+    static constexpr int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NVP;
+    static constexpr int LCH = REC_F4 + SP / 4 + NV;          // float4 chunks loaded per instance
+    static constexpr int NG = 8 + S + NV;                     // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
+    static constexpr int GS = NG | 1;                         // odd stride
+    static constexpr int G_OFF = LBATCH * STRIDE;
+    static constexpr int HITS_OFF = (G_OFF + TILE_PIX * GS + 3) & ~3;   // 16-B aligned
+    static constexpr int IDS_OFF = HITS_OFF + NWARP * 32 * HIT_STRIDE_L;
+    static constexpr int SMEM_FLOATS = IDS_OFF + LBATCH;
+};
+
 template <int S_T, int NV_T, bool RGSS>
 __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
@@ -326,20 +341,16 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
     float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures,
     const int32_t* __restrict__ num_rendered) {
+    using LY = LaneBwdLayout<S_T, NV_T>;
     constexpr int S = S_T, NV = NV_T;
-    constexpr int SP = (S + 3) & ~3;
-    constexpr int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;
-    constexpr int CH = STRIDE / 4;
-    constexpr int NG = 8 + S + NV;          // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
-    constexpr int GS = NG | 1;              // odd stride
+    constexpr int SP = LY::SP, NVP = LY::NVP, STRIDE = LY::STRIDE, LCH = LY::LCH, NG = LY::NG, GS = LY::GS;
     static_assert(NG + 5 <= 32, "lane mode needs one lane per gradient channel plus 5 geo lanes");
 
     extern __shared__ __align__(16) float smem[];
     float* stage = smem;                                   // [LBATCH][STRIDE]
-    float* G = stage + LBATCH * STRIDE;                    // [256][GS]
-    float* hits = G + TILE_PIX * GS + 3;                   // [NWARP][32][HIT_STRIDE_L] (+3: 256*GS is 0 mod 4 only if GS%4==0... keep 16-B alignment below)
-    hits = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(hits) + 15) & ~uintptr_t(15));
-    int* ids = reinterpret_cast<int*>(hits + NWARP * 32 * HIT_STRIDE_L);  // [LBATCH]
+    float* G = smem + LY::G_OFF;                           // [256][GS]
+    float* hits = smem + LY::HITS_OFF;                     // [NWARP][32][HIT_STRIDE_L]
+    int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [LBATCH]
     __shared__ int tile_max_s;
 
     const int W = c.W, H = c.H;
@@ -349,11 +360,13 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const int total = (int)(range.y - range.x);
     if (total == 0 || num_rendered[1]) return;  // empty tile, or the forward's bins overflowed (nothing valid)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int px = (tile % gx) * TILE + (tid & 15), py = (tile / gx) * TILE + (tid >> 4);
+    const int wx0 = (tile % gx) * TILE + (wid & 1) * WARP_PX_W, wy0 = (tile / gx) * TILE + (wid >> 1) * WARP_PX_H;
+    const int px = wx0 + (lane & (WARP_PX_W - 1)), py = wy0 + (lane / WARP_PX_W);
     const bool inside = px < W && py < H;
     const size_t HW = (size_t)H * W;
     const size_t pix_id = (size_t)W * py + px;
     const float pxf = (float)px, pyf = (float)py;
+    const float wx0f = (float)wx0, wy0f = (float)wy0;
 
     bool surface = true, ppd = true, normalize_depth = true;
     if (!RGSS) {
@@ -371,7 +384,8 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     // ---- pixel-gradient row (shared: read by the channel lanes; registers: this pixel's own copy) ----
     float* Grow = G + tid * GS;
     float gD = 0.f, gDn = 0.f, Kpix = 0.f;
-    float gC[3] = {0, 0, 0}, gN[3] = {0, 0, 0}, gF[S > 0 ? S : 1], gV[NV > 0 ? NV : 1];
+    float gC[3] = {0, 0, 0}, gN[3] = {0, 0, 0}, gF[S > 0 ? S : 1];
+    unsigned long long gV2[NVP > 0 ? NVP / 2 : 1];   // SV-channel pixel gradients as FFMA2 operand pairs
     {
         float gO = 0.f;
         if (inside) {
@@ -390,8 +404,14 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
         Grow[7] = gDn;
 #pragma unroll
         for (int i = 0; i < S; i++) { gF[i] = inside ? gpix_feature[i * HW + pix_id] : 0.f; Grow[8 + i] = gF[i]; }
+        float gV[NVP > 0 ? NVP : 1];
 #pragma unroll
-        for (int i = 0; i < NV; i++) { gV[i] = inside ? gpix_vfeature[i * HW + pix_id] : 0.f; Grow[8 + S + i] = gV[i]; }
+        for (int i = 0; i < NVP; i++) {
+            gV[i] = (i < NV && inside) ? gpix_vfeature[i * HW + pix_id] : 0.f;
+            if (i < NV) Grow[8 + S + i] = gV[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NVP / 2; i++) gV2[i] = pack2(gV[2 * i], gV[2 * i + 1]);
         const float* bg = c.bg;
         const float bgdot = bg[0] * gC[0] + bg[1] * gC[1] + bg[2] * gC[2];
         Kpix = gO * T_final - T_final * bgdot;
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     }
 
     // ---- lane roles ---------------------------------------------------------------------------------
-    //   hit record: [0..3] w*w0..w3 | [4] w | [5,6] dmean | [7,8,9] dconic | [10] dopacity | [11] pixel
+    //   hit record: [0..3] w*w0..w3 | [4] w | [5,6] dmean | [7,8,9] dconic | [10] dopacity | [11] pixel's G-row offset
     //   scalar target of a0: geo_grad component (>=0), feature index (encoded as 16+i), or none (-1)
     int l_gch = 0, l_sel0 = 4, l_k0 = -1;
     bool l_vf = false;
@@ -412,14 +432,24 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     else if (lane < 8 + S) { l_gch = lane; l_k0 = 16 + (lane - 8); }           // flat features
     else if (lane < NG) { l_gch = lane; l_vf = true; }                         // SV channel lane-8-S
     else if (lane < NG + 5) { l_sel0 = 6 + (lane - NG); l_k0 = 1 + (lane - NG); }  // dmean.y, dconic xyw, dopacity
+    const float* Glane = G + l_gch;
 
     // ---- tile-wide traversal start --------------------------------------------------------------
     if (tid == 0) tile_max_s = 0;
+    if constexpr (NVP != NV) {  // zero the padding channels of the transposed rows once
+        constexpr int PADC = NVP - NV;
+        for (int q = tid; q < LBATCH * 4 * PADC; q += TILE_PIX) {
+            const int i = q / (4 * PADC), r = q - i * 4 * PADC;
+            stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / PADC) * NVP + NV + r % PADC] = 0.f;
+        }
+    }
     __syncthreads();
+    int warp_max;
     {
         int m = last_contributor;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        warp_max = m;
         if (lane == 0) atomicMax(&tile_max_s, m);
     }
     __syncthreads();
@@ -433,13 +463,15 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     for (int top = tile_max; top > 0; top -= LBATCH) {
         const int nb = min(LBATCH, top);
         __syncthreads();  // every warp is done with the previous batch's staged records
-        for (int q = tid; q < nb * CH; q += TILE_PIX) {
-            const int i = q / CH, ch = q - i * CH;
+        for (int q = tid; q < nb * LCH; q += TILE_PIX) {
+            const int i = q / LCH, ch = q - i * LCH;
             const int id = (int)point_list[range.x + top - 1 - i];
+            float* dst = stage + i * STRIDE;
             float4 v;
             if (ch < REC_F4) {
                 v = __ldg(rec + (size_t)id * REC_F4 + ch);
                 if (ch == 0) ids[i] = id;
+                reinterpret_cast<float4*>(dst)[ch] = v;
             } else if (ch < REC_F4 + SP / 4) {
                 const int f0 = (ch - REC_F4) * 4;
                 const float* src = features + (size_t)id * S + f0;
@@ -450,14 +482,33 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
                     v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
                     v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
                 }
+                reinterpret_cast<float4*>(dst)[ch] = v;
             } else {
-                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + (ch - REC_F4 - SP / 4));
+                const int cidx = ch - REC_F4 - SP / 4;
+                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + cidx);
+                float* t = dst + SVGIR_REC_FLOATS + SP + cidx;   // transpose: vertex-major rows of NVP channels
+                t[0] = v.x; t[NVP] = v.y; t[2 * NVP] = v.z; t[3 * NVP] = v.w;
             }
-            reinterpret_cast<float4*>(stage)[q] = v;
         }
         __syncthreads();
 
-        for (int j = 0; j < nb; j++) {
+        // per-warp cull: instances behind every pixel's last contributor, or whose alpha >= 1/255 ellipse cannot
+        // reach this warp's 8x4 pixels, are never evaluated
+        unsigned m;
+        {
+            bool keep = false;
+            if (lane < nb && top - 1 - lane < warp_max) {
+                const float4* r = reinterpret_cast<const float4*>(stage + lane * STRIDE);
+                const float4 q0 = r[0];
+                const float2 q1 = *reinterpret_cast<const float2*>(r + 1);
+                keep = footprint_overlaps(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, wx0f, wy0f, WARP_PX_W - 1.f, WARP_PX_H - 1.f);
+            }
+            m = __ballot_sync(0xffffffffu, keep);
+        }
+
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
             const int pos = top - 1 - j;  // 0-based position in the tile's sorted list
             const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
             const float4 q0 = r[0];
@@ -505,12 +556,22 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
 #pragma unroll
                     for (int ch = 0; ch < S; ch++) V = fmaf(f[ch], gF[ch], V);
                 }
-                const float4* vf = reinterpret_cast<const float4*>(f + SP);
+                if constexpr (NV > 0) {
+                    // sum_c gV_c * sum_k w_k vf[4c+k] = sum_k w_k * <vfT[k][:], gV>: channel pairs per FFMA2
+                    const float wk[4] = {w0, w1, w2, w3};
 #pragma unroll
-                for (int cidx = 0; cidx < NV; cidx++) {
-                    const float4 t = vf[cidx];
-                    const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
-                    V = fmaf(s4, gV[cidx], V);
+                    for (int k = 0; k < 4; k++) {
+                        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(f + SP + k * NVP);
+                        unsigned long long acc = 0ull;
+#pragma unroll
+                        for (int q = 0; q < NVP / 4; q++) {
+                            const ulonglong2 t = row[q];
+                            acc = ffma2(t.x, gV2[2 * q], acc);
+                            acc = ffma2(t.y, gV2[2 * q + 1], acc);
+                        }
+                        const float2 d = unpack2(acc);
+                        V = fmaf(wk[k], d.x + d.y, V);
+                    }
                 }
                 A = last_alpha * V_last + (1.f - last_alpha) * A;
                 V_last = V;
@@ -524,16 +585,15 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
                 float4* h4 = reinterpret_cast<float4*>(my_hits + rank * HIT_STRIDE_L);
                 h4[0] = make_float4(w * w0, w * w1, w * w2, w * w3);
                 h4[1] = make_float4(w, dmx, dmy, dL_ddist * (e.dx * e.dx));
-                h4[2] = make_float4(dL_ddist * (e.dx * e.dy), dL_ddist * (e.dy * e.dy), e.G * dL_dalpha, __int_as_float(tid));
+                h4[2] = make_float4(dL_ddist * (e.dx * e.dy), dL_ddist * (e.dy * e.dy), e.G * dL_dalpha, __int_as_float(tid * GS));
             }
             __syncwarp();
             const int nh = __popc(ballot);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
-#pragma unroll 2
+#pragma unroll 4
             for (int hh = 0; hh < nh; hh++) {
                 const float* h = my_hits + hh * HIT_STRIDE_L;
-                const int pix = __float_as_int(h[11]);
-                const float Gv = G[pix * GS + l_gch];
+                const float Gv = Glane[__float_as_int(h[11])];
                 a0 = fmaf(h[l_sel0], Gv, a0);
                 if (NV > 0) {
                     const float4 hw = *reinterpret_cast<const float4*>(h);
@@ -559,11 +619,7 @@ template <int S_T, int NV_T, bool RGSS>
 static int launch_lane_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                            const svgir_raster_state& st, svgir_raster_grads& g, cudaStream_t s) {
     const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
-    constexpr int SP = (S_T + 3) & ~3;
-    constexpr int stride = SVGIR_REC_FLOATS + SP + 4 * NV_T;
-    constexpr int gs = (8 + S_T + NV_T) | 1;
-    const size_t smem = sizeof(float) * ((size_t)LBATCH * stride + (size_t)TILE_PIX * gs + 8 +
-                                         (size_t)NWARP * 32 * HIT_STRIDE_L + LBATCH);
+    const size_t smem = sizeof(float) * (size_t)LaneBwdLayout<S_T, NV_T>::SMEM_FLOATS;
     auto k = composite_bwd_lane_kernel<S_T, NV_T, RGSS>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -32,13 +32,17 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
     float* __restrict__ out_opac, float* __restrict__ out_feature, float* __restrict__ out_vfeature,
     float* __restrict__ out_weights) {
     constexpr bool GENERIC = S_T < 0;
+    // PACKED: the staged vfeature row is transposed to [4 vertices][NVP channels] so that channel PAIRS are
+    // accumulated with one FFMA2 each (2 fused multiply-adds per issue slot)
+    constexpr bool PACKED = !GENERIC && NV_T > 0;
     constexpr int MAXS = GENERIC ? SVGIR_MAX_S : (S_T > 0 ? S_T : 1);
     constexpr int MAXNV = GENERIC ? SVGIR_MAX_NV : (NV_T > 0 ? NV_T : 1);
+    constexpr int NVP_T = PACKED ? ((NV_T + 3) & ~3) : 0;   // channels padded to a float4
     const int S = GENERIC ? c.S : S_T;
     const int NV = GENERIC ? c.VS / 4 : NV_T;
     const int SP = (S + 3) & ~3;          // feature row padded to float4
-    const int STRIDE = SVGIR_REC_FLOATS + SP + 4 * NV;  // floats per staged instance
-    const int CH = STRIDE / 4;            // float4 chunks per staged instance
+    const int STRIDE = SVGIR_REC_FLOATS + SP + (PACKED ? 4 * NVP_T : 4 * NV);  // floats per staged instance
+    const int LCH = REC_F4 + SP / 4 + NV;  // float4 chunks loaded per instance
 
     extern __shared__ __align__(16) float smem[];
     float* stage = smem;                                  // [FWD_BATCH][STRIDE]
@@ -49,13 +53,14 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
     const int tile = blockIdx.x;
-    const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int px = tx0 + (tid & 15), py = ty0 + (tid >> 4);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wx0 = (tile % gx) * TILE + (wid & 1) * WARP_PX_W, wy0 = (tile / gx) * TILE + (wid >> 1) * WARP_PX_H;
+    const int px = wx0 + (lane & (WARP_PX_W - 1)), py = wy0 + (lane / WARP_PX_W);
     const bool inside = px < W && py < H;
     const size_t HW = (size_t)H * W;
     const size_t pix_id = (size_t)W * py + px;
     const float pxf = (float)px, pyf = (float)py;
+    const float wx0f = (float)wx0, wy0f = (float)wy0;
 
     bool surface = true, ppd = true, normalize_depth = true;
     if (!RGSS) {
@@ -70,16 +75,27 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
 
     float T = 1.0f, D = 0.f;
     float C[3] = {0, 0, 0}, N[3] = {0, 0, 0};
-    float F[MAXS], VF[MAXNV];
+    float F[MAXS], VF[PACKED ? 1 : MAXNV];
+    unsigned long long VF2[PACKED ? NVP_T / 2 : 1];
 #pragma unroll
     for (int i = 0; i < MAXS; i++) F[i] = 0.f;
+    if (PACKED) {
 #pragma unroll
-    for (int i = 0; i < MAXNV; i++) VF[i] = 0.f;
+        for (int i = 0; i < NVP_T / 2; i++) VF2[i] = 0ull;
+    } else {
+#pragma unroll
+        for (int i = 0; i < MAXNV; i++) VF[i] = 0.f;
+    }
     uint32_t last_contributor = 0;
     bool done = !inside;
 
     for (int i = tid; i < 2 * 8 * FWD_BATCH; i += TILE_PIX) wsum[i] = 0.f;
-    const int wid = tid >> 5;
+    if (PACKED && NVP_T != NV_T) {  // zero the padding channels of the transposed rows once
+        for (int q = tid; q < FWD_BATCH * 4 * (NVP_T - NV_T); q += TILE_PIX) {
+            const int i = q / (4 * (NVP_T - NV_T)), r = q - i * 4 * (NVP_T - NV_T);
+            stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / (NVP_T - NV_T)) * NVP_T + NV_T + r % (NVP_T - NV_T)] = 0.f;
+        }
+    }
 
     int nbatch = 0;
     for (int base = 0; base < total; base += FWD_BATCH, nbatch++) {
@@ -96,13 +112,15 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
         if (ndone == TILE_PIX) break;
         const int nb = min(FWD_BATCH, total - base);
         // cooperative 128-bit staging of records + feature rows
-        for (int q = tid; q < nb * CH; q += TILE_PIX) {
-            const int i = q / CH, ch = q - i * CH;
+        for (int q = tid; q < nb * LCH; q += TILE_PIX) {
+            const int i = q / LCH, ch = q - i * LCH;
             const int id = (int)point_list[range.x + base + i];
+            float* dst = stage + i * STRIDE;
             float4 v;
             if (ch < REC_F4) {
                 v = __ldg(rec + (size_t)id * REC_F4 + ch);
                 if (ch == 0) ids[par * FWD_BATCH + i] = id;
+                reinterpret_cast<float4*>(dst)[ch] = v;
             } else if (ch < REC_F4 + SP / 4) {
                 const int f0 = (ch - REC_F4) * 4;
                 const float* src = features + (size_t)id * S + f0;
@@ -113,78 +131,123 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
                     v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
                     v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
                 }
+                reinterpret_cast<float4*>(dst)[ch] = v;
             } else {
                 const int cidx = ch - REC_F4 - SP / 4;
                 v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + cidx);
+                if (PACKED) {  // transpose: vertex-major rows of NVP channels
+                    float* t = dst + SVGIR_REC_FLOATS + SP + cidx;
+                    t[0] = v.x; t[NVP_T] = v.y; t[2 * NVP_T] = v.z; t[3 * NVP_T] = v.w;
+                } else {
+                    reinterpret_cast<float4*>(dst)[ch] = v;
+                }
             }
-            reinterpret_cast<float4*>(stage)[q] = v;
         }
         __syncthreads();
 
-        for (int j = 0; j < nb; j++) {
-            const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
-            const float4 q0 = r[0];
-            const float4 q1 = r[1];
-            PairEval e;
-            bool hit = false;
-            float test_T = 0.f;
-            if (!done) {
-                hit = eval_alpha<RGSS>(pxf, pyf, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e);
+        // per-warp footprint cull: one bit per staged instance whose alpha >= 1/255 ellipse can reach this
+        // warp's 8x4 pixels; the others are never evaluated
+        unsigned masks[FWD_BATCH / 32];
+        const bool warp_live = !__all_sync(0xffffffffu, done);
+#pragma unroll
+        for (int h = 0; h < FWD_BATCH / 32; h++) {
+            const int i = h * 32 + lane;
+            bool keep = false;
+            if (warp_live && i < nb) {
+                const float4* r = reinterpret_cast<const float4*>(stage + i * STRIDE);
+                const float4 q0 = r[0];
+                const float2 q1 = *reinterpret_cast<const float2*>(r + 1);
+                keep = footprint_overlaps(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, wx0f, wy0f, WARP_PX_W - 1.f, WARP_PX_H - 1.f);
+            }
+            masks[h] = __ballot_sync(0xffffffffu, keep);
+        }
+
+#pragma unroll
+        for (int h = 0; h < FWD_BATCH / 32; h++) {
+            unsigned m = masks[h];
+            while (m) {
+                const int j = h * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+                const float4 q0 = r[0];
+                const float4 q1 = r[1];
+                PairEval e;
+                bool hit = false;
+                float test_T = 0.f;
+                if (!done) {
+                    hit = eval_alpha<RGSS>(pxf, pyf, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e);
+                    if (hit) {
+                        test_T = mul_(T, sub_(1.f, e.alpha));
+                        if (test_T < 0.0001f) { done = true; hit = false; }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                float w = 0.f;
                 if (hit) {
-                    test_T = mul_(T, sub_(1.f, e.alpha));
-                    if (test_T < 0.0001f) { done = true; hit = false; }
-                }
-            }
-            if (!__any_sync(0xffffffffu, hit)) continue;
-            float w = 0.f;
-            if (hit) {
-                w = mul_(e.alpha, T);
-                float depth_k = q1.z;
-                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                if (sv) {
-                    const float4 q2 = r[2];
-                    const float4 q3 = r[3];
-                    const float u0 = fma_(e.dx, q2.x, mul_(e.dy, q2.y));
-                    const float u1 = fma_(e.dx, q2.z, mul_(e.dy, q2.w));
-                    depth_k = sub_(q1.z, fma_(q3.x, u0, mul_(q3.y, u1)));
-                    if (!RGSS) {
-                        float u = fmaf(u0, q1.w, 0.5f), v = fmaf(u1, q3.z, 0.5f);
-                        u = fminf(0.999f, fmaxf(0.001f, u));
-                        v = fminf(0.999f, fmaxf(0.001f, v));
-                        w0 = (1.0f - u) * (1.0f - v);
-                        w1 = u * (1.0f - v);
-                        w2 = (1.0f - u) * v;
-                        w3 = u * v;
+                    w = mul_(e.alpha, T);
+                    float depth_k = q1.z;
+                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                    if (sv) {
+                        const float4 q2 = r[2];
+                        const float4 q3 = r[3];
+                        const float u0 = fma_(e.dx, q2.x, mul_(e.dy, q2.y));
+                        const float u1 = fma_(e.dx, q2.z, mul_(e.dy, q2.w));
+                        depth_k = sub_(q1.z, fma_(q3.x, u0, mul_(q3.y, u1)));
+                        if (!RGSS) {
+                            float u = fmaf(u0, q1.w, 0.5f), v = fmaf(u1, q3.z, 0.5f);
+                            u = fminf(0.999f, fmaxf(0.001f, u));
+                            v = fminf(0.999f, fmaxf(0.001f, v));
+                            w0 = (1.0f - u) * (1.0f - v);
+                            w1 = u * (1.0f - v);
+                            w2 = (1.0f - u) * v;
+                            w3 = u * v;
+                        }
                     }
-                }
-                D = fmaf(depth_k, w, D);
-                const float4 q4 = r[4];
-                C[0] = fmaf(q4.x, w, C[0]);
-                C[1] = fmaf(q4.y, w, C[1]);
-                C[2] = fmaf(q4.z, w, C[2]);
-                if (surface) {
-                    const float4 q5 = r[5];
-                    N[0] = fmaf(q4.w, w, N[0]);
-                    N[1] = fmaf(q5.x, w, N[1]);
-                    N[2] = fmaf(q5.y, w, N[2]);
-                }
-                const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
-#pragma unroll
-                for (int ch = 0; ch < MAXS; ch++)
-                    if (ch < S) F[ch] = fmaf(f[ch], w, F[ch]);
-                const float4* vf = reinterpret_cast<const float4*>(f + SP);
-#pragma unroll
-                for (int cidx = 0; cidx < MAXNV; cidx++)
-                    if (cidx < NV) {
-                        const float4 t = vf[cidx];
-                        const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
-                        VF[cidx] = fmaf(w, s4, VF[cidx]);
+                    D = fmaf(depth_k, w, D);
+                    const float4 q4 = r[4];
+                    C[0] = fmaf(q4.x, w, C[0]);
+                    C[1] = fmaf(q4.y, w, C[1]);
+                    C[2] = fmaf(q4.z, w, C[2]);
+                    if (surface) {
+                        const float4 q5 = r[5];
+                        N[0] = fmaf(q4.w, w, N[0]);
+                        N[1] = fmaf(q5.x, w, N[1]);
+                        N[2] = fmaf(q5.y, w, N[2]);
                     }
-                T = test_T;
-                last_contributor = (uint32_t)(base + j + 1);
+                    const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+#pragma unroll
+                    for (int ch = 0; ch < MAXS; ch++)
+                        if (ch < S) F[ch] = fmaf(f[ch], w, F[ch]);
+                    if (PACKED) {
+                        // VF_c += (w*w_k) * vf[4c+k], two channels per FFMA2 (reference: w * sum_k w_k vf[4c+k])
+                        const float wk[4] = {w * w0, w * w1, w * w2, w * w3};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const unsigned long long wk2 = pack2(wk[k], wk[k]);
+                            const ulonglong2* row = reinterpret_cast<const ulonglong2*>(f + SP + k * NVP_T);
+#pragma unroll
+                            for (int q = 0; q < NVP_T / 4; q++) {
+                                const ulonglong2 t = row[q];
+                                VF2[2 * q] = ffma2(t.x, wk2, VF2[2 * q]);
+                                VF2[2 * q + 1] = ffma2(t.y, wk2, VF2[2 * q + 1]);
+                            }
+                        }
+                    } else {
+                        const float4* vf = reinterpret_cast<const float4*>(f + SP);
+#pragma unroll
+                        for (int cidx = 0; cidx < MAXNV; cidx++)
+                            if (cidx < NV) {
+                                const float4 t = vf[cidx];
+                                const float s4 = ((t.x * w0 + t.y * w1) + t.z * w2) + t.w * w3;
+                                VF[cidx] = fmaf(w, s4, VF[cidx]);
+                            }
+                    }
+                    T = test_T;
+                    last_contributor = (uint32_t)(base + j + 1);
+                }
+                const float wt = warp_sum(w);
+                if (lane == 0) wsum[(par * 8 + wid) * FWD_BATCH + j] = wt;
             }
-            const float wt = warp_sum(w);
-            if (lane == 0) wsum[(par * 8 + wid) * FWD_BATCH + j] = wt;
         }
     }
     // flush the last computed batch's weight sums
@@ -208,9 +271,18 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
 #pragma unroll
         for (int ch = 0; ch < MAXS; ch++)
             if (ch < S) out_feature[ch * HW + pix_id] = F[ch];
+        if (PACKED) {
 #pragma unroll
-        for (int cidx = 0; cidx < MAXNV; cidx++)
-            if (cidx < NV) out_vfeature[cidx * HW + pix_id] = VF[cidx];
+            for (int i = 0; i < NVP_T / 2; i++) {
+                const float2 v = unpack2(VF2[i]);
+                if (2 * i < NV_T) out_vfeature[(size_t)(2 * i) * HW + pix_id] = v.x;
+                if (2 * i + 1 < NV_T) out_vfeature[(size_t)(2 * i + 1) * HW + pix_id] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int cidx = 0; cidx < MAXNV; cidx++)
+                if (cidx < NV) out_vfeature[cidx * HW + pix_id] = VF[cidx];
+        }
         out_normal[0 * HW + pix_id] = surface ? N[0] : 0.f;
         out_normal[1 * HW + pix_id] = surface ? N[1] : 0.f;
         out_normal[2 * HW + pix_id] = surface ? N[2] : 0.f;
@@ -225,7 +297,8 @@ static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
                       svgir_raster_out& out, cudaStream_t s) {
     const int gx = (c.W + TILE - 1) / TILE, gy = (c.H + TILE - 1) / TILE;
     const int SP = (c.S + 3) & ~3;
-    const int stride = SVGIR_REC_FLOATS + SP + c.VS;
+    const int nvf = (S_T >= 0 && NV_T > 0) ? 4 * ((NV_T + 3) & ~3) : c.VS;  // packed kernels pad the transposed rows
+    const int stride = SVGIR_REC_FLOATS + SP + nvf;
     const size_t smem = sizeof(float) * ((size_t)FWD_BATCH * stride + 2 * 8 * FWD_BATCH + 2 * FWD_BATCH);
     auto k = composite_fwd_kernel<S_T, NV_T, RGSS>;
     if (smem > 48 * 1024) {
