@@ -126,19 +126,28 @@ def run_ours(args):
     params = pc.trainable() + [env]
     # N>1: .grad of every parameter is a view into one flat buffer, reduced with ONE NCCL all-reduce
     # per step (svgir_b200/dist.py); N=1 lets autograd hand over its gradient tensors.
-    bucket = svdist.FlatGradBucket(params) if world > 1 else None
+    # The bucket is laid out in two segments in the order the backward pass finishes them (rasteriser-side
+    # gradients, then shading-side ones); each segment's all-reduce is issued from inside the backward pass, so
+    # the first one travels over NVLink while the shading backward kernel is still running, and both are
+    # captured INSIDE the step's CUDA graph (--reduce post: one all-reduce after the graph instead).
+    overlap = world > 1 and args.reduce == "overlap"
+    bucket = svdist.FlatGradBucket(params, segments=pipeline.reduce_segments(pc) if overlap else None,
+                                   extra_floats=1) if world > 1 else None
     # The step is captured once into a CUDA graph (pipeline.GraphedTrainingStep) and replayed: one
     # cudaGraphLaunch per iteration, camera + ground truth copied into static buffers, binning capacity
     # checked after every replay. --eager runs the same step launch by launch instead.
-    runner = None if args.eager else pipeline.GraphedTrainingStep(pc, env, bg, cam_dev[0], gt_dev[0], bucket=bucket)
+    runner = None if args.eager else pipeline.GraphedTrainingStep(pc, env, bg, cam_dev[0], gt_dev[0], bucket=bucket,
+                                                                         reduce_in_graph=overlap)
 
     def eager_step(i):
         v = (i * world + rank) % N_VIEWS
         if bucket is None:
             return pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
         bucket.zero()
-        loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)], zero_grad=False)
-        bucket.all_reduce()  # per-surfel gradient exchange over NVLink
+        loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)], zero_grad=False,
+                                           overlap_bucket=bucket if overlap else None)
+        if not overlap:
+            bucket.all_reduce()  # per-surfel gradient exchange over NVLink
         return loss, res
 
     def step(i):
@@ -146,7 +155,7 @@ def run_ours(args):
             return eager_step(i)
         v = (i * world + rank) % N_VIEWS
         loss, res = runner(cam_dev[v], gt_dev[i % len(gt_dev)])
-        if bucket is not None:
+        if bucket is not None and not overlap:
             bucket.all_reduce()
         return loss, res
 
@@ -218,8 +227,8 @@ def run_ours(args):
             if bucket is not None:
                 bucket.zero()
             loss, res = pipeline.training_step(cam, pc, env, bg, gt_host[i % len(gt_host)].to(dev, non_blocking=True),
-                                               zero_grad=bucket is None)
-        if bucket is not None:
+                                               zero_grad=bucket is None, overlap_bucket=bucket if overlap else None)
+        if bucket is not None and not overlap:
             bucket.all_reduce()
         return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
 
@@ -310,6 +319,9 @@ def run_ours(args):
             "kernel_timing": "CUDA events around each launch on the launching stream" + ("" if runner is None else
                              ", separate eager pass of the same kernels/inputs right after the timed region"),
             "gpu_launches": int(launches),
+            "grad_allreduce": None if bucket is None else {
+                "bytes": bucket.nbytes, "mode": "2 segments issued inside the backward pass, captured in the step's graph"
+                if overlap else "one all-reduce after the step"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
                          "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
                          "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
@@ -393,7 +405,9 @@ def run_relight(args):
     ms_frame = float(t_ms.item()) / args.steps
     if rank == 0:
         pk, pk_src = peaks()
-        alg = P_SURFELS * (ns * 32 + 124) + P_SURFELS * 4 * (12 * 5 + 7)
+        # shading runs on the surfels that survive the rasteriser's culling unless --shade-all
+        n_sh = P_SURFELS if args.shade_all else int(res["visibility_filter"].sum())
+        alg = n_sh * (ns * 32 + 124) + n_sh * 4 * (12 * 5 + 7)
         ach = alg / (kt["shade_fwd"] * 1e-3) / 1e9 if kt["shade_fwd"] > 0 else 0.0
         print(json.dumps({
             "metric": "relight ms/frame", "value": round(ms_frame / world, 4), "unit": "ms/frame", "n_gpus": world,
@@ -402,7 +416,8 @@ def run_relight(args):
             "config": {"workload": "C3-eval: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
                                    "S=7/VS=64 at %dx%d, fixed HDR env map" % (ns, P_SURFELS // 1000, WIDTH, HEIGHT),
                        "grid": "%d views x %d env maps, round-robin over ranks" % (N_VIEWS, n_env),
-                       "l2": "working set > L2 (light buffers 3.7 GB/frame)", "R": int(res["num_rendered"])},
+                       "l2": "working set > L2 (light buffers 3.7 GB/frame)", "R": int(res["num_rendered"]),
+                       "surfels_shaded": n_sh},
             "clocks": clk, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "shade_fwd", "achieved": round(ach, 1), "peak": pk["hbm_gbs"],
                          "peak_source": pk_src, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
@@ -554,6 +569,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
     ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
+    ap.add_argument("--reduce", default="overlap", choices=["overlap", "post"],
+                    help="N>1: overlap = segment-wise all-reduce issued inside the backward pass and captured in the graph; "
+                         "post = one all-reduce after the step")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "relight"],
                     help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")

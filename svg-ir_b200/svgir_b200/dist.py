@@ -69,9 +69,19 @@ class FlatGradBucket:
 
     `.grad` of each parameter is a VIEW into the buffer, so autograd accumulates straight into it
     (no torch.cat / copy before the collective) and the optimiser reads the reduced gradient in
-    place. `zero()` is one memset; `all_reduce()` is one collective per step."""
+    place. `zero()` is one memset; `all_reduce()` is one collective per step.
 
-    def __init__(self, params: Sequence[torch.Tensor], average: bool = False):
+    Overlap (`segments=[[param indices], ...]`, in the order the backward pass finishes them): the
+    buffer is laid out segment by segment and `begin_overlap()` arms post-accumulate hooks; as soon
+    as every parameter of a segment has received its gradient, that segment's all-reduce is issued
+    asynchronously (NCCL's own stream), so it runs under the rest of the backward pass -- for the
+    stage-2 step the rasteriser-side gradients (SH, opacity, scale, rotation: 56 of 87 floats per
+    surfel) travel while the shading backward kernel is still running. `finish_overlap()` issues
+    whatever is left and makes the current stream wait for all of it. The whole sequence can be
+    captured into a CUDA graph (pipeline.GraphedTrainingStep)."""
+
+    def __init__(self, params: Sequence[torch.Tensor], average: bool = False,
+                 segments: Optional[Sequence[Sequence[int]]] = None, extra_floats: int = 0):
         params = [p for p in params if p is not None]
         if not params:
             raise ValueError("FlatGradBucket needs at least one parameter")
@@ -81,15 +91,39 @@ class FlatGradBucket:
                 raise ValueError("all bucket parameters must be fp32 on one device")
         self.params = list(params)
         self.average = average
-        self.offsets = []
+        if segments is None:
+            segments = [list(range(len(self.params)))]
+        seen = sorted(i for seg in segments for i in seg)
+        if seen != list(range(len(self.params))):
+            raise ValueError("segments must name every parameter exactly once")
+        self.segments = [list(seg) for seg in segments if len(seg)]
+        self.offsets = [0] * len(self.params)
+        self.seg_bounds = []
         n = 0
-        for p in self.params:
-            self.offsets.append(n)
-            n += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned for vector loads
+        for seg in self.segments:
+            lo = n
+            for i in seg:
+                self.offsets[i] = n
+                n += (self.params[i].numel() + 3) // 4 * 4  # keep every view 16-byte aligned for vector loads
+            self.seg_bounds.append((lo, n))
+        # `extra_floats` scalars ride at the tail of the LAST segment (summed over ranks with it): the graphed
+        # step puts its binning-overflow flag there so every rank takes the same re-capture decision.
+        self.extra_offset = n
+        if extra_floats:
+            n += (int(extra_floats) + 3) // 4 * 4
+            self.seg_bounds[-1] = (self.seg_bounds[-1][0], n)
         self.numel = n
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.extra = self.flat[self.extra_offset:self.extra_offset + int(extra_floats)] if extra_floats else None
         self.attach()
         self._work = None
+        self._seg_of = {i: k for k, seg in enumerate(self.segments) for i in seg}
+        self._hooks = []
+        self._armed = False
+        self._pending = []
+        self._issued = []
+        self._ready = []
+        self.overlap_log = []   # segment issue order of the last overlapped step (tests / diagnostics)
 
     def attach(self):
         """(Re)binds p.grad to the buffer views (call again if something replaced .grad)."""
@@ -109,9 +143,11 @@ class FlatGradBucket:
         p, o = self.params[i], self.offsets[i]
         return self.flat[o:o + p.numel()].view_as(p)
 
-    def all_reduce(self, async_op: bool = False):
-        """Sum (or mean) over ranks. With async_op the NCCL kernel runs on its own stream and overlaps
-        whatever the caller enqueues next; call wait() before reading the gradients."""
+    def segment(self, k: int) -> torch.Tensor:
+        lo, hi = self.seg_bounds[k]
+        return self.flat[lo:hi]
+
+    def _gather_if_detached(self):
         if not self.attached():  # something (e.g. zero_grad(set_to_none=True)) replaced .grad: gather
             for p, o in zip(self.params, self.offsets):
                 if p.grad is not None:
@@ -119,6 +155,11 @@ class FlatGradBucket:
                 else:
                     self.flat[o:o + p.numel()].zero_()
             self.attach()
+
+    def all_reduce(self, async_op: bool = False):
+        """Sum (or mean) over ranks. With async_op the NCCL kernel runs on its own stream and overlaps
+        whatever the caller enqueues next; call wait() before reading the gradients."""
+        self._gather_if_detached()
         if world_size() == 1:
             return None
         if self.average:
@@ -130,6 +171,51 @@ class FlatGradBucket:
         if self._work is not None:
             self._work.wait()
             self._work = None
+
+    # ---- segment-wise all-reduce overlapped with the backward pass -----------------------------
+    def _issue(self, k: int):
+        if self._issued[k]:
+            return
+        self._issued[k] = True
+        self.overlap_log.append(k)
+        if world_size() == 1:
+            return
+        seg = self.segment(k)
+        if self.average:
+            seg.div_(world_size())
+        self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
+
+    def _on_grad(self, i: int):
+        if not self._armed:
+            return
+        k = self._seg_of[i]
+        self._ready[k] += 1
+        if self._ready[k] == len(self.segments[k]):
+            self._issue(k)
+
+    def begin_overlap(self):
+        """Arms the hooks for ONE backward pass in which every parameter receives at most one
+        accumulated gradient (one view per step). Gradients must accumulate into the attached views."""
+        if not self._hooks:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i)))
+        if not self.attached():
+            self.attach()
+        self._ready = [0] * len(self.segments)
+        self._issued = [False] * len(self.segments)
+        self._pending = []
+        self.overlap_log = []
+        self._armed = True
+
+    def finish_overlap(self):
+        """Issues the segments whose hooks did not all fire (parameters without a gradient this step),
+        then makes the current stream wait for every outstanding all-reduce."""
+        self._armed = False
+        for k in range(len(self.segments)):
+            self._issue(k)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
 
     @property
     def nbytes(self) -> int:

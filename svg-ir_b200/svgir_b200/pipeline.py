@@ -203,10 +203,13 @@ FUSED_LOSS = True
 
 
 def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg, gt_image, zero_grad=True,
-                  fused_loss: Optional[bool] = None):
+                  fused_loss: Optional[bool] = None, overlap_bucket=None):
     """One stage-2 iteration of the hot path: shade + rasterise forward, loss, backward. Gradients
     are left in .grad of pc.trainable() and env_param. Returns (loss tensor, result dict).
-    Both tails compute the same loss and gradients (tests/test_fused_loss_gpu.py)."""
+    Both tails compute the same loss and gradients (tests/test_fused_loss_gpu.py).
+    With `overlap_bucket` (dist.FlatGradBucket whose views are the .grad tensors) the per-surfel gradient
+    all-reduce is issued segment by segment from inside the backward pass and has completed (on the current
+    stream) when this returns."""
     if zero_grad:
         for t in pc.trainable() + [env_param]:
             t.grad = None
@@ -220,8 +223,25 @@ def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg,
     else:
         res = render_view(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
         loss = image_loss(res, gt_image)
+    if overlap_bucket is not None:
+        st = res.get("raster_state")
+        if overlap_bucket.extra is not None and st is not None:
+            # this rank's binning-overflow flag joins the last gradient segment: after the all-reduce every rank
+            # sees "some rank overflowed" and takes the same re-capture decision (GraphedTrainingStep.finish)
+            overlap_bucket.extra[0:1].copy_(st.t["num_rendered"][1:2])
+        overlap_bucket.begin_overlap()
     loss.backward()
+    if overlap_bucket is not None:
+        overlap_bucket.finish_overlap()
     return loss, res
+
+
+def reduce_segments(pc: SurfelModel) -> list:
+    """Bucket segments for `pc.trainable() + [env]` in the order the stage-2 backward finishes them: the
+    rasteriser's preprocess backward completes opacity / scaling / rotation / SH first (56 floats per surfel),
+    the shading backward then completes xyz (it also receives the view-direction gradient), base colour,
+    roughness, shading normals and the env map (31 floats per surfel + the map)."""
+    return [[1, 2, 3, 4], [0, 5, 6, 7, 8]]
 
 
 class GraphedTrainingStep:
@@ -241,8 +261,14 @@ class GraphedTrainingStep:
     """
 
     def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
-                 gt_image: torch.Tensor, bucket=None, warmup: int = 2):
+                 gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False):
         self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
+        # reduce_in_graph: the segment-wise NCCL all-reduce of `bucket` is captured INSIDE the graph, overlapped
+        # with the shading backward (FlatGradBucket.begin_overlap); the caller must not all-reduce again.
+        self.reduce_in_graph = bool(reduce_in_graph and bucket is not None)
+        if self.reduce_in_graph and bucket.extra is None:
+            raise ValueError("reduce_in_graph needs FlatGradBucket(..., extra_floats>=1) for the overflow flag")
+        self.flag_host = torch.zeros((1,), dtype=torch.float32).pin_memory() if self.reduce_in_graph else None
         dev = pc.xyz.device
         self.dev = dev
         self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
@@ -274,7 +300,8 @@ class GraphedTrainingStep:
             for _ in range(self.warmup):  # eager: sizes the binning hint, warms allocators / lazy inits
                 self._zero()
                 with raster.count_mode("speculative"):
-                    _, r = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False)
+                    _, r = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False,
+                                         overlap_bucket=self.bucket if self.reduce_in_graph else None)
             R = int(r["num_rendered"])
             raster.reserve(self.dev, self.pc.xyz.shape[0], self.cam.image_width, self.cam.image_height,
                            int(R * raster.ASYNC_SLACK) + raster.ASYNC_MARGIN)
@@ -288,7 +315,10 @@ class GraphedTrainingStep:
             if self.bucket is not None:
                 self.bucket.zero()
             with raster.count_mode("async", owner_resolves=True):
-                self.loss, self.res = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False)
+                self.loss, self.res = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False,
+                                                    overlap_bucket=self.bucket if self.reduce_in_graph else None)
+            if self.reduce_in_graph:
+                self.flag_host.copy_(self.bucket.extra[0:1], non_blocking=True)
         self.launches_per_step = launch_count() - n0  # svgir kernels inside the graph
         self.captures += 1
 
@@ -328,12 +358,17 @@ class GraphedTrainingStep:
             torch.cuda.current_stream(self.dev).synchronize()
             st.pending = True  # the graph re-wrote count_host
             try:
-                return st.resolve()
+                R = st.resolve()   # raises the capacity hint on a local overflow
+                if not (self.reduce_in_graph and float(self.flag_host[0]) > 0):
+                    return R
+                # another rank overflowed: every rank re-captures and re-runs together (the step's
+                # all-reduce lives in the graph, so the replays must stay matched across ranks)
             except raster.CapacityOverflow:
-                self.graph = None
-                self._capture()
-                self.graph.replay()
-                st = self.res["raster_state"]
+                pass
+            self.graph = None
+            self._capture()
+            self.graph.replay()
+            st = self.res["raster_state"]
         raise RuntimeError("GraphedTrainingStep: binning capacity did not converge")
 
 

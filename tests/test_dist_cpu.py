@@ -46,6 +46,39 @@ def test_flat_bucket_views_single_process():
     assert bk.attached() and torch.allclose(a.grad, torch.full((5, 3), 3.0))
 
 
+def test_segmented_bucket_issues_segments_in_backward_order():
+    """Single process: segment k's reduce is issued as soon as all of its parameters have their gradient,
+    i.e. in the order the backward pass finishes them, and the extra slot sits in the last segment."""
+    a = torch.randn(6, 2, requires_grad=True)
+    b = torch.randn(7, requires_grad=True)
+    c = torch.randn(3, 3, requires_grad=True)
+    bk = D.FlatGradBucket([a, b, c], segments=[[1], [0, 2]], extra_floats=1)
+    assert bk.offsets[1] == 0 and bk.seg_bounds[0] == (0, 8)
+    assert bk.seg_bounds[1][1] == bk.numel and bk.extra.numel() == 1
+    assert bk.extra.data_ptr() == bk.flat.data_ptr() + 4 * bk.extra_offset
+    # forward order a -> c -> b means backward finishes b first, then c, then a
+    y = ((a * 2).sum() + (c * 3).sum()) * 1.0
+    z = y + (b * 5).sum()
+    bk.zero()
+    bk.extra[0] = 1.0
+    bk.begin_overlap()
+    z.backward()
+    assert bk.overlap_log == [0, 1]
+    bk.finish_overlap()
+    assert bk.attached()
+    assert torch.allclose(a.grad, torch.full((6, 2), 2.0)) and torch.allclose(b.grad, torch.full((7,), 5.0))
+    assert torch.allclose(c.grad, torch.full((3, 3), 3.0)) and float(bk.extra[0]) == 1.0
+    # a parameter without a gradient this step: finish_overlap() still issues its segment
+    bk.zero()
+    bk.begin_overlap()
+    (b * 1.0).sum().backward()
+    assert bk.overlap_log == [0]
+    bk.finish_overlap()
+    assert bk.overlap_log == [0, 1]
+    with pytest.raises(ValueError):
+        D.FlatGradBucket([a, b, c], segments=[[0], [0, 2]])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -79,6 +112,18 @@ def _worker(rank, world, port, q):
     exp_env = 5 * 2 * env.detach()
     ok = (torch.allclose(base.grad, exp_base, rtol=1e-5, atol=1e-5) and torch.allclose(rough.grad, exp_rough)
           and torch.allclose(env.grad, exp_env, rtol=1e-5, atol=1e-5) and bk.attached())
+    # the same exchange, segment-wise from inside the backward pass (what GraphedTrainingStep captures)
+    bk2 = D.FlatGradBucket([base, rough, env], segments=[[2, 1], [0]], extra_floats=1)
+    bk2.zero()
+    bk2.extra[0] = float(rank == 1)      # "rank 1 overflowed its bins"
+    bk2.begin_overlap()
+    loss = sum(((base - targets[v]) ** 2).sum() * (v + 1) + (rough * (v + 1)).sum() + (env * env).sum()
+               for v in D.views_for_rank(5, rank, world))
+    loss.backward()
+    bk2.finish_overlap()
+    ok = ok and (torch.allclose(base.grad, exp_base, rtol=1e-5, atol=1e-5) and torch.allclose(rough.grad, exp_rough)
+                 and torch.allclose(env.grad, exp_env, rtol=1e-5, atol=1e-5) and bk2.attached()
+                 and float(bk2.extra[0]) == 1.0 and sorted(bk2.overlap_log) == [0, 1])
     t = D.max_over_ranks(float(rank + 1), dev)
     q.put((rank, bool(ok), t, len(mine)))
     dist.barrier()

@@ -1,0 +1,110 @@
+"""View-sharded data parallel step over NCCL on 2 GPUs of one box: each rank renders its own
+view inside a CUDA graph whose backward pass issues the segment-wise gradient all-reduce; the reduced
+gradient on every rank must equal the SUM of the two views' gradients computed locally (eagerly, no
+collective) on that same rank -- so the check needs no cross-process comparison. Also exercises the
+matched re-capture: one rank's binning overflow must make BOTH ranks re-capture (the overflow flag
+travels in the last gradient segment). Skipped with fewer than 2 GPUs (`gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                          LOCAL_RANK=str(rank))
+        from svgir_b200 import dist as D, pipeline, raster, scene
+        r, w, dev = D.init_from_env()
+        P, W, H, Ns = 6000, 160, 128, 16
+        cloud = scene.make_surfels(P, seed=11)
+        mats = scene.make_materials(cloud, Ns, seed=12, env_hw=(16, 32))
+        cams = [pipeline.camera_from_scene(scene.look_at_camera(W, H, v, 4), dev) for v in range(4)]
+        gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(2)]
+        bg = torch.zeros(3, device=dev)
+
+        def model():
+            pc = pipeline.model_from_scene(cloud, mats, dev)
+            env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+            return pc, env
+
+        # local reference: both views rendered eagerly on this rank, gradients summed by autograd
+        pc_e, env_e = model()
+        pc_g, env_g = model()
+        params = pc_g.trainable() + [env_g]
+        bucket = D.FlatGradBucket(params, segments=pipeline.reduce_segments(pc_g), extra_floats=1)
+        runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0], bucket=bucket, reduce_in_graph=True)
+        worst = 0.0
+        for step in range(3):
+            views = [(2 * step + k) % 4 for k in range(world)]
+            for t in pc_e.trainable() + [env_e]:
+                t.grad = None
+            for v in views:
+                pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v % 2], zero_grad=False)
+            runner(cams[views[rank]], gts[views[rank] % 2])
+            torch.cuda.synchronize()
+            assert sorted(bucket.overlap_log) == [0, 1]
+            for a, b in zip(params, pc_e.trainable() + [env_e]):
+                rel = float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20))
+                worst = max(worst, rel)
+        caps_before = runner.captures
+        # Matched re-capture. Both ranks drop their graph; rank 1 re-captures with NO slack in its binning capacity.
+        # Then the surfels grow 1.2x (scaling is a per-step input of the graph): rank 1 overflows, rank 0 (2x slack)
+        # does not -- the flag in the last gradient segment must make BOTH re-capture and re-run together.
+        old = (raster.ASYNC_SLACK, raster.ASYNC_MARGIN)
+        if rank == 1:
+            raster._CAP_HINT.clear()
+            raster.ASYNC_SLACK, raster.ASYNC_MARGIN = 1.0, 16
+        runner.graph = None
+        runner(cams[rank], gts[rank])
+        raster.ASYNC_SLACK, raster.ASYNC_MARGIN = old
+        with torch.no_grad():
+            pc_g.scaling.mul_(1.2)
+            pc_e.scaling.mul_(1.2)
+        runner(cams[rank], gts[rank])
+        torch.cuda.synchronize()
+        for t in pc_e.trainable() + [env_e]:
+            t.grad = None
+        for v in range(world):
+            pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v], zero_grad=False)
+        for a, b in zip(params, pc_e.trainable() + [env_e]):
+            worst = max(worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+        q.put((rank, worst, runner.captures - caps_before, None))
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    except Exception as e:  # surface the failure instead of a hang
+        import traceback
+        q.put((rank, 1e9, -1, traceback.format_exc()))
+
+
+def test_two_rank_graphed_step_overlapped_allreduce():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
+    for rank, worst, recaptures, err in res:
+        assert err is None, err
+        assert worst < 1e-3, (rank, worst)
+        # one capture after the forced graph drop, one more on rank 1's overflow -- on BOTH ranks
+        assert recaptures == 2, (rank, recaptures)
