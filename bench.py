@@ -331,6 +331,18 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_reference_sample(1, 0)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # drop the captured graph before the communicator goes away; with collectives captured INSIDE the graph
+        # (--reduce overlap) NCCL's teardown was seen to block (gpurun_out/s2), so that mode leaves without it
+        runner = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if overlap:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -569,9 +581,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
     ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
-    ap.add_argument("--reduce", default="overlap", choices=["overlap", "post"],
-                    help="N>1: overlap = segment-wise all-reduce issued inside the backward pass and captured in the graph; "
-                         "post = one all-reduce after the step")
+    ap.add_argument("--reduce", default="post", choices=["overlap", "post"],
+                    help="N>1: post (default) = one NCCL all-reduce of the flat gradient bucket right after the step's graph; "
+                         "overlap = segment-wise all-reduce issued inside the backward pass and captured in the graph "
+                         "(measured slower on B200 x2: the NCCL kernel takes SMs from the shading backward, 657 vs 678 it/s)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="train", choices=["train", "relight"],
                     help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")

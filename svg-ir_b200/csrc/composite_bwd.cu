@@ -324,10 +324,10 @@ struct LaneBwdLayout {
     static constexpr int LCH = REC_F4 + SP / 4 + NV;          // float4 chunks loaded per instance
     static constexpr int NG = 8 + S + NV;                     // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
     static constexpr int GS = NG | 1;                         // odd stride
-    static constexpr int G_OFF = LBATCH * STRIDE;
+    static constexpr int G_OFF = 2 * LBATCH * STRIDE;            // stage is double-buffered (LDGSTS pipeline)
     static constexpr int HITS_OFF = (G_OFF + TILE_PIX * GS + 3) & ~3;   // 16-B aligned
     static constexpr int IDS_OFF = HITS_OFF + NWARP * 32 * HIT_STRIDE_L;
-    static constexpr int SMEM_FLOATS = IDS_OFF + LBATCH;
+    static constexpr int SMEM_FLOATS = IDS_OFF + 3 * LBATCH;      // 3-slot ring of staged surfel ids
 };
 
 template <int S_T, int NV_T, bool RGSS>
@@ -347,10 +347,10 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     static_assert(NG + 5 <= 32, "lane mode needs one lane per gradient channel plus 5 geo lanes");
 
     extern __shared__ __align__(16) float smem[];
-    float* stage = smem;                                   // [LBATCH][STRIDE]
+    float* stage = smem;                                   // [2][LBATCH][STRIDE]
     float* G = smem + LY::G_OFF;                           // [256][GS]
     float* hits = smem + LY::HITS_OFF;                     // [NWARP][32][HIT_STRIDE_L]
-    int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [LBATCH]
+    int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [3][LBATCH]
     __shared__ int tile_max_s;
 
     const int W = c.W, H = c.H;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     if (tid == 0) tile_max_s = 0;
     if constexpr (NVP != NV) {  // zero the padding channels of the transposed rows once
         constexpr int PADC = NVP - NV;
-        for (int q = tid; q < LBATCH * 4 * PADC; q += TILE_PIX) {
+        for (int q = tid; q < 2 * LBATCH * 4 * PADC; q += TILE_PIX) {
             const int i = q / (4 * PADC), r = q - i * 4 * PADC;
             stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / PADC) * NVP + NV + r % PADC] = 0.f;
         }
@@ -460,37 +460,60 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     float T = T_final, A = 0.f, last_alpha = 0.f, V_last = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    for (int top = tile_max; top > 0; top -= LBATCH) {
+    // ---- asynchronous staging pipeline (same scheme as the forward compositor) ---------------------
+    // batch k = sorted positions top_k-1 ... top_k-nb (back to front), top_k = tile_max - k*LBATCH
+    auto issue_ids = [&](int top, int slot) {
         const int nb = min(LBATCH, top);
-        __syncthreads();  // every warp is done with the previous batch's staged records
+        if (tid < nb) cp_async4(ids + slot * LBATCH + tid, point_list + range.x + top - 1 - tid);
+    };
+    auto issue_data = [&](int top, int slot, int buf) {
+        const int nb = min(LBATCH, top);
+        float* sb = stage + buf * LBATCH * STRIDE;
+        const int* idl = ids + slot * LBATCH;
         for (int q = tid; q < nb * LCH; q += TILE_PIX) {
             const int i = q / LCH, ch = q - i * LCH;
-            const int id = (int)point_list[range.x + top - 1 - i];
-            float* dst = stage + i * STRIDE;
-            float4 v;
+            const int id = idl[i];
+            float* dst = sb + i * STRIDE;
             if (ch < REC_F4) {
-                v = __ldg(rec + (size_t)id * REC_F4 + ch);
-                if (ch == 0) ids[i] = id;
-                reinterpret_cast<float4*>(dst)[ch] = v;
+                cp_async16(dst + 4 * ch, rec + (size_t)id * REC_F4 + ch);
             } else if (ch < REC_F4 + SP / 4) {
                 const int f0 = (ch - REC_F4) * 4;
                 const float* src = features + (size_t)id * S + f0;
-                if ((S & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
+                if ((S & 3) == 0) cp_async16(dst + 4 * ch, src);
                 else {
-                    v.x = f0 + 0 < S ? __ldg(src + 0) : 0.f;
-                    v.y = f0 + 1 < S ? __ldg(src + 1) : 0.f;
-                    v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
-                    v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (f0 + e < S) cp_async4(dst + 4 * ch + e, src + e);
+                        else dst[4 * ch + e] = 0.f;
+                    }
                 }
-                reinterpret_cast<float4*>(dst)[ch] = v;
             } else {
                 const int cidx = ch - REC_F4 - SP / 4;
-                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + cidx);
+                const float* src = vfeatures + (size_t)id * (4 * NV) + 4 * cidx;
                 float* t = dst + SVGIR_REC_FLOATS + SP + cidx;   // transpose: vertex-major rows of NVP channels
-                t[0] = v.x; t[NVP] = v.y; t[2 * NVP] = v.z; t[3 * NVP] = v.w;
+                cp_async4(t, src); cp_async4(t + NVP, src + 1);
+                cp_async4(t + 2 * NVP, src + 2); cp_async4(t + 3 * NVP, src + 3);
             }
         }
-        __syncthreads();
+    };
+    issue_ids(tile_max, 0);
+    if (tile_max > LBATCH) issue_ids(tile_max - LBATCH, 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    issue_data(tile_max, 0, 0);
+    cp_async_commit();
+
+    int kb = 0;
+    for (int top = tile_max; top > 0; top -= LBATCH, kb++) {
+        const int nb = min(LBATCH, top);
+        cp_async_wait<0>();
+        __syncthreads();  // batch kb is staged; every warp is done with batch kb-1
+        if (top > LBATCH) issue_data(top - LBATCH, (kb + 1) % 3, (kb + 1) & 1);
+        if (top > 2 * LBATCH) issue_ids(top - 2 * LBATCH, (kb + 2) % 3);
+        cp_async_commit();
+        const float* sb = stage + (kb & 1) * LBATCH * STRIDE;
+        const int* idb = ids + (kb % 3) * LBATCH;
 
         // per-warp cull: instances behind every pixel's last contributor, or whose alpha >= 1/255 ellipse cannot
         // reach this warp's 8x4 pixels, are never evaluated
@@ -498,7 +521,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
         {
             bool keep = false;
             if (lane < nb && top - 1 - lane < warp_max) {
-                const float4* r = reinterpret_cast<const float4*>(stage + lane * STRIDE);
+                const float4* r = reinterpret_cast<const float4*>(sb + lane * STRIDE);
                 const float4 q0 = r[0];
                 const float2 q1 = *reinterpret_cast<const float2*>(r + 1);
                 keep = footprint_overlaps(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, wx0f, wy0f, WARP_PX_W - 1.f, WARP_PX_H - 1.f);
@@ -510,7 +533,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
             const int j = __ffs(m) - 1;
             m &= m - 1;
             const int pos = top - 1 - j;  // 0-based position in the tile's sorted list
-            const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+            const float4* r = reinterpret_cast<const float4*>(sb + j * STRIDE);
             const float4 q0 = r[0];
             const float4 q1 = r[1];
             PairEval e;
@@ -551,7 +574,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
                     V += q4.w * gN[0] + q5.x * gN[1] + q5.y * gN[2];
                 }
                 V = fmaf(depth_k, gDn, V);
-                const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+                const float* f = sb + j * STRIDE + SVGIR_REC_FLOATS;
                 if (feat_to_alpha) {
 #pragma unroll
                     for (int ch = 0; ch < S; ch++) V = fmaf(f[ch], gF[ch], V);
@@ -603,7 +626,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
             }
             __syncwarp();
             // this warp's complete contribution to instance j: straight to L2
-            const int id = ids[j];
+            const int id = idb[j];
             if (l_k0 >= 16) {
                 if (a0 != 0.f) atomicAdd(dL_dfeatures + (size_t)id * S + (l_k0 - 16), a0);
             } else if (l_k0 >= 0) {

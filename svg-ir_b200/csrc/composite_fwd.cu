@@ -23,7 +23,7 @@ namespace svgir {
 #define FWD_BATCH 64
 
 template <int S_T, int NV_T, bool RGSS>
-__global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
+__global__ void __launch_bounds__(TILE_PIX, S_T >= 0 && S_T <= 8 ? 4 : 1) composite_fwd_kernel(
     const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
     const float4* __restrict__ rec, const uint2* __restrict__ ranges,
     const uint32_t* __restrict__ point_list, const int32_t* __restrict__ num_rendered,
@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
     const int LCH = REC_F4 + SP / 4 + NV;  // float4 chunks loaded per instance
 
     extern __shared__ __align__(16) float smem[];
-    float* stage = smem;                                  // [FWD_BATCH][STRIDE]
-    float* wsum = smem + FWD_BATCH * STRIDE;              // [2][8 warps][FWD_BATCH] warp-private blend-weight sums
-    int* ids = reinterpret_cast<int*>(wsum + 2 * 8 * FWD_BATCH);  // [2][FWD_BATCH]
+    float* stage = smem;                                  // [2][FWD_BATCH][STRIDE]  double-buffered (LDGSTS pipeline)
+    float* wsum = smem + 2 * FWD_BATCH * STRIDE;          // [2][8 warps][FWD_BATCH] warp-private blend-weight sums
+    int* ids = reinterpret_cast<int*>(wsum + 2 * 8 * FWD_BATCH);  // [4][FWD_BATCH] ring of staged surfel ids
 
     if (num_rendered[1]) return;  // binning overflowed: nothing valid to render
     const int W = c.W, H = c.H;
@@ -91,15 +91,69 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
 
     for (int i = tid; i < 2 * 8 * FWD_BATCH; i += TILE_PIX) wsum[i] = 0.f;
     if (PACKED && NVP_T != NV_T) {  // zero the padding channels of the transposed rows once
-        for (int q = tid; q < FWD_BATCH * 4 * (NVP_T - NV_T); q += TILE_PIX) {
+        for (int q = tid; q < 2 * FWD_BATCH * 4 * (NVP_T - NV_T); q += TILE_PIX) {
             const int i = q / (4 * (NVP_T - NV_T)), r = q - i * 4 * (NVP_T - NV_T);
             stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / (NVP_T - NV_T)) * NVP_T + NV_T + r % (NVP_T - NV_T)] = 0.f;
         }
     }
 
+    // ---- asynchronous staging pipeline -----------------------------------------------------------
+    // While batch k is composited, the records + feature rows of batch k+1 stream into the other stage
+    // buffer and the surfel ids of batch k+2 into the id ring, all with LDGSTS (cp.async: no registers,
+    // no scoreboard wait); the vfeature rows are transposed on the way by 4-byte copies. One barrier per
+    // batch: it publishes batch k and retires every warp's reads of batch k-1.
+    auto issue_ids = [&](int base, int slot) {
+        const int nb = min(FWD_BATCH, total - base);
+        if (tid < nb) cp_async4(ids + slot * FWD_BATCH + tid, point_list + range.x + base + tid);
+    };
+    auto issue_data = [&](int base, int slot, int buf) {
+        const int nb = min(FWD_BATCH, total - base);
+        float* sb = stage + buf * FWD_BATCH * STRIDE;
+        const int* idl = ids + slot * FWD_BATCH;
+        for (int q = tid; q < nb * LCH; q += TILE_PIX) {
+            const int i = q / LCH, ch = q - i * LCH;
+            const int id = idl[i];
+            float* dst = sb + i * STRIDE;
+            if (ch < REC_F4) {
+                cp_async16(dst + 4 * ch, rec + (size_t)id * REC_F4 + ch);
+            } else if (ch < REC_F4 + SP / 4) {
+                const int f0 = (ch - REC_F4) * 4;
+                const float* src = features + (size_t)id * S + f0;
+                if ((S & 3) == 0) cp_async16(dst + 4 * ch, src);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (f0 + e < S) cp_async4(dst + 4 * ch + e, src + e);
+                        else dst[4 * ch + e] = 0.f;
+                    }
+                }
+            } else {
+                const int cidx = ch - REC_F4 - SP / 4;
+                const float* src = vfeatures + (size_t)id * (4 * NV) + 4 * cidx;
+                if (PACKED) {  // transpose: vertex-major rows of NVP channels
+                    float* t = dst + SVGIR_REC_FLOATS + SP + cidx;
+                    cp_async4(t, src); cp_async4(t + NVP_T, src + 1);
+                    cp_async4(t + 2 * NVP_T, src + 2); cp_async4(t + 3 * NVP_T, src + 3);
+                } else {
+                    cp_async16(dst + 4 * ch, src);
+                }
+            }
+        }
+    };
+    if (total > 0) {
+        issue_ids(0, 0);
+        if (FWD_BATCH < total) issue_ids(FWD_BATCH, 1);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        issue_data(0, 0, 0);
+        cp_async_commit();
+    }
+
     int nbatch = 0;
     for (int base = 0; base < total; base += FWD_BATCH, nbatch++) {
         const int par = nbatch & 1;
+        cp_async_wait<0>();
         const int ndone = __syncthreads_count(done);
         // flush the previous batch's per-instance weight sums (one atomic per tile x instance)
         if (nbatch > 0 && tid < FWD_BATCH) {
@@ -107,43 +161,14 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
             float wv = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; k++) { wv += ws[k * FWD_BATCH]; ws[k * FWD_BATCH] = 0.f; }
-            if (wv != 0.f) atomicAdd(&out_weights[ids[(par ^ 1) * FWD_BATCH + tid]], wv);
+            if (wv != 0.f) atomicAdd(&out_weights[ids[((nbatch - 1) & 3) * FWD_BATCH + tid]], wv);
         }
         if (ndone == TILE_PIX) break;
         const int nb = min(FWD_BATCH, total - base);
-        // cooperative 128-bit staging of records + feature rows
-        for (int q = tid; q < nb * LCH; q += TILE_PIX) {
-            const int i = q / LCH, ch = q - i * LCH;
-            const int id = (int)point_list[range.x + base + i];
-            float* dst = stage + i * STRIDE;
-            float4 v;
-            if (ch < REC_F4) {
-                v = __ldg(rec + (size_t)id * REC_F4 + ch);
-                if (ch == 0) ids[par * FWD_BATCH + i] = id;
-                reinterpret_cast<float4*>(dst)[ch] = v;
-            } else if (ch < REC_F4 + SP / 4) {
-                const int f0 = (ch - REC_F4) * 4;
-                const float* src = features + (size_t)id * S + f0;
-                if ((S & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
-                else {
-                    v.x = f0 + 0 < S ? __ldg(src + 0) : 0.f;
-                    v.y = f0 + 1 < S ? __ldg(src + 1) : 0.f;
-                    v.z = f0 + 2 < S ? __ldg(src + 2) : 0.f;
-                    v.w = f0 + 3 < S ? __ldg(src + 3) : 0.f;
-                }
-                reinterpret_cast<float4*>(dst)[ch] = v;
-            } else {
-                const int cidx = ch - REC_F4 - SP / 4;
-                v = __ldg(reinterpret_cast<const float4*>(vfeatures + (size_t)id * (4 * NV)) + cidx);
-                if (PACKED) {  // transpose: vertex-major rows of NVP channels
-                    float* t = dst + SVGIR_REC_FLOATS + SP + cidx;
-                    t[0] = v.x; t[NVP_T] = v.y; t[2 * NVP_T] = v.z; t[3 * NVP_T] = v.w;
-                } else {
-                    reinterpret_cast<float4*>(dst)[ch] = v;
-                }
-            }
-        }
-        __syncthreads();
+        if (base + FWD_BATCH < total) issue_data(base + FWD_BATCH, (nbatch + 1) & 3, par ^ 1);
+        if (base + 2 * FWD_BATCH < total) issue_ids(base + 2 * FWD_BATCH, (nbatch + 2) & 3);
+        cp_async_commit();
+        const float* sb = stage + par * FWD_BATCH * STRIDE;
 
         // per-warp footprint cull: one bit per staged instance whose alpha >= 1/255 ellipse can reach this
         // warp's 8x4 pixels; the others are never evaluated
@@ -154,7 +179,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
             const int i = h * 32 + lane;
             bool keep = false;
             if (warp_live && i < nb) {
-                const float4* r = reinterpret_cast<const float4*>(stage + i * STRIDE);
+                const float4* r = reinterpret_cast<const float4*>(sb + i * STRIDE);
                 const float4 q0 = r[0];
                 const float2 q1 = *reinterpret_cast<const float2*>(r + 1);
                 keep = footprint_overlaps(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, wx0f, wy0f, WARP_PX_W - 1.f, WARP_PX_H - 1.f);
@@ -168,7 +193,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
             while (m) {
                 const int j = h * 32 + __ffs(m) - 1;
                 m &= m - 1;
-                const float4* r = reinterpret_cast<const float4*>(stage + j * STRIDE);
+                const float4* r = reinterpret_cast<const float4*>(sb + j * STRIDE);
                 const float4 q0 = r[0];
                 const float4 q1 = r[1];
                 PairEval e;
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
                         N[1] = fmaf(q5.x, w, N[1]);
                         N[2] = fmaf(q5.y, w, N[2]);
                     }
-                    const float* f = stage + j * STRIDE + SVGIR_REC_FLOATS;
+                    const float* f = sb + j * STRIDE + SVGIR_REC_FLOATS;
 #pragma unroll
                     for (int ch = 0; ch < MAXS; ch++)
                         if (ch < S) F[ch] = fmaf(f[ch], w, F[ch]);
@@ -250,14 +275,15 @@ __global__ void __launch_bounds__(TILE_PIX) composite_fwd_kernel(
             }
         }
     }
-    // flush the last computed batch's weight sums
+    // flush the last computed batch's weight sums (already flushed and zeroed if the loop broke out early)
+    cp_async_wait<0>();
     __syncthreads();
     if (nbatch > 0 && tid < FWD_BATCH) {
         const int par = (nbatch - 1) & 1;
         float wv = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; k++) wv += wsum[(par * 8 + k) * FWD_BATCH + tid];
-        if (wv != 0.f) atomicAdd(&out_weights[ids[par * FWD_BATCH + tid]], wv);
+        if (wv != 0.f) atomicAdd(&out_weights[ids[((nbatch - 1) & 3) * FWD_BATCH + tid]], wv);
     }
 
     if (inside) {
@@ -299,7 +325,7 @@ static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
     const int SP = (c.S + 3) & ~3;
     const int nvf = (S_T >= 0 && NV_T > 0) ? 4 * ((NV_T + 3) & ~3) : c.VS;  // packed kernels pad the transposed rows
     const int stride = SVGIR_REC_FLOATS + SP + nvf;
-    const size_t smem = sizeof(float) * ((size_t)FWD_BATCH * stride + 2 * 8 * FWD_BATCH + 2 * FWD_BATCH);
+    const size_t smem = sizeof(float) * ((size_t)2 * FWD_BATCH * stride + 2 * 8 * FWD_BATCH + 4 * FWD_BATCH);
     auto k = composite_fwd_kernel<S_T, NV_T, RGSS>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
