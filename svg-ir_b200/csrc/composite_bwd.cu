@@ -313,6 +313,9 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
 // (warp, instance) -- no warp-private accumulators, no flush pass, one barrier pair per 32 instances, and
 // 46 KB instead of 81 KB of shared memory per CTA (4 resident CTAs per SM instead of 2).
 #define LBATCH 32
+#ifndef LSTAGES
+#define LSTAGES 3   // staging ring depth of the lane kernel
+#endif
 #define HIT_STRIDE_L 12   // 3 float4 per hit: 128-bit stores/loads are conflict-free at this stride
 
 template <int S_T, int NV_T>
@@ -324,14 +327,14 @@ struct LaneBwdLayout {
     static constexpr int LCH = REC_F4 + SP / 4 + NV;          // float4 chunks loaded per instance
     static constexpr int NG = 8 + S + NV;                     // pixel-gradient row: 1,gC3,gN3,gD',gF,gVF
     static constexpr int GS = NG | 1;                         // odd stride
-    static constexpr int G_OFF = 2 * LBATCH * STRIDE;            // stage is double-buffered (LDGSTS pipeline)
+    static constexpr int G_OFF = LSTAGES * LBATCH * STRIDE;      // stage is a ring of LSTAGES buffers
     static constexpr int HITS_OFF = (G_OFF + TILE_PIX * GS + 3) & ~3;   // 16-B aligned
     static constexpr int IDS_OFF = HITS_OFF + NWARP * 32 * HIT_STRIDE_L;
-    static constexpr int SMEM_FLOATS = IDS_OFF + 3 * LBATCH;      // 3-slot ring of staged surfel ids
+    static constexpr int SMEM_FLOATS = IDS_OFF + 8 * LBATCH;      // 8-slot ring of staged surfel ids
 };
 
 template <int S_T, int NV_T, bool RGSS>
-__global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
+__global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
     const float4* __restrict__ rec, const uint2* __restrict__ ranges,
     const uint32_t* __restrict__ point_list, const float* __restrict__ final_T,
@@ -347,11 +350,13 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     static_assert(NG + 5 <= 32, "lane mode needs one lane per gradient channel plus 5 geo lanes");
 
     extern __shared__ __align__(16) float smem[];
-    float* stage = smem;                                   // [2][LBATCH][STRIDE]
+    float* stage = smem;                                   // [LSTAGES][LBATCH][STRIDE]
     float* G = smem + LY::G_OFF;                           // [256][GS]
     float* hits = smem + LY::HITS_OFF;                     // [NWARP][32][HIT_STRIDE_L]
-    int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [3][LBATCH]
+    int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [8][LBATCH]
     __shared__ int tile_max_s;
+    __shared__ __align__(8) uint64_t full_bar[LSTAGES];    // batch staged   (256 LDGSTS-completion arrivals)
+    __shared__ __align__(8) uint64_t empty_bar[LSTAGES];   // batch consumed (one arrival per warp)
 
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
@@ -435,10 +440,15 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     const float* Glane = G + l_gch;
 
     // ---- tile-wide traversal start --------------------------------------------------------------
-    if (tid == 0) tile_max_s = 0;
+    if (tid == 0) {
+        tile_max_s = 0;
+#pragma unroll
+        for (int i = 0; i < LSTAGES; i++) { mbar_init(&full_bar[i], TILE_PIX); mbar_init(&empty_bar[i], TILE_PIX / 32); }
+        mbar_fence_init();
+    }
     if constexpr (NVP != NV) {  // zero the padding channels of the transposed rows once
         constexpr int PADC = NVP - NV;
-        for (int q = tid; q < 2 * LBATCH * 4 * PADC; q += TILE_PIX) {
+        for (int q = tid; q < LSTAGES * LBATCH * 4 * PADC; q += TILE_PIX) {
             const int i = q / (4 * PADC), r = q - i * 4 * PADC;
             stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / PADC) * NVP + NV + r % PADC] = 0.f;
         }
@@ -460,16 +470,19 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
     float T = T_final, A = 0.f, last_alpha = 0.f, V_last = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    // ---- asynchronous staging pipeline (same scheme as the forward compositor) ---------------------
-    // batch k = sorted positions top_k-1 ... top_k-nb (back to front), top_k = tile_max - k*LBATCH
-    auto issue_ids = [&](int top, int slot) {
+    // ---- asynchronous staging ring (same scheme as the forward compositor, composite_fwd.cu) ----------
+    // batch b = sorted positions top_b-1 ... top_b-nb (back to front), top_b = tile_max - b*LBATCH. Records of batch
+    // k+2 and ids of batch k+4 are requested with LDGSTS at the end of round k; full_bar / empty_bar replace the
+    // CTA-wide barriers, so warps drift up to LSTAGES-1 batches apart instead of idling at a __syncthreads.
+    auto issue_ids = [&](int b) {
+        const int top = tile_max - b * LBATCH;
         const int nb = min(LBATCH, top);
-        if (tid < nb) cp_async4(ids + slot * LBATCH + tid, point_list + range.x + top - 1 - tid);
+        if (tid < nb) cp_async4(ids + (b & 7) * LBATCH + tid, point_list + range.x + top - 1 - tid);
     };
-    auto issue_data = [&](int top, int slot, int buf) {
-        const int nb = min(LBATCH, top);
+    auto issue_data = [&](int b, int buf) {
+        const int nb = min(LBATCH, tile_max - b * LBATCH);
         float* sb = stage + buf * LBATCH * STRIDE;
-        const int* idl = ids + slot * LBATCH;
+        const int* idl = ids + (b & 7) * LBATCH;
         for (int q = tid; q < nb * LCH; q += TILE_PIX) {
             const int i = q / LCH, ch = q - i * LCH;
             const int id = idl[i];
@@ -480,12 +493,10 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
                 const int f0 = (ch - REC_F4) * 4;
                 const float* src = features + (size_t)id * S + f0;
                 if ((S & 3) == 0) cp_async16(dst + 4 * ch, src);
-                else {
+                else {  // the padding floats [S, SP) of the row are never read
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
+                    for (int e = 0; e < 4; e++)
                         if (f0 + e < S) cp_async4(dst + 4 * ch + e, src + e);
-                        else dst[4 * ch + e] = 0.f;
-                    }
                 }
             } else {
                 const int cidx = ch - REC_F4 - SP / 4;
@@ -496,24 +507,24 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
             }
         }
     };
-    issue_ids(tile_max, 0);
-    if (tile_max > LBATCH) issue_ids(tile_max - LBATCH, 1);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    issue_data(tile_max, 0, 0);
-    cp_async_commit();
+    const int nrounds = (tile_max + LBATCH - 1) / LBATCH;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (b < nrounds) issue_ids(b);
+    cp_async_wait_all();
+    __syncthreads();   // ids of batches 0..3 are visible
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+        if (b < nrounds) { issue_data(b, b); cp_async_mbar_arrive_noinc(&full_bar[b]); }
 
-    int kb = 0;
-    for (int top = tile_max; top > 0; top -= LBATCH, kb++) {
+    int st = 0;          // kb % LSTAGES
+    unsigned ph = 0;     // (kb / LSTAGES) & 1
+    for (int kb = 0; kb < nrounds; kb++) {
+        const int top = tile_max - kb * LBATCH;
         const int nb = min(LBATCH, top);
-        cp_async_wait<0>();
-        __syncthreads();  // batch kb is staged; every warp is done with batch kb-1
-        if (top > LBATCH) issue_data(top - LBATCH, (kb + 1) % 3, (kb + 1) & 1);
-        if (top > 2 * LBATCH) issue_ids(top - 2 * LBATCH, (kb + 2) % 3);
-        cp_async_commit();
-        const float* sb = stage + (kb & 1) * LBATCH * STRIDE;
-        const int* idb = ids + (kb % 3) * LBATCH;
+        mbar_wait(&full_bar[st], ph);
+        const float* sb = stage + st * LBATCH * STRIDE;
+        const int* idb = ids + (kb & 7) * LBATCH;
 
         // per-warp cull: instances behind every pixel's last contributor, or whose alpha >= 1/255 ellipse cannot
         // reach this warp's 8x4 pixels, are never evaluated
@@ -635,7 +646,20 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_lane_kernel(
                 red_add_f32x4(dL_dvfeatures + (size_t)id * (4 * NV) + 4 * (lane - 8 - S), make_float4(a1, a2, a3, a4));
             }
         }
+        // round epilogue: release buffer st, then request batch kb+2 into the buffer batch kb+2-LSTAGES occupied
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (kb + 2 < nrounds) {
+            const int nst = st + 2 >= LSTAGES ? st + 2 - LSTAGES : st + 2;
+            const unsigned nph = st + 2 >= LSTAGES ? ph ^ 1u : ph;
+            if (kb + 2 >= LSTAGES) mbar_wait(&empty_bar[nst], nph ^ 1u);
+            issue_data(kb + 2, nst);
+            if (kb + 4 < nrounds) issue_ids(kb + 4);
+            cp_async_mbar_arrive_noinc(&full_bar[nst]);
+        }
+        if (++st == LSTAGES) { st = 0; ph ^= 1u; }
     }
+    cp_async_wait_all();
 }
 
 template <int S_T, int NV_T, bool RGSS>

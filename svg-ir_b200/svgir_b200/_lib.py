@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libsvgir_b200.so")
+# SVGIR_B200_LIB: load another build of the same library (kernel A/B tuning runs); default = the in-tree build
+_SO = os.environ.get("SVGIR_B200_LIB") or os.path.join(_HERE, "libsvgir_b200.so")
 _CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 REC_FLOATS = 24
