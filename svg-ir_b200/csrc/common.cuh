@@ -90,7 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   // suspend-time hint: sleep, do not spin
         "@p bra MBAR_DONE;\n"
         "bra MBAR_WAIT;\n"
         "MBAR_DONE:\n"

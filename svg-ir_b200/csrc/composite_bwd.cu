@@ -355,8 +355,9 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     float* hits = smem + LY::HITS_OFF;                     // [NWARP][32][HIT_STRIDE_L]
     int* ids = reinterpret_cast<int*>(smem + LY::IDS_OFF); // [8][LBATCH]
     __shared__ int tile_max_s;
-    __shared__ __align__(8) uint64_t full_bar[LSTAGES];    // batch staged   (256 LDGSTS-completion arrivals)
+    __shared__ __align__(8) uint64_t full_bar[LSTAGES];    // batch staged   (32 LDGSTS-completion arrivals: the issuing warp)
     __shared__ __align__(8) uint64_t empty_bar[LSTAGES];   // batch consumed (one arrival per warp)
+    __shared__ int ticket[8];                              // per-batch election of the issuing warp
 
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
@@ -443,9 +444,10 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     if (tid == 0) {
         tile_max_s = 0;
 #pragma unroll
-        for (int i = 0; i < LSTAGES; i++) { mbar_init(&full_bar[i], TILE_PIX); mbar_init(&empty_bar[i], TILE_PIX / 32); }
+        for (int i = 0; i < LSTAGES; i++) { mbar_init(&full_bar[i], 32); mbar_init(&empty_bar[i], TILE_PIX / 32); }
         mbar_fence_init();
     }
+    if (tid < 8) ticket[tid] = 0;
     if constexpr (NVP != NV) {  // zero the padding channels of the transposed rows once
         constexpr int PADC = NVP - NV;
         for (int q = tid; q < LSTAGES * LBATCH * 4 * PADC; q += TILE_PIX) {
@@ -470,20 +472,28 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     float T = T_final, A = 0.f, last_alpha = 0.f, V_last = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    // ---- asynchronous staging ring (same scheme as the forward compositor, composite_fwd.cu) ----------
-    // batch b = sorted positions top_b-1 ... top_b-nb (back to front), top_b = tile_max - b*LBATCH. Records of batch
-    // k+2 and ids of batch k+4 are requested with LDGSTS at the end of round k; full_bar / empty_bar replace the
-    // CTA-wide barriers, so warps drift up to LSTAGES-1 batches apart instead of idling at a __syncthreads.
-    auto issue_ids = [&](int b) {
+    // ---- asynchronous staging ring ------------------------------------------------------------------------
+    // batch b = sorted positions top_b-1 ... top_b-nb (back to front), top_b = tile_max - b*LBATCH, lives in buffer
+    // b % LSTAGES. There is no CTA-wide barrier in the loop:
+    //   * the FIRST warp to finish round k (elected with a ticket) requests batch k+2 and the surfel ids of batch
+    //     k+4 with LDGSTS (cp.async: no registers, no scoreboard wait; vfeature rows are transposed on the way by
+    //     4-byte copies) -- the fastest warp has the slack, and nobody waits for the slowest warp to issue;
+    //   * full_bar[s] completes when that warp's copies have landed (cp.async.mbarrier.arrive.noinc), and is what a
+    //     warp waits on before it composites a batch;
+    //   * empty_bar[s] counts the 8 warps that finished reading buffer s, and is what the issuing warp waits on
+    //     before it overwrites it.
+    // Warps drift up to LSTAGES-1 batches apart instead of idling at a __syncthreads (the barrier stall was 2.9 of
+    // 9 stall cycles per issue with the CTA-synchronous double buffer).
+    auto issue_ids = [&](int b, int t) {
         const int top = tile_max - b * LBATCH;
         const int nb = min(LBATCH, top);
-        if (tid < nb) cp_async4(ids + (b & 7) * LBATCH + tid, point_list + range.x + top - 1 - tid);
+        if (t < nb) cp_async4(ids + (b & 7) * LBATCH + t, point_list + range.x + top - 1 - t);
     };
-    auto issue_data = [&](int b, int buf) {
+    auto issue_data = [&](int b, int buf) {   // by one warp
         const int nb = min(LBATCH, tile_max - b * LBATCH);
         float* sb = stage + buf * LBATCH * STRIDE;
         const int* idl = ids + (b & 7) * LBATCH;
-        for (int q = tid; q < nb * LCH; q += TILE_PIX) {
+        for (int q = lane; q < nb * LCH; q += 32) {
             const int i = q / LCH, ch = q - i * LCH;
             const int id = idl[i];
             float* dst = sb + i * STRIDE;
@@ -510,12 +520,10 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     const int nrounds = (tile_max + LBATCH - 1) / LBATCH;
 #pragma unroll
     for (int b = 0; b < 4; b++)
-        if (b < nrounds) issue_ids(b);
+        if (b < nrounds) issue_ids(b, tid);
     cp_async_wait_all();
-    __syncthreads();   // ids of batches 0..3 are visible
-#pragma unroll
-    for (int b = 0; b < 2; b++)
-        if (b < nrounds) { issue_data(b, b); cp_async_mbar_arrive_noinc(&full_bar[b]); }
+    __syncthreads();   // ids of batches 0..3, the barriers and the tickets are visible
+    if (wid < 2 && wid < nrounds) { issue_data(wid, wid); cp_async_mbar_arrive_noinc(&full_bar[wid]); }
 
     int st = 0;          // kb % LSTAGES
     unsigned ph = 0;     // (kb / LSTAGES) & 1
@@ -648,13 +656,18 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
         }
         // round epilogue: release buffer st, then request batch kb+2 into the buffer batch kb+2-LSTAGES occupied
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[st]);
-        if (kb + 2 < nrounds) {
+        int tk = 1;
+        if (lane == 0) {
+            mbar_arrive(&empty_bar[st]);
+            if (kb + 2 < nrounds) tk = atomicAdd(&ticket[(kb + 2) & 7], 1);   // 8 tickets per batch: first = multiple of 8
+        }
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if ((tk & 7) == 0) {   // this warp finished round kb first: it stages batch kb+2
             const int nst = st + 2 >= LSTAGES ? st + 2 - LSTAGES : st + 2;
             const unsigned nph = st + 2 >= LSTAGES ? ph ^ 1u : ph;
-            if (kb + 2 >= LSTAGES) mbar_wait(&empty_bar[nst], nph ^ 1u);
+            if (kb + 2 >= LSTAGES) mbar_wait(&empty_bar[nst], nph ^ 1u);   // batch kb+2-LSTAGES consumed by all warps
             issue_data(kb + 2, nst);
-            if (kb + 4 < nrounds) issue_ids(kb + 4);
+            if (kb + 4 < nrounds) issue_ids(kb + 4, lane);
             cp_async_mbar_arrive_noinc(&full_bar[nst]);
         }
         if (++st == LSTAGES) { st = 0; ph ^= 1u; }
