@@ -406,6 +406,28 @@ int svgir_train_loss_forward(const svgir_train_loss_cfg* cfg, const svgir_train_
 int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in,
                               const float* grad_loss, const svgir_train_loss_grads* g, void* stream);
 
+/* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
+ * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps
+ * its flat gradient buffer in a symmetric allocation that is peer-mapped into all ranks of the box; the
+ * backward kernels write their gradients straight into it, and ONE kernel per rank then sums the buffers
+ * in place: a flag barrier over peer memory, rank r reduces slice r of all `world` buffers (NVSwitch
+ * multicast `multimem.ld_reduce` when `multicast` is set, otherwise 128-bit peer loads), writes the sum
+ * back into every rank's buffer (`multimem.st` / peer stores), flag barrier. No staging copy, no NCCL.
+ * `flags[i]` is rank i's flag area: SVGIR_PEER_FLAG_WORDS zero-initialised u32, never touched by the host
+ * afterwards (the put/wait protocol leaves it zeroed, so the launch can be replayed from a CUDA graph).
+ * All ranks must launch with the same numel; numel*4 bytes must be 16-byte aligned per slice (the kernel
+ * rounds slices to 4 floats). The grid is at most one CTA per SM so all CTAs are co-resident. */
+#define SVGIR_MAX_PEERS 8
+#define SVGIR_PEER_BLOCKS 128
+#define SVGIR_PEER_FLAG_WORDS (2 * SVGIR_PEER_BLOCKS * SVGIR_MAX_PEERS)
+typedef struct svgir_peer_comm {
+    int32_t world, rank;
+    float* bufs[SVGIR_MAX_PEERS];            /* bufs[i]: rank i's buffer as mapped in THIS process */
+    unsigned int* flags[SVGIR_MAX_PEERS];    /* flags[i]: rank i's flag area as mapped in this process */
+    float* multicast;                        /* multicast mapping of the buffers (NVLS), or NULL */
+} svgir_peer_comm;
+int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

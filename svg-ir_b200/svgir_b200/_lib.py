@@ -74,6 +74,17 @@ def build(verbose: bool = False) -> str:
     return _SO
 
 
+MAX_PEERS = 8
+PEER_BLOCKS = 128
+PEER_FLAG_WORDS = 2 * PEER_BLOCKS * MAX_PEERS
+
+
+class PeerComm(C.Structure):
+    """svgir_peer_comm (include/svgir_b200.h)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("bufs", c_fp * MAX_PEERS), ("flags", c_fp * MAX_PEERS),
+                ("multicast", c_fp)]
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -100,6 +111,8 @@ def lib() -> C.CDLL:
     L.svgir_timing_collect.restype = C.c_int
     L.svgir_launch_count.argtypes = [C.c_int]
     L.svgir_launch_count.restype = C.c_longlong
+    L.svgir_peer_allreduce.argtypes = [C.POINTER(PeerComm), C.c_longlong, C.c_void_p]
+    L.svgir_peer_allreduce.restype = C.c_int
     _lib = L
     return L
 
@@ -134,5 +147,5 @@ EXPORTED_SYMBOLS = [
     "svgir_timing_collect", "svgir_launch_count", "svgir_bvh_workspace_bytes", "svgir_bvh_leaf_aabbs",
     "svgir_bvh_build", "svgir_bvh_pack_leaves", "svgir_bvh_trace_opacity",
     "svgir_sample_incident_rays", "svgir_render_equation_sh_forward", "svgir_render_equation_sh_backward",
-    "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward",
+    "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce",
 ]

@@ -39,6 +39,18 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, torch.device
     return rank, world, dev
 
 
+def background_group(max_ctas: int = 4):
+    """A second NCCL communicator over all ranks whose kernels use at most `max_ctas` CTAs: collectives issued on it
+    run concurrently with a compute kernel at the cost of ~max_ctas of the 148 SMs (the default communicator's
+    16-32 CTAs slowed the shading backward from 0.48 to 0.80 ms at N=8). Returns None outside NCCL."""
+    if not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return dist.new_group(backend="nccl", pg_options=opts)
+
+
 def world_size() -> int:
     return dist.get_world_size() if dist.is_initialized() else 1
 
@@ -64,6 +76,76 @@ def relight_grid_for_rank(n_views: int, n_envs: int, rank: int, world: int) -> L
     return [(i // n_views, i % n_views) for i in range(rank, n_views * n_envs, world)]
 
 
+class PeerAllReduce:
+    """Flat fp32 gradient storage in a symmetric (peer-mapped) allocation + the one-kernel NVLink all-reduce over it
+    (csrc/peer_allreduce.cu, `svgir_peer_allreduce`). The backward kernels write their gradients straight into this
+    buffer; `all_reduce()` launches ONE kernel on the current stream that sums the buffers of all ranks in place
+    (NVSwitch multicast ld_reduce / st when the allocation has a multicast mapping, 128-bit peer loads and stores
+    otherwise). The launch is capturable: pipeline.GraphedTrainingStep records it at the end of the step's graph.
+
+    torch.distributed._symmetric_memory is used for what PyTorch is here for: allocating device memory and exchanging
+    the peer mappings at start-up. Raises if the box cannot provide peer-mapped memory; callers fall back to NCCL.
+    SVGIR_PEER_MULTICAST=0 forces the peer load/store path."""
+
+    def __init__(self, device: torch.device, group=None):
+        if not dist.is_initialized() or dist.get_world_size() < 2:
+            raise RuntimeError("PeerAllReduce needs an initialised process group with >= 2 ranks")
+        from . import _lib
+        if dist.get_world_size() > _lib.MAX_PEERS:
+            raise RuntimeError("PeerAllReduce supports up to %d ranks of one box" % _lib.MAX_PEERS)
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.storage = None
+        self.flat = None
+        self.comm = None
+        self.numel = 0
+        self.multicast = False
+
+    def allocate(self, numel: int) -> torch.Tensor:
+        """Returns the zeroed flat buffer of `numel` floats (a view into the symmetric allocation)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        n = (int(numel) + 3) // 4 * 4
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.storage = symm_mem.empty(n + _lib.PEER_FLAG_WORDS, dtype=torch.float32, device=self.device)
+        self.storage.zero_()
+        hdl = symm_mem.rendezvous(self.storage, self.group)
+        self.hdl = hdl
+        world, rank = int(hdl.world_size), int(hdl.rank)
+        comm = _lib.PeerComm()
+        comm.world, comm.rank = world, rank
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        for i in range(world):
+            comm.bufs[i] = ptrs[i]
+            comm.flags[i] = ptrs[i] + 4 * n
+        mc = 0
+        if os.environ.get("SVGIR_PEER_MULTICAST", "1") != "0":
+            try:
+                mc = int(hdl.multicast_ptr or 0) if hdl.has_multicast_support else 0
+            except Exception:
+                mc = 0
+        comm.multicast = mc or None
+        self.multicast = bool(mc)
+        self.comm, self.numel = comm, n
+        self.flat = self.storage[:n]
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)   # every rank's flags are zeroed before the first launch
+        torch.cuda.synchronize(self.device)
+        return self.flat[:int(numel)]
+
+    def all_reduce(self, tensor: Optional[torch.Tensor] = None):
+        """In-place sum over ranks of the whole flat buffer (the `tensor` argument, if given, must be a view of it)."""
+        from . import _lib
+        if tensor is not None and (tensor.data_ptr() < self.flat.data_ptr() or
+                                   tensor.data_ptr() + 4 * tensor.numel() > self.flat.data_ptr() + 4 * self.numel):
+            raise ValueError("PeerAllReduce.all_reduce: tensor is not a view of the symmetric buffer")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().svgir_peer_allreduce(self.comm, self.numel, stream), "peer_allreduce")
+
+
 class FlatGradBucket:
     """One contiguous fp32 buffer holding the gradients of every trainable tensor.
 
@@ -81,7 +163,9 @@ class FlatGradBucket:
     captured into a CUDA graph (pipeline.GraphedTrainingStep)."""
 
     def __init__(self, params: Sequence[torch.Tensor], average: bool = False,
-                 segments: Optional[Sequence[Sequence[int]]] = None, extra_floats: int = 0):
+                 segments: Optional[Sequence[Sequence[int]]] = None, extra_floats: int = 0,
+                 segment_groups: Optional[Sequence] = None, alloc: Optional[Callable[[int], torch.Tensor]] = None,
+                 reducer: Optional[Callable[[torch.Tensor], None]] = None):
         params = [p for p in params if p is not None]
         if not params:
             raise ValueError("FlatGradBucket needs at least one parameter")
@@ -97,6 +181,12 @@ class FlatGradBucket:
         if seen != list(range(len(self.params))):
             raise ValueError("segments must name every parameter exactly once")
         self.segments = [list(seg) for seg in segments if len(seg)]
+        # optional process group per segment (None = default group): a segment whose all-reduce runs UNDER a compute
+        # kernel goes over a communicator restricted to a few CTAs (`background_group`), so the collective does not
+        # take SMs away from that kernel; the last, exposed segment uses the full-width default communicator
+        self.segment_groups = list(segment_groups) if segment_groups is not None else [None] * len(self.segments)
+        if len(self.segment_groups) != len(self.segments):
+            raise ValueError("segment_groups must have one entry per segment")
         self.offsets = [0] * len(self.params)
         self.seg_bounds = []
         n = 0
@@ -113,7 +203,15 @@ class FlatGradBucket:
             n += (int(extra_floats) + 3) // 4 * 4
             self.seg_bounds[-1] = (self.seg_bounds[-1][0], n)
         self.numel = n
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        # `alloc(n)` supplies the flat storage (PeerAllReduce.allocate: peer-mapped memory) and `reducer(flat)` the
+        # in-place sum over ranks (PeerAllReduce.all_reduce: one kernel on the current stream, no NCCL); with a
+        # reducer the bucket must be a single segment, reduced after the backward pass
+        self.reducer = reducer
+        if reducer is not None and len(self.segments) != 1:
+            raise ValueError("a custom reducer works on the whole bucket: use one segment")
+        self.flat = alloc(n) if alloc is not None else torch.zeros(n, dtype=torch.float32, device=dev)
+        if self.flat.numel() != n or self.flat.dtype != torch.float32 or self.flat.device != dev:
+            raise ValueError("alloc must return %d fp32 elements on %s" % (n, dev))
         self.extra = self.flat[self.extra_offset:self.extra_offset + int(extra_floats)] if extra_floats else None
         self.attach()
         self._work = None
@@ -164,6 +262,9 @@ class FlatGradBucket:
             return None
         if self.average:
             self.flat.div_(world_size())
+        if self.reducer is not None:
+            self.reducer(self.flat)   # stream-ordered kernel: nothing to wait for
+            return None
         self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return self._work
 
@@ -183,7 +284,10 @@ class FlatGradBucket:
         seg = self.segment(k)
         if self.average:
             seg.div_(world_size())
-        self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
+        if self.reducer is not None:
+            self.reducer(self.flat)
+            return
+        self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.segment_groups[k], async_op=True))
 
     def _on_grad(self, i: int):
         if not self._armed:
@@ -196,7 +300,7 @@ class FlatGradBucket:
     def begin_overlap(self):
         """Arms the hooks for ONE backward pass in which every parameter receives at most one
         accumulated gradient (one view per step). Gradients must accumulate into the attached views."""
-        if not self._hooks:
+        if not self._hooks and self.reducer is None:   # a custom reducer runs once, from finish_overlap()
             for i, p in enumerate(self.params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i)))
         if not self.attached():

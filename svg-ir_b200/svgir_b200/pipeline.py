@@ -67,6 +67,28 @@ class ViewCamera:
     camera_center: torch.Tensor         # [3]
     patch_bbox: torch.Tensor            # [4]
     prcppoint: torch.Tensor             # [2]
+    # optional: ONE flat 48-float tensor the five tensors above are views of (`blocked_camera`), so a view's
+    # per-step constants move with a single copy instead of five
+    block: Optional[torch.Tensor] = None
+
+
+_CAM_SLICES = ((0, 16, (4, 4)), (16, 32, (4, 4)), (32, 35, (3,)), (36, 40, (4,)), (40, 42, (2,)))
+
+
+def blocked_camera(image_height, image_width, tanfovx, tanfovy, world_view_transform, full_proj_transform, camera_center,
+                   patch_bbox, prcppoint, device=None, pin=False) -> ViewCamera:
+    """ViewCamera whose tensors are 16-byte-aligned views into one contiguous fp32 block."""
+    src = (world_view_transform, full_proj_transform, camera_center, patch_bbox, prcppoint)
+    dev = device if device is not None else src[0].device
+    block = torch.zeros(48, dtype=torch.float32, device=dev)
+    if pin:
+        block = block.pin_memory()
+    views = []
+    for (lo, hi, shape), t in zip(_CAM_SLICES, src):
+        v = block[lo:hi].view(shape)
+        v.copy_(t.to(torch.float32))
+        views.append(v)
+    return ViewCamera(image_height, image_width, tanfovx, tanfovy, *views, block=block)
 
 
 def rgb_to_srgb(img):
@@ -75,9 +97,9 @@ def rgb_to_srgb(img):
 
 
 def camera_from_scene(cam, device) -> ViewCamera:
-    d = lambda a: torch.from_numpy(a).to(device)
-    return ViewCamera(cam.H, cam.W, cam.tanfovx, cam.tanfovy, d(cam.viewmatrix), d(cam.projmatrix), d(cam.campos),
-                      d(cam.patch_bbox), d(cam.prcppoint))
+    d = lambda a: torch.from_numpy(a)
+    return blocked_camera(cam.H, cam.W, cam.tanfovx, cam.tanfovy, d(cam.viewmatrix), d(cam.projmatrix), d(cam.campos),
+                          d(cam.patch_bbox), d(cam.prcppoint), device=device)
 
 
 def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
@@ -271,9 +293,9 @@ class GraphedTrainingStep:
         self.flag_host = torch.zeros((1,), dtype=torch.float32).pin_memory() if self.reduce_in_graph else None
         dev = pc.xyz.device
         self.dev = dev
-        self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
-                              cam.world_view_transform.clone(), cam.full_proj_transform.clone(),
-                              cam.camera_center.clone(), cam.patch_bbox.clone(), cam.prcppoint.clone())
+        self.cam = blocked_camera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                                  cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                  cam.patch_bbox, cam.prcppoint, device=dev)
         self.gt = gt_image.clone()
         self.graph = None
         self.loss = None
@@ -327,9 +349,14 @@ class GraphedTrainingStep:
         if (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy) != (c.image_height, c.image_width, c.tanfovx, c.tanfovy):
             self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
                                   c.world_view_transform, c.full_proj_transform, c.camera_center, c.patch_bbox,
-                                  c.prcppoint)
+                                  c.prcppoint, block=c.block)
             c = self.cam
             self.graph = None
+        if cam.block is not None and c.block is not None:
+            c.block.copy_(cam.block, non_blocking=True)   # one copy for all per-view constants
+            if gt_image is not self.gt:
+                self.gt.copy_(gt_image, non_blocking=True)
+            return
         c.world_view_transform.copy_(cam.world_view_transform, non_blocking=True)
         c.full_proj_transform.copy_(cam.full_proj_transform, non_blocking=True)
         c.camera_center.copy_(cam.camera_center, non_blocking=True)

@@ -98,13 +98,126 @@ def test_two_rank_graphed_step_overlapped_allreduce():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        if p.is_alive():
-            p.kill()
+    try:
+        res = sorted(q.get(timeout=300) for _ in range(world))
+    finally:   # never leave a rank spinning on the GPU
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
     for rank, worst, recaptures, err in res:
         assert err is None, err
         assert worst < 1e-3, (rank, worst)
         # one capture after the forced graph drop, one more on rank 1's overflow -- on BOTH ranks
         assert recaptures == 2, (rank, recaptures)
+
+
+def _peer_worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                          LOCAL_RANK=str(rank))
+        import torch.distributed as dist
+        from svgir_b200 import dist as D, pipeline, scene
+        r, w, dev = D.init_from_env()
+        out = {}
+        for mc in ("1", "0"):   # NVSwitch multicast path (when the box has it), then the peer load/store path
+            os.environ["SVGIR_PEER_MULTICAST"] = mc
+            peer = D.PeerAllReduce(dev)
+            n = 1_000_003 * 4
+            flat = peer.allocate(n)
+            g = torch.Generator(device=dev).manual_seed(100 + rank)
+            worst = 0.0
+            for it in range(3):
+                x = torch.randn(n, device=dev, generator=g)
+                flat.copy_(x)
+                ref = x.clone()
+                dist.all_reduce(ref)            # NCCL as the checker
+                peer.all_reduce()
+                worst = max(worst, float((flat - ref).abs().max() / ref.abs().max()))
+            # the same launch replayed from a CUDA graph (the flags return to zero after every launch)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                peer.all_reduce()               # warm-up on the side stream
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            flat.fill_(float(rank + 1))
+            with torch.cuda.graph(graph):
+                peer.all_reduce()
+            for it in range(3):
+                flat.fill_(float(rank + 1 + it))
+                torch.cuda.synchronize()
+                dist.barrier()
+                graph.replay()
+                torch.cuda.synchronize()
+                want = sum(float(k + 1 + it) for k in range(world))
+                worst = max(worst, float((flat - want).abs().max()))
+            out[mc] = (worst, peer.multicast)
+            del graph
+            torch.cuda.synchronize()
+            dist.barrier()
+
+        # the graphed data-parallel step with the peer all-reduce recorded at the end of the graph
+        os.environ["SVGIR_PEER_MULTICAST"] = "1"
+        P, W, H, Ns = 6000, 160, 128, 16
+        cloud = scene.make_surfels(P, seed=11)
+        mats = scene.make_materials(cloud, Ns, seed=12, env_hw=(16, 32))
+        cams = [pipeline.camera_from_scene(scene.look_at_camera(W, H, v, 4), dev) for v in range(4)]
+        gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(2)]
+        bg = torch.zeros(3, device=dev)
+
+        def model():
+            pc = pipeline.model_from_scene(cloud, mats, dev)
+            env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+            return pc, env
+
+        pc_e, env_e = model()
+        pc_g, env_g = model()
+        params = pc_g.trainable() + [env_g]
+        peer = D.PeerAllReduce(dev)
+        bucket = D.FlatGradBucket(params, extra_floats=1, alloc=peer.allocate, reducer=peer.all_reduce)
+        runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0], bucket=bucket, reduce_in_graph=True)
+        step_worst = 0.0
+        for step in range(3):
+            views = [(2 * step + k) % 4 for k in range(world)]
+            for t in pc_e.trainable() + [env_e]:
+                t.grad = None
+            for v in views:
+                pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v % 2], zero_grad=False)
+            runner(cams[views[rank]], gts[views[rank] % 2])
+            torch.cuda.synchronize()
+            for a, b in zip(params, pc_e.trainable() + [env_e]):
+                step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+        q.put((rank, out, step_worst, None))
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
+    except Exception:
+        import traceback
+        q.put((rank, None, 1e9, traceback.format_exc()))
+
+
+def test_two_rank_peer_memory_allreduce():
+    """svgir_peer_allreduce (one kernel over NVLink peer memory) against NCCL on random data, replayed from a CUDA
+    graph, and as the gradient exchange recorded at the end of the graphed data-parallel step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = sorted(q.get(timeout=300) for _ in range(world))
+    finally:   # never leave a rank spinning on the GPU
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, out, step_worst, err in res:
+        assert err is None, err
+        for mc, (worst, used_mc) in out.items():
+            assert worst < 1e-6, (rank, mc, worst, used_mc)
+        assert step_worst < 1e-3, (rank, step_worst)
