@@ -81,7 +81,7 @@ class PeerAllReduce:
     (csrc/peer_allreduce.cu, `svgir_peer_allreduce`). The backward kernels write their gradients straight into this
     buffer; `all_reduce()` launches ONE kernel on the current stream that sums the buffers of all ranks in place
     (NVSwitch multicast ld_reduce / st when the allocation has a multicast mapping, 128-bit peer loads and stores
-    otherwise). The launch is capturable: pipeline.GraphedTrainingStep records it at the end of the step's graph.
+    otherwise; multicast is chosen from 4 ranks up). The launch is capturable: pipeline.GraphedTrainingStep records it at the end of the step's graph.
 
     torch.distributed._symmetric_memory is used for what PyTorch is here for: allocating device memory and exchanging
     the peer mappings at start-up. Raises if the box cannot provide peer-mapped memory; callers fall back to NCCL.
@@ -106,10 +106,6 @@ class PeerAllReduce:
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         n = (int(numel) + 3) // 4 * 4
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
         self.storage = symm_mem.empty(n + _lib.PEER_FLAG_WORDS, dtype=torch.float32, device=self.device)
         self.storage.zero_()
         hdl = symm_mem.rendezvous(self.storage, self.group)
@@ -121,8 +117,11 @@ class PeerAllReduce:
         for i in range(world):
             comm.bufs[i] = ptrs[i]
             comm.flags[i] = ptrs[i] + 4 * n
+        # multicast moves (1 + 1/N) x the buffer per NVLink direction, peer loads/stores 2 (N-1)/N x: multicast from 4 ranks
+        # up (measured: N=2 0.32 vs 0.19 ms, N=8 0.26 vs 0.32 ms). SVGIR_PEER_MULTICAST=1 / 0 forces the choice.
         mc = 0
-        if os.environ.get("SVGIR_PEER_MULTICAST", "1") != "0":
+        want = os.environ.get("SVGIR_PEER_MULTICAST", "auto")
+        if want == "1" or (want != "0" and world >= 4):
             try:
                 mc = int(hdl.multicast_ptr or 0) if hdl.has_multicast_support else 0
             except Exception:
@@ -258,13 +257,15 @@ class FlatGradBucket:
         """Sum (or mean) over ranks. With async_op the NCCL kernel runs on its own stream and overlaps
         whatever the caller enqueues next; call wait() before reading the gradients."""
         self._gather_if_detached()
+        if self.reducer is not None:
+            if self.average:
+                self.flat.div_(world_size())
+            self.reducer(self.flat)   # stream-ordered kernel: nothing to wait for
+            return None
         if world_size() == 1:
             return None
         if self.average:
             self.flat.div_(world_size())
-        if self.reducer is not None:
-            self.reducer(self.flat)   # stream-ordered kernel: nothing to wait for
-            return None
         self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return self._work
 
@@ -279,14 +280,16 @@ class FlatGradBucket:
             return
         self._issued[k] = True
         self.overlap_log.append(k)
+        if self.reducer is not None:   # whole-buffer reducer (it knows its own world)
+            if self.average:
+                self.flat.div_(world_size())
+            self.reducer(self.flat)
+            return
         if world_size() == 1:
             return
         seg = self.segment(k)
         if self.average:
             seg.div_(world_size())
-        if self.reducer is not None:
-            self.reducer(self.flat)
-            return
         self._pending.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.segment_groups[k], async_op=True))
 
     def _on_grad(self, i: int):

@@ -79,6 +79,42 @@ def test_segmented_bucket_issues_segments_in_backward_order():
         D.FlatGradBucket([a, b, c], segments=[[0], [0, 2]])
 
 
+def test_bucket_with_external_storage_and_custom_reducer():
+    """The hooks PeerAllReduce plugs into (alloc = peer-mapped storage, reducer = the one-kernel all-reduce):
+    gradients accumulate straight into the supplied storage, the reducer runs exactly once per step, after the
+    backward pass, on the whole buffer; segmented buckets cannot take a whole-buffer reducer."""
+    a = torch.randn(5, 3, requires_grad=True)
+    b = torch.randn(7, requires_grad=True)
+    arena = torch.full((64,), 7.0)
+    calls = []
+
+    def alloc(n):
+        v = arena[:n]
+        v.zero_()
+        return v
+
+    def reducer(flat):
+        calls.append(flat.data_ptr())
+        flat.mul_(2.0)   # stands in for "sum over 2 identical ranks"
+
+    bk = D.FlatGradBucket([a, b], extra_floats=1, alloc=alloc, reducer=reducer)
+    assert bk.flat.data_ptr() == arena.data_ptr() and bk.attached() and bk.extra is not None
+    bk.begin_overlap()               # reducer mode arms no hooks: nothing may fire inside backward
+    (a.sum() + (b * b).sum()).backward()
+    assert calls == []
+    bk.finish_overlap()
+    assert calls == [arena.data_ptr()]
+    assert torch.allclose(bk.view(0), torch.full((5, 3), 2.0)) and torch.allclose(bk.view(1), 4 * b.detach())
+    bk.zero()
+    (a.sum()).backward()
+    bk.all_reduce()                  # the post-step entry point goes through the same reducer
+    assert len(calls) == 2 and torch.allclose(bk.view(0), torch.full((5, 3), 2.0))
+    with pytest.raises(ValueError):
+        D.FlatGradBucket([a, b], segments=[[0], [1]], reducer=reducer)
+    with pytest.raises(ValueError):
+        D.FlatGradBucket([a, b], alloc=lambda n: torch.zeros(n + 4))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
