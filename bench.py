@@ -404,10 +404,21 @@ def run_relight(args):
     bg = torch.zeros(3, device=dev)
     grid = svdist.relight_grid_for_rank(N_VIEWS, n_env, rank, world)
 
-    def frame(i):
+    # The frame is captured once into a CUDA graph (pipeline.GraphedRelightFrame) and replayed per (view, env map):
+    # camera block + env map copied into static buffers, binning capacity checked after every replay.
+    # --eager issues the ~70 launches of a frame one by one instead (and blocks on num_rendered mid-frame).
+    runner = None if args.eager else pipeline.GraphedRelightFrame(pc, envs[0], bg, cams[0])
+
+    def eager_frame(i):
         e, v = grid[i % len(grid)]  # (env, view), env-major
         with torch.no_grad():
             return pipeline.render_view(cams[v], pc, (envs[e], shading.MODE_FIXED), bg, is_training=False)
+
+    def frame(i):
+        if runner is None:
+            return eager_frame(i)
+        e, v = grid[i % len(grid)]
+        return runner(cams[v], envs[e])
 
     for i in range(args.warmup):
         res = frame(i)
@@ -416,7 +427,8 @@ def run_relight(args):
         dist.barrier()
     _lib.launch_count(reset=True)
     _lib.timing_collect(reset=True)
-    _lib.timing_enable(True)
+    if runner is None:
+        _lib.timing_enable(True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -430,16 +442,63 @@ def run_relight(args):
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
+    launches = _lib.launch_count() if runner is None else runner.launches_per_frame * args.steps
+    if runner is not None:   # per-kernel times: the same frames launched eagerly, each launch bracketed by events
+        _lib.timing_enable(True)
+        for i in range(min(args.steps, 5)):
+            eager_frame(args.warmup + i)
+        torch.cuda.synchronize()
     _lib.timing_enable(False)
-    launches = _lib.launch_count()
     kt = {}
     for k in ("shade_fwd", "composite_fwd", "preprocess", "emit", "sort_small", "tile_scan"):
         t, n = _lib.timing_collect(k)
         kt[k] = t / max(n, 1)
+    _lib.timing_collect(reset=True)
     t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_frame = float(t_ms.item()) / args.steps
+
+    # end to end: camera block + env map from pinned host memory every frame, the relit image read back to pinned
+    # host memory (what eval_relighting_tensoIR.py:331-340 saves)
+    e2e_ms = None
+    if not args.no_e2e:
+        cam_np = [scene.look_at_camera(WIDTH, HEIGHT, v, N_VIEWS) for v in range(N_VIEWS)]
+        cam_host = [pipeline.blocked_camera(HEIGHT, WIDTH, c.tanfovx, c.tanfovy, *[torch.from_numpy(getattr(c, k))
+                    for k in ("viewmatrix", "projmatrix", "campos", "patch_bbox", "prcppoint")], pin=True) for c in cam_np]
+        env_host = [e.cpu().pin_memory() for e in envs]
+        img_host = torch.empty((3, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+
+        def e2e_frame(i):
+            e, v = grid[i % len(grid)]
+            if runner is not None:
+                r = runner(cam_host[v], env_host[e])
+            else:
+                c = cam_host[v]
+                cam = pipeline.blocked_camera(HEIGHT, WIDTH, c.tanfovx, c.tanfovy, c.world_view_transform, c.full_proj_transform,
+                                              c.camera_center, c.patch_bbox, c.prcppoint, device=dev)
+                with torch.no_grad():
+                    r = pipeline.render_view(cam, pc, (env_host[e].to(dev, non_blocking=True), shading.MODE_FIXED), bg,
+                                             is_training=False)
+            img_host.copy_(r["pbr"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(2):
+            e2e_frame(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for i in range(args.steps):
+            e2e_frame(2 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / args.steps
+        e2e_h2d = cam_host[0].block.numel() * 4 + env_host[0].numel() * 4
+        e2e_d2h = img_host.numel() * 4
     if rank == 0:
         pk, pk_src = peaks()
         # shading runs on the surfels that survive the rasteriser's culling unless --shade-all
@@ -456,6 +515,10 @@ def run_relight(args):
                        "l2": "working set > L2 (light buffers 3.7 GB/frame)", "R": int(res["num_rendered"]),
                        "surfels_shaded": n_sh},
             "clocks": clk, "gpu_launches": int(launches),
+            "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/frame)" % runner.launches_per_frame,
+            "e2e": None if e2e_ms is None else {"value": round(e2e_ms / world, 4), "unit": "ms/frame", "h2d_bytes_per_step": int(e2e_h2d),
+                                                "d2h_bytes_per_step": int(e2e_d2h),
+                                                "inputs": "camera block + env map from pinned host memory; relit image read back"},
             "roofline": {"bound": "hbm", "kernel": "shade_fwd", "achieved": round(ach, 1), "peak": pk["hbm_gbs"],
                          "peak_source": pk_src, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
                          "algorithmic_bytes": int(alg), "avg_ms": round(kt["shade_fwd"], 4)},

@@ -399,6 +399,96 @@ class GraphedTrainingStep:
         raise RuntimeError("GraphedTrainingStep: binning capacity did not converge")
 
 
+class GraphedRelightFrame:
+    """One relighting frame (eval_relighting_tensoIR.py:303-331: `render_view(..., is_training=False)` under a fixed
+    HDR env map) captured ONCE into a CUDA graph and replayed per (view, env map): the eager frame issues ~70 launches
+    and blocks on `num_rendered`, which costs as much host time as the kernels take. Same capacity protocol as
+    GraphedTrainingStep: fixed binning capacity, (num_rendered, overflow) lands in pinned memory, `finish()` checks it
+    after the replay and re-captures + re-runs on overflow. Per-frame inputs (camera block, env map) are copied into
+    static device buffers; the result dict holds static tensors overwritten by the next frame."""
+
+    def __init__(self, pc: SurfelModel, env_map: torch.Tensor, bg: torch.Tensor, cam: ViewCamera, warmup: int = 2,
+                 env_mode=None):
+        self.pc, self.bg = pc, bg
+        dev = pc.xyz.device
+        self.dev = dev
+        self.env_mode = shading.MODE_FIXED if env_mode is None else env_mode
+        self.env = env_map.detach().clone()
+        self.cam = blocked_camera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
+                                  cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                  cam.patch_bbox, cam.prcppoint, device=dev)
+        self.graph = None
+        self.res = None
+        self.captures = 0
+        self.launches_per_frame = 0
+        self.warmup = warmup
+
+    def _frame(self):
+        with torch.no_grad():
+            return render_view(self.cam, self.pc, (self.env, self.env_mode), self.bg, is_training=False)
+
+    def _capture(self):
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                with raster.count_mode("speculative"):
+                    r = self._frame()
+            R = int(r["num_rendered"])
+            raster.reserve(self.dev, self.pc.xyz.shape[0], self.cam.image_width, self.cam.image_height,
+                           int(R * raster.ASYNC_SLACK) + raster.ASYNC_MARGIN)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        raster.prepare_capture(1)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(self.graph):
+            with raster.count_mode("async", owner_resolves=True):
+                self.res = self._frame()
+        self.launches_per_frame = launch_count() - n0
+        self.captures += 1
+
+    def load_inputs(self, cam: ViewCamera, env_map: Optional[torch.Tensor]):
+        c = self.cam
+        if (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy) != (c.image_height, c.image_width, c.tanfovx, c.tanfovy):
+            self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, c.world_view_transform,
+                                  c.full_proj_transform, c.camera_center, c.patch_bbox, c.prcppoint, block=c.block)
+            c = self.cam
+            self.graph = None
+        if cam.block is not None:
+            c.block.copy_(cam.block, non_blocking=True)
+        else:
+            for k in ("world_view_transform", "full_proj_transform", "camera_center", "patch_bbox", "prcppoint"):
+                getattr(c, k).copy_(getattr(cam, k), non_blocking=True)
+        if env_map is not None and env_map is not self.env:
+            self.env.copy_(env_map, non_blocking=True)
+
+    def __call__(self, cam: ViewCamera, env_map: Optional[torch.Tensor] = None, check: bool = True) -> dict:
+        self.load_inputs(cam, env_map)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        if check:
+            self.finish()
+        return self.res
+
+    def finish(self) -> int:
+        st = self.res["raster_state"]
+        for _ in range(4):
+            torch.cuda.current_stream(self.dev).synchronize()
+            st.pending = True  # the graph re-wrote count_host
+            try:
+                return st.resolve()
+            except raster.CapacityOverflow:
+                pass
+            self.graph = None
+            self._capture()
+            self.graph.replay()
+            st = self.res["raster_state"]
+        raise RuntimeError("GraphedRelightFrame: binning capacity did not converge")
+
+
 def smoke_step(P=3000, W=96, H=64, Ns=16) -> dict:
     from . import scene
     dev = torch.device("cuda:0")

@@ -112,3 +112,26 @@ def test_async_count_mode_lazy_and_overflow_error():
     finally:
         raster._CAP_HINT.clear()
         raster._CAP_HINT.update(old)
+
+
+def test_graphed_relight_frame_matches_eager():
+    """pipeline.GraphedRelightFrame (forward-only eval frame, fixed HDR env map, S=7 / VS=64) replayed over changing
+    views and env maps gives the eager render_view images bit for bit; one capture serves the whole sweep."""
+    from svgir_b200 import shading
+    pipeline, cloud, mats, cams, gts, dev = _setup(Ns=24)
+    bg = torch.zeros(3, device=dev)
+    pc = pipeline.model_from_scene(cloud, mats, dev, requires_grad=False)
+    rng = np.random.default_rng(5)
+    envs = [torch.from_numpy(rng.uniform(0, 4, (16, 32, 3)).astype(np.float32)).to(dev) for _ in range(2)]
+    runner = pipeline.GraphedRelightFrame(pc, envs[0], bg, cams[0])
+    for v, e in ((0, 0), (1, 0), (2, 1), (3, 1), (1, 0)):
+        with torch.no_grad():
+            want = pipeline.render_view(cams[v], pc, (envs[e], shading.MODE_FIXED), bg, is_training=False)
+        want = {k: want[k].clone() for k in ("render", "pbr", "normal", "depth", "opacity", "base_color", "roughness",
+                                               "lights", "direct", "indirect", "visibility")}
+        R = int(pipeline.render_view(cams[v], pc, (envs[e], shading.MODE_FIXED), bg, is_training=False)["num_rendered"])
+        got = runner(cams[v], envs[e])
+        assert int(got["num_rendered"]) == R
+        for k, w in want.items():
+            assert torch.equal(got[k], w), k
+    assert runner.captures == 1 and runner.launches_per_frame >= 6
