@@ -406,6 +406,28 @@ int svgir_train_loss_forward(const svgir_train_loss_cfg* cfg, const svgir_train_
 int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in,
                               const float* grad_loss, const svgir_train_loss_grads* g, void* stream);
 
+/* ---- G-buffer resolve of an evaluation / relighting frame -----------------------------------------
+ * The torch tail of render_view's eval branch (gaussian_renderer/svgss.py:187-262 with is_training=False:
+ * divide by opacity.clamp_min(1e-5), split, rgb_to_srgb (utils/graphics_utils.py:198-213), opacity filter
+ * r*o + (1-o)*bg) as ONE kernel instead of ~45 elementwise launches. Inputs are the rasteriser's raw
+ * outputs for the eval G-buffer: feature [7,H,W] = light 3 | local light 3 | visibility 1; vfeature [16,H,W] =
+ * pbr 3 | base colour 3 | shading normal 3 | roughness 1 | direct 3 | indirect 3 (svgss.py:150-166).
+ * Every output is [3,H,W] (roughness / visibility are broadcast against the 3-channel background exactly as
+ * the reference's opacity_filter does); NULL outputs are skipped. */
+typedef struct svgir_resolve_eval_out {
+    float* pbr;          /* srgb(pbr*o + (1-o)*bg) */
+    float* normal;       /* shading normal / o (no filter) */
+    float* base_color;   /* filter(srgb(base)) */
+    float* roughness;    /* filter(rough), 3 channels */
+    float* lights;       /* filter(srgb(light)) */
+    float* local_lights; /* filter(srgb(local)) */
+    float* visibility;   /* filter(vis), 3 channels */
+    float* direct;       /* srgb(direct) */
+    float* indirect;     /* srgb(indirect) */
+} svgir_resolve_eval_out;
+int svgir_resolve_eval(int W, int H, const float* bg, const float* opacity, const float* feature,
+                       const float* vfeature, const svgir_resolve_eval_out* out, void* stream);
+
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
  * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps
  * its flat gradient buffer in a symmetric allocation that is peer-mapped into all ranks of the box; the

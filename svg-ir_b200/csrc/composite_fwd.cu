@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(TILE_PIX, S_T >= 0 && S_T <= 8 ? 4 : 1) compos
 
     for (int i = tid; i < 2 * 8 * FWD_BATCH; i += TILE_PIX) wsum[i] = 0.f;
     if (PACKED && NVP_T != NV_T) {  // zero the padding channels of the transposed rows once
-        for (int q = tid; q < 2 * FWD_BATCH * 4 * (NVP_T - NV_T); q += TILE_PIX) {
-            const int i = q / (4 * (NVP_T - NV_T)), r = q - i * 4 * (NVP_T - NV_T);
-            stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / (NVP_T - NV_T)) * NVP_T + NV_T + r % (NVP_T - NV_T)] = 0.f;
+        constexpr int PADC = NVP_T > NV_T ? NVP_T - NV_T : 1;
+        for (int q = tid; q < 2 * FWD_BATCH * 4 * PADC; q += TILE_PIX) {
+            const int i = q / (4 * PADC), r = q - i * 4 * PADC;
+            stage[i * STRIDE + SVGIR_REC_FLOATS + SP + (r / PADC) * NVP_T + NV_T + r % PADC] = 0.f;
         }
     }
 

@@ -200,3 +200,55 @@ extern "C" int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const 
     { TimedScope ts_("train_loss_bwd", s); train_loss_bwd_kernel<<<nb, LOSS_THREADS, 0, s>>>(*cfg, *in, grad_loss, *g); }
     return check_launch("train_loss_bwd", false, s);
 }
+
+// ---- evaluation / relighting frame resolve (svgss.py:187-262, eval branch) ---------------------------------
+namespace svgir {
+
+__device__ __forceinline__ float srgb_clamped(float x) { return fminf(fmaxf(srgb_unclamped(x), 0.f), 1.f); }
+
+// HBM-bound: 24 floats in, up to 27 floats out per pixel, every image touched exactly once.
+__global__ void __launch_bounds__(256) resolve_eval_kernel(int HWi, const float* __restrict__ bgp, const float* __restrict__ opacity,
+                                                           const float* __restrict__ feature, const float* __restrict__ vfeature,
+                                                           const svgir_resolve_eval_out o) {
+    const size_t HW = (size_t)HWi;
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= HW) return;
+    const float bg[3] = {bgp[0], bgp[1], bgp[2]};
+    const float op = opacity[p];
+    const float inv = 1.0f / fmaxf(op, 1e-5f);
+    const float om = 1.0f - op;
+    float f[7], v[16];
+#pragma unroll
+    for (int i = 0; i < 7; i++) f[i] = feature[i * HW + p] * inv;
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = vfeature[i * HW + p] * inv;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float fill = om * bg[k];
+        if (o.pbr) o.pbr[k * HW + p] = srgb_clamped(v[k] * op + fill);
+        if (o.normal) o.normal[k * HW + p] = v[6 + k];
+        if (o.base_color) o.base_color[k * HW + p] = srgb_clamped(v[3 + k]) * op + fill;
+        if (o.roughness) o.roughness[k * HW + p] = v[9] * op + fill;
+        if (o.lights) o.lights[k * HW + p] = srgb_clamped(f[k]) * op + fill;
+        if (o.local_lights) o.local_lights[k * HW + p] = srgb_clamped(f[3 + k]) * op + fill;
+        if (o.visibility) o.visibility[k * HW + p] = f[6] * op + fill;
+        if (o.direct) o.direct[k * HW + p] = srgb_clamped(v[10 + k]);
+        if (o.indirect) o.indirect[k * HW + p] = srgb_clamped(v[13 + k]);
+    }
+}
+
+}  // namespace svgir
+
+extern "C" int svgir_resolve_eval(int W, int H, const float* bg, const float* opacity, const float* feature,
+                                  const float* vfeature, const svgir_resolve_eval_out* out, void* stream) {
+    using namespace svgir;
+    if (W <= 0 || H <= 0 || !bg || !opacity || !feature || !vfeature || !out) {
+        set_error("resolve_eval: bad size or null pointer");
+        return SVGIR_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long HW = (long long)W * H;
+    { TimedScope ts_("resolve_eval", s);
+      resolve_eval_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s>>>((int)HW, bg, opacity, feature, vfeature, *out); }
+    return check_launch("resolve_eval", false, s);
+}

@@ -147,5 +147,5 @@ EXPORTED_SYMBOLS = [
     "svgir_timing_collect", "svgir_launch_count", "svgir_bvh_workspace_bytes", "svgir_bvh_leaf_aabbs",
     "svgir_bvh_build", "svgir_bvh_pack_leaves", "svgir_bvh_trace_opacity",
     "svgir_sample_incident_rays", "svgir_render_equation_sh_forward", "svgir_render_equation_sh_backward",
-    "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce",
+    "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce", "svgir_resolve_eval",
 ]

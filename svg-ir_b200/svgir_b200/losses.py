@@ -113,3 +113,31 @@ def fused_train_loss(color, geo_normal, opacity, vfeature, gt_image, bg, lambda_
     (`rendered_image, rendered_normal, rendered_opacity, rendered_vfeature` of svgss.py:171-184)."""
     return _FusedTrainLoss.apply(color, geo_normal, opacity, vfeature, gt_image, bg, lambda_pbr, lambda_normal,
                                  pbr_ch, normal_ch)
+
+
+class ResolveEvalOut(C.Structure):
+    """svgir_resolve_eval_out (include/svgir_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("pbr", "normal", "base_color", "roughness", "lights", "local_lights",
+                                           "visibility", "direct", "indirect")]
+
+
+def resolve_eval(opacity: torch.Tensor, feature: torch.Tensor, vfeature: torch.Tensor, bg: torch.Tensor) -> dict:
+    """The torch tail of render_view's eval branch (gaussian_renderer/svgss.py:187-262, is_training=False) as ONE
+    kernel: raw (opacity-premultiplied) feature [7,H,W] / vfeature [16,H,W] -> the nine [3,H,W] result images.
+    Forward only (the eval drivers run under torch.no_grad())."""
+    L = _lib.lib()
+    if feature.shape[0] != 7 or vfeature.shape[0] != 16:
+        raise ValueError("resolve_eval expects the eval G-buffer: feature [7,H,W], vfeature [16,H,W]")
+    H, W = int(opacity.shape[-2]), int(opacity.shape[-1])
+    f32 = dict(dtype=torch.float32, device=opacity.device)
+    names = [n for n, _ in ResolveEvalOut._fields_]
+    store = torch.empty((len(names), 3, H, W), **f32)   # one allocation for the nine images
+    out = ResolveEvalOut(*[store[i].data_ptr() for i in range(len(names))])
+    opacity, feature, vfeature = opacity.contiguous(), feature.contiguous(), vfeature.contiguous()
+    bg = bg.to(**f32).contiguous()
+    L.svgir_resolve_eval.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(ResolveEvalOut), C.c_void_p]
+    L.svgir_resolve_eval.restype = C.c_int
+    _lib.check(L.svgir_resolve_eval(W, H, bg.data_ptr(), opacity.data_ptr(), feature.data_ptr(), vfeature.data_ptr(),
+                                    C.byref(out), torch.cuda.current_stream(opacity.device).cuda_stream), "resolve_eval")
+    return {n: store[i] for i, n in enumerate(names)}

@@ -113,6 +113,11 @@ def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
     return m
 
 
+# render_view, eval branch: True = the G-buffer resolve tail runs as one CUDA kernel (losses.resolve_eval) when no
+# gradient is being recorded; False = the torch mirror of gaussian_renderer/svgss.py:187-262.
+FUSED_RESOLVE = True
+
+
 def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier, is_training,
                          debug, shade_culled):
     """svgss.py:15-184: shading, feature packing and the rasteriser call; returns the rasteriser's raw 9-tuple
@@ -166,6 +171,17 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
                                                               is_training, debug, shade_culled)
     (num_rendered, rendered_image, rendered_normal, rendered_opacity, rendered_depth, rendered_feature,
      rendered_vfeature, weights, radii) = raw
+
+    if (not is_training and FUSED_RESOLVE and rendered_feature.is_cuda and rendered_feature.shape[0] == 7 and
+            rendered_vfeature.shape[0] == 16 and not (torch.is_grad_enabled() and rendered_vfeature.requires_grad)):
+        # eval / relighting frame: the whole torch tail below as one kernel (losses.resolve_eval)
+        res = losses.resolve_eval(rendered_opacity, rendered_feature, rendered_vfeature, bg_color)
+        res.update({
+            "render": rendered_image, "depth": rendered_depth, "geo_normal": rendered_normal, "opacity": rendered_opacity,
+            "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "num_rendered": num_rendered, "weights": weights,
+            "raster_state": num_rendered._st if isinstance(num_rendered, raster.LazyCount) else None, "diffuse_light": None})
+        return res
 
     inv_o = 1.0 / rendered_opacity.clamp_min(1e-5)
     rendered_feature = rendered_feature * inv_o

@@ -69,3 +69,36 @@ def test_training_step_fused_matches_torch_tail():
     for a, b in zip(g1, g0):
         rel = float((a - b).norm() / b.norm().clamp_min(1e-20))
         assert rel < 1e-3, rel    # north-star gradient tolerance (atomic order differs run to run)
+
+
+@pytest.mark.parametrize("bgv", [(0.0, 0.0, 0.0), (0.1, 0.2, 0.3)])
+def test_eval_frame_fused_resolve_matches_torch_tail(bgv):
+    """render_view(is_training=False): the one-kernel eval resolve (losses.resolve_eval, csrc/resolve.cu) against the
+    torch mirror of gaussian_renderer/svgss.py:187-262 on the same rasteriser outputs -- every result image within
+    2e-6 absolute (powf vs torch.pow in rgb_to_srgb; everything else is the same fp32 arithmetic)."""
+    import numpy as np
+    from svgir_b200 import pipeline, scene, shading
+    dev = torch.device("cuda:0")
+    cloud = scene.make_surfels(5000, seed=21)
+    mats = scene.make_materials(cloud, 24, seed=22, env_hw=(16, 32))
+    pc = pipeline.model_from_scene(cloud, mats, dev, requires_grad=False)
+    cam = pipeline.camera_from_scene(scene.look_at_camera(144, 112, 1, 4), dev)
+    env = torch.from_numpy(np.random.default_rng(3).uniform(0, 4, (16, 32, 3)).astype(np.float32)).to(dev)
+    bg = torch.tensor(bgv, device=dev)
+    old = pipeline.FUSED_RESOLVE
+    try:
+        with torch.no_grad():
+            pipeline.FUSED_RESOLVE = True
+            got = pipeline.render_view(cam, pc, (env, shading.MODE_FIXED), bg, is_training=False)
+            pipeline.FUSED_RESOLVE = False
+            want = pipeline.render_view(cam, pc, (env, shading.MODE_FIXED), bg, is_training=False)
+    finally:
+        pipeline.FUSED_RESOLVE = old
+    keys = ("pbr", "normal", "base_color", "roughness", "lights", "local_lights", "visibility", "direct", "indirect")
+    for k in keys:
+        assert got[k].shape == want[k].shape, (k, got[k].shape, want[k].shape)
+        err = float((got[k] - want[k]).abs().max())
+        assert err <= 2e-6 * max(1.0, float(want[k].abs().max())), (k, err)
+    for k in ("render", "depth", "opacity", "geo_normal"):
+        assert torch.equal(got[k], want[k]), k
+    assert float(want["pbr"].max()) > 0.05 and float(want["opacity"].max()) > 0.5   # the frame is not empty
