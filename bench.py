@@ -135,11 +135,15 @@ def run_ours(args):
     # NVLink at the end of the step's graph (csrc/peer_allreduce.cu); falls back to the NCCL all-reduce after the
     # graph when the box cannot provide peer-mapped memory
     peer, reduce_note = None, None
-    if world > 1 and args.reduce == "p2p":
+    if world > 1 and args.reduce in ("p2p", "p2p-overlap"):
         ok = torch.ones(1, device=dev)
         try:
             peer = svdist.PeerAllReduce(dev)
-            bucket = svdist.FlatGradBucket(params, extra_floats=1, alloc=peer.allocate, reducer=peer.all_reduce)
+            if args.reduce == "p2p":
+                bucket = svdist.FlatGradBucket(params, extra_floats=1, alloc=peer.allocate, reducer=peer.all_reduce)
+            else:   # rasteriser-side segment summed on a side stream under the shading backward
+                bucket = svdist.FlatGradBucket(params, segments=pipeline.reduce_segments(pc), extra_floats=1,
+                                               alloc=peer.allocate, segment_peer=peer)
         except Exception as e:  # noqa: BLE001
             ok.zero_()
             reduce_note = "p2p unavailable (%s: %s); NCCL all-reduce after the step" % (type(e).__name__, str(e)[:120])
@@ -341,8 +345,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "grad_allreduce": None if bucket is None else {
                 "bytes": bucket.nbytes, "mode":
-                ("svgir_peer_allreduce: one kernel over NVLink peer memory (%s), recorded at the end of the step's graph"
-                 % ("NVSwitch multicast ld_reduce/st" if peer.multicast else "128-bit peer loads/stores")) if peer is not None else
+                (("svgir_peer_allreduce over NVLink peer memory (%s), in the step's graph: " % (
+                    "NVSwitch multicast ld_reduce/st" if peer.multicast else "128-bit peer loads/stores")) +
+                 ("one kernel at the end of the step" if args.reduce == "p2p" else
+                  "rasteriser-side segment on a side stream (%d CTAs) under the shading backward, shading-side segment after it"
+                  % peer.BG_GRID)) if peer is not None else
                 (("2 segments issued inside the backward pass, captured in the step's graph; the overlapped one on a "
                   "%d-CTA communicator" % args.bg_ctas if args.bg_ctas > 0 else
                   "2 segments issued inside the backward pass, captured in the step's graph") if overlap else
@@ -669,7 +676,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
     ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
-    ap.add_argument("--reduce", default="p2p", choices=["overlap", "post", "p2p"],
+    ap.add_argument("--reduce", default="p2p", choices=["overlap", "post", "p2p", "p2p-overlap"],
                     help="N>1: p2p (default) = the svgir one-kernel all-reduce over NVLink peer memory at the end of the step's graph "
                          "(B200 x8: 2859 it/s vs 2739 with NCCL), falling back to `post` if the box has no peer-mapped memory; "
                          "post = one NCCL all-reduce of the flat gradient bucket right after the step's graph; "

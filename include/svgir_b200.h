@@ -441,7 +441,8 @@ int svgir_resolve_eval(int W, int H, const float* bg, const float* opacity, cons
  * rounds slices to 4 floats). The grid is at most one CTA per SM so all CTAs are co-resident. */
 #define SVGIR_MAX_PEERS 8
 #define SVGIR_PEER_BLOCKS 128
-#define SVGIR_PEER_FLAG_WORDS (2 * SVGIR_PEER_BLOCKS * SVGIR_MAX_PEERS)
+#define SVGIR_PEER_BANKS 4   /* independent flag banks: one per all-reduce that may be in flight at the same time */
+#define SVGIR_PEER_FLAG_WORDS (SVGIR_PEER_BANKS * 2 * SVGIR_PEER_BLOCKS * SVGIR_MAX_PEERS)
 typedef struct svgir_peer_comm {
     int32_t world, rank;
     float* bufs[SVGIR_MAX_PEERS];            /* bufs[i]: rank i's buffer as mapped in THIS process */
@@ -449,6 +450,13 @@ typedef struct svgir_peer_comm {
     float* multicast;                        /* multicast mapping of the buffers (NVLS), or NULL */
 } svgir_peer_comm;
 int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel, void* stream);
+/* The same on the sub-range [offset, offset+numel) of the buffers (both multiples of 4 floats), with flag bank
+ * `bank` (< SVGIR_PEER_BANKS; two launches that can overlap in time must use different banks) and `grid` CTAs
+ * (0 = default; the NVLink ports saturate at ~16). Used to sum the rasteriser-side gradients on a side stream while
+ * the shading backward still runs: svgir_shade_reserve_sms(n) makes the shading kernels leave n SMs to it. */
+int svgir_peer_allreduce_range(const svgir_peer_comm* comm, long long offset, long long numel, int bank, int grid,
+                               void* stream);
+void svgir_shade_reserve_sms(int n);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ struct PeerArgs {
     float* bufs[SVGIR_MAX_PEERS];
     unsigned int* flags[SVGIR_MAX_PEERS];
     float* mc;
-    long long numel;
+    long long offset, numel;   // floats
+    int bank;
 };
 
 __device__ __forceinline__ void put_flag(unsigned int* remote) {
@@ -37,7 +38,7 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& a, int phase) {
     __syncthreads();
     if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
         const int peer = threadIdx.x;
-        const int slot = (phase * SVGIR_PEER_BLOCKS + blockIdx.x) * SVGIR_MAX_PEERS;
+        const int slot = ((a.bank * 2 + phase) * SVGIR_PEER_BLOCKS + blockIdx.x) * SVGIR_MAX_PEERS;
         __threadfence_system();
         put_flag(a.flags[peer] + slot + a.rank);     // "rank a.rank, CTA b arrived" in the peer's area
         wait_flag(a.flags[a.rank] + slot + peer);    // the peer's CTA b arrived here
@@ -81,9 +82,9 @@ template <int WORLD, bool MC, bool WEAK>
 __global__ void __launch_bounds__(512) peer_allreduce_kernel(const PeerArgs a) {
     peer_barrier(a, 0);
     // slice of this rank, in float4 units
-    const long long n4 = (a.numel + 3) / 4;
+    const long long o4 = a.offset / 4, n4 = (a.numel + 3) / 4;
     const long long per = (n4 + WORLD - 1) / WORLD;
-    const long long lo = per * a.rank, hi = min(n4, lo + per);
+    const long long lo = o4 + per * a.rank, hi = min(o4 + n4, lo + per);
     const long long stride = (long long)gridDim.x * blockDim.x;
     constexpr int U = MC ? 8 : (WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2));   // independent 16-byte requests in flight per thread: U (x WORLD)
     for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
@@ -140,15 +141,20 @@ static void launch_world(const PeerArgs& a, bool mc, bool weak, int grid, cudaSt
 
 using namespace svgir;
 
-extern "C" int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel, void* stream) {
+extern "C" int svgir_peer_allreduce_range(const svgir_peer_comm* comm, long long offset, long long numel, int bank,
+                                          int grid_req, void* stream) {
     if (!comm || comm->world < 1 || comm->world > SVGIR_MAX_PEERS || comm->rank < 0 || comm->rank >= comm->world) {
         set_error("peer_allreduce: bad comm (world must be 1..%d)", SVGIR_MAX_PEERS);
         return SVGIR_ERR_INVALID;
     }
-    if (numel < 0 || (numel & 3)) { set_error("peer_allreduce: numel must be a non-negative multiple of 4"); return SVGIR_ERR_INVALID; }
+    if (numel < 0 || (numel & 3) || offset < 0 || (offset & 3)) {
+        set_error("peer_allreduce: offset and numel must be non-negative multiples of 4");
+        return SVGIR_ERR_INVALID;
+    }
+    if (bank < 0 || bank >= SVGIR_PEER_BANKS) { set_error("peer_allreduce: bank %d outside [0,%d)", bank, SVGIR_PEER_BANKS); return SVGIR_ERR_INVALID; }
     if (comm->world == 1 || numel == 0) return SVGIR_OK;
     PeerArgs a;
-    a.world = comm->world; a.rank = comm->rank; a.mc = comm->multicast; a.numel = numel;
+    a.world = comm->world; a.rank = comm->rank; a.mc = comm->multicast; a.offset = offset; a.numel = numel; a.bank = bank;
     for (int i = 0; i < SVGIR_MAX_PEERS; i++) {
         a.bufs[i] = i < comm->world ? comm->bufs[i] : nullptr;
         a.flags[i] = i < comm->world ? comm->flags[i] : nullptr;
@@ -160,14 +166,15 @@ extern "C" int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel
     cudaStream_t s = (cudaStream_t)stream;
     // grid <= SVGIR_PEER_BLOCKS (< one CTA per SM): all CTAs co-resident, each pairs with its peers' twin. The NVLink
     // ports saturate with few CTAs (B200 x8, 104 MB: multicast 0.262 ms at 32 CTAs, 0.279 ms at 128; peer
-    // loads/stores 0.32 ms at any grid; NCCL 0.405 ms -- profiles/r01j_peer_allreduce.json)
+    // loads/stores 0.32 ms at any grid; NCCL 0.405 ms -- profiles/r01j_peer_allreduce_n8.json)
     const bool mc = a.mc != nullptr;
-    int grid = mc ? 32 : 64;
+    int grid = grid_req > 0 ? grid_req : (mc ? 32 : 64);
+    if (grid > SVGIR_PEER_BLOCKS) grid = SVGIR_PEER_BLOCKS;
     // tuning knobs (read per call so one process can A/B them): SVGIR_PEER_WEAK=0 -> system-scope relaxed accesses,
-    // SVGIR_PEER_GRID=<n> -> fewer CTAs (must be the same on every rank)
+    // SVGIR_PEER_GRID=<n> -> CTA count of default-grid launches (must be the same on every rank)
     const char* ev = getenv("SVGIR_PEER_WEAK");
     const bool weak = !(ev && ev[0] == '0');
-    if ((ev = getenv("SVGIR_PEER_GRID")) != nullptr) { const int g = atoi(ev); if (g >= 1 && g <= SVGIR_PEER_BLOCKS) grid = g; }
+    if (grid_req <= 0 && (ev = getenv("SVGIR_PEER_GRID")) != nullptr) { const int g = atoi(ev); if (g >= 1 && g <= SVGIR_PEER_BLOCKS) grid = g; }
     { TimedScope ts_("peer_allreduce", s);
       switch (comm->world) {
           case 2: launch_world<2>(a, mc, weak, grid, s); break;
@@ -179,4 +186,8 @@ extern "C" int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel
           default: launch_world<8>(a, mc, weak, grid, s); break;
       } }
     return check_launch("peer_allreduce", false, s);
+}
+
+extern "C" int svgir_peer_allreduce(const svgir_peer_comm* comm, long long numel, void* stream) {
+    return svgir_peer_allreduce_range(comm, 0, numel, 0, 0, stream);
 }

@@ -849,10 +849,15 @@ __global__ void __launch_bounds__(256) direct_light_bwd_kernel(int n, int He, in
 using namespace svgir;
 
 // persistent grid: enough CTAs to fill the 148 SMs a few times over, never more than the work
+// svgir_shade_reserve_sms(n): the persistent grids leave n SMs free for a kernel running beside them (the
+// peer-memory gradient all-reduce of the rasteriser-side segment, which is resident before the shading backward
+// starts); with a full-width grid the displaced CTAs would run as a second wave and double the kernel's time.
+static int g_reserved_sms = 0;
 static int shade_grid(int N, int threads, int ctas_per_sm) {
     const int wpc = threads / 32;
     const int need = (N + wpc - 1) / wpc;
-    return need < 148 * ctas_per_sm ? need : 148 * ctas_per_sm;
+    const int sms = 148 - g_reserved_sms;
+    return need < sms * ctas_per_sm ? need : sms * ctas_per_sm;
 }
 
 template <bool SPLIT, bool MET>
@@ -882,6 +887,8 @@ static void launch_shade_bwd(const ShadeArgs& a, const ShadeGradsK& g, cudaStrea
 }
 
 extern "C" {
+
+void svgir_shade_reserve_sms(int n) { g_reserved_sms = n < 0 ? 0 : (n > 100 ? 100 : n); }
 
 static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, ShadeArgs& a, cudaStream_t s) {
     if (!c || !in || c->N < 0 || c->Ns <= 0 || c->env_h <= 0 || c->env_w <= 0) { set_error("shade: bad cfg"); return SVGIR_ERR_INVALID; }

@@ -76,7 +76,8 @@ def build(verbose: bool = False) -> str:
 
 MAX_PEERS = 8
 PEER_BLOCKS = 128
-PEER_FLAG_WORDS = 2 * PEER_BLOCKS * MAX_PEERS
+PEER_BANKS = 4
+PEER_FLAG_WORDS = PEER_BANKS * 2 * PEER_BLOCKS * MAX_PEERS
 
 
 class PeerComm(C.Structure):
@@ -113,6 +114,10 @@ def lib() -> C.CDLL:
     L.svgir_launch_count.restype = C.c_longlong
     L.svgir_peer_allreduce.argtypes = [C.POINTER(PeerComm), C.c_longlong, C.c_void_p]
     L.svgir_peer_allreduce.restype = C.c_int
+    L.svgir_peer_allreduce_range.argtypes = [C.POINTER(PeerComm), C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+    L.svgir_peer_allreduce_range.restype = C.c_int
+    L.svgir_shade_reserve_sms.argtypes = [C.c_int]
+    L.svgir_shade_reserve_sms.restype = None
     _lib = L
     return L
 
@@ -148,4 +153,5 @@ EXPORTED_SYMBOLS = [
     "svgir_bvh_build", "svgir_bvh_pack_leaves", "svgir_bvh_trace_opacity",
     "svgir_sample_incident_rays", "svgir_render_equation_sh_forward", "svgir_render_equation_sh_backward",
     "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce", "svgir_resolve_eval",
+    "svgir_peer_allreduce_range", "svgir_shade_reserve_sms",
 ]

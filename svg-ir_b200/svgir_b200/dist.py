@@ -135,6 +135,50 @@ class PeerAllReduce:
         torch.cuda.synchronize(self.device)
         return self.flat[:int(numel)]
 
+    # ---- segment-wise exchange overlapped with the backward pass --------------------------------------------
+    BG_GRID = int(os.environ.get("SVGIR_PEER_BG_GRID", "16"))   # CTAs (= SMs) of an overlapped segment's kernel
+
+    def begin_segments(self):
+        """Before the backward pass: the shading kernels launched from now on leave BG_GRID SMs to the overlapped
+        all-reduce (their persistent grid would otherwise run its displaced CTAs as a second wave)."""
+        from . import _lib
+        self._joins = []
+        _lib.lib().svgir_shade_reserve_sms(self.BG_GRID)
+
+    def reduce_segment(self, k: int, lo: int, hi: int, last: bool):
+        """Sums floats [lo, hi) of the buffer over ranks with flag bank k. Every segment but the last runs on a side
+        stream (forked from / joined to the current one with events, so it is capturable) on BG_GRID CTAs, beside
+        whatever the backward pass launches next; the last one runs on the current stream at full width."""
+        from . import _lib
+        L = _lib.lib()
+        if k >= _lib.PEER_BANKS:
+            raise ValueError("at most %d segments" % _lib.PEER_BANKS)
+        lo4, hi4 = lo // 4 * 4, (hi + 3) // 4 * 4
+        cur = torch.cuda.current_stream(self.device)
+        if last:
+            L.svgir_shade_reserve_sms(0)
+            _lib.check(L.svgir_peer_allreduce_range(self.comm, lo4, hi4 - lo4, k, 0, cur.cuda_stream), "peer_allreduce")
+            return
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._side.wait_event(fork)
+        _lib.check(L.svgir_peer_allreduce_range(self.comm, lo4, hi4 - lo4, k, self.BG_GRID, self._side.cuda_stream),
+                   "peer_allreduce")
+        join = torch.cuda.Event()
+        join.record(self._side)
+        self._joins.append(join)
+
+    def end_segments(self):
+        """After the last segment: the current stream waits for the overlapped ones."""
+        from . import _lib
+        _lib.lib().svgir_shade_reserve_sms(0)
+        cur = torch.cuda.current_stream(self.device)
+        for j in getattr(self, "_joins", []):
+            cur.wait_event(j)
+        self._joins = []
+
     def all_reduce(self, tensor: Optional[torch.Tensor] = None):
         """In-place sum over ranks of the whole flat buffer (the `tensor` argument, if given, must be a view of it)."""
         from . import _lib
@@ -164,7 +208,7 @@ class FlatGradBucket:
     def __init__(self, params: Sequence[torch.Tensor], average: bool = False,
                  segments: Optional[Sequence[Sequence[int]]] = None, extra_floats: int = 0,
                  segment_groups: Optional[Sequence] = None, alloc: Optional[Callable[[int], torch.Tensor]] = None,
-                 reducer: Optional[Callable[[torch.Tensor], None]] = None):
+                 reducer: Optional[Callable[[torch.Tensor], None]] = None, segment_peer: Optional["PeerAllReduce"] = None):
         params = [p for p in params if p is not None]
         if not params:
             raise ValueError("FlatGradBucket needs at least one parameter")
@@ -205,6 +249,11 @@ class FlatGradBucket:
         # `alloc(n)` supplies the flat storage (PeerAllReduce.allocate: peer-mapped memory) and `reducer(flat)` the
         # in-place sum over ranks (PeerAllReduce.all_reduce: one kernel on the current stream, no NCCL); with a
         # reducer the bucket must be a single segment, reduced after the backward pass
+        # `segment_peer`: segment-wise exchange through PeerAllReduce.reduce_segment -- every segment but the last is
+        # summed on a side stream while the backward pass continues (hooks fire as in the NCCL overlap mode)
+        self.segment_peer = segment_peer
+        if segment_peer is not None and reducer is not None:
+            raise ValueError("use either reducer (whole buffer) or segment_peer (per segment)")
         self.reducer = reducer
         if reducer is not None and len(self.segments) != 1:
             raise ValueError("a custom reducer works on the whole bucket: use one segment")
@@ -262,6 +311,11 @@ class FlatGradBucket:
                 self.flat.div_(world_size())
             self.reducer(self.flat)   # stream-ordered kernel: nothing to wait for
             return None
+        if self.segment_peer is not None:
+            if self.average:
+                self.flat.div_(world_size())
+            self.segment_peer.all_reduce(self.flat)
+            return None
         if world_size() == 1:
             return None
         if self.average:
@@ -284,6 +338,12 @@ class FlatGradBucket:
             if self.average:
                 self.flat.div_(world_size())
             self.reducer(self.flat)
+            return
+        if self.segment_peer is not None:
+            lo, hi = self.seg_bounds[k]
+            if self.average:
+                self.flat[lo:hi].div_(world_size())
+            self.segment_peer.reduce_segment(k, lo, hi, last=(k == len(self.segments) - 1))
             return
         if world_size() == 1:
             return
@@ -313,6 +373,8 @@ class FlatGradBucket:
         self._pending = []
         self.overlap_log = []
         self._armed = True
+        if self.segment_peer is not None:
+            self.segment_peer.begin_segments()
 
     def finish_overlap(self):
         """Issues the segments whose hooks did not all fire (parameters without a gradient this step),
@@ -323,6 +385,8 @@ class FlatGradBucket:
         for w in self._pending:
             w.wait()
         self._pending = []
+        if self.segment_peer is not None:
+            self.segment_peer.end_segments()
 
     @property
     def nbytes(self) -> int:

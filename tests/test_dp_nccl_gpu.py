@@ -189,6 +189,25 @@ def _peer_worker(rank, world, port, q):
             torch.cuda.synchronize()
             for a, b in zip(params, pc_e.trainable() + [env_e]):
                 step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+        # segment-wise exchange: the rasteriser-side gradients are summed on a side stream (16 CTAs) while the shading
+        # backward runs on the SMs left to it, the shading-side segment after it -- all inside the step's graph
+        pc_s, env_s = model()
+        params_s = pc_s.trainable() + [env_s]
+        peer_s = D.PeerAllReduce(dev)
+        bucket_s = D.FlatGradBucket(params_s, segments=pipeline.reduce_segments(pc_s), extra_floats=1,
+                                    alloc=peer_s.allocate, segment_peer=peer_s)
+        runner_s = pipeline.GraphedTrainingStep(pc_s, env_s, bg, cams[0], gts[0], bucket=bucket_s, reduce_in_graph=True)
+        for step in range(3):
+            views = [(2 * step + k + 1) % 4 for k in range(world)]
+            for t in pc_e.trainable() + [env_e]:
+                t.grad = None
+            for v in views:
+                pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v % 2], zero_grad=False)
+            runner_s(cams[views[rank]], gts[views[rank] % 2])
+            torch.cuda.synchronize()
+            assert sorted(bucket_s.overlap_log) == [0, 1], bucket_s.overlap_log
+            for a, b in zip(params_s, pc_e.trainable() + [env_e]):
+                step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
         q.put((rank, out, step_worst, None))
         torch.cuda.synchronize()
         dist.barrier()
