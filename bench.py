@@ -676,12 +676,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
     ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
-    ap.add_argument("--reduce", default="p2p", choices=["overlap", "post", "p2p", "p2p-overlap"],
-                    help="N>1: p2p (default) = the svgir one-kernel all-reduce over NVLink peer memory at the end of the step's graph "
-                         "(B200 x8: 2859 it/s vs 2739 with NCCL), falling back to `post` if the box has no peer-mapped memory; "
-                         "post = one NCCL all-reduce of the flat gradient bucket right after the step's graph; "
-                         "overlap = segment-wise all-reduce issued inside the backward pass and captured in the graph "
-                         "(measured slower on B200 x2: the NCCL kernel takes SMs from the shading backward, 657 vs 678 it/s)")
+    ap.add_argument("--reduce", default="p2p-overlap", choices=["overlap", "post", "p2p", "p2p-overlap"],
+                    help="N>1 gradient exchange. p2p-overlap (default): svgir kernels over NVLink peer memory inside the step's graph, "
+                         "the rasteriser-side segment on a side stream under the shading backward, the shading-side segment after it "
+                         "(B200 x8: 3021 it/s = 96.5%% of 8 x N=1); p2p: one such kernel at the end of the step (2891 it/s); both fall "
+                         "back to `post` if the box has no peer-mapped memory. post: one NCCL all-reduce after the graph (2739 it/s). "
+                         "overlap: NCCL, segment-wise inside the backward pass (slower: the NCCL kernel takes SMs from the shading backward)")
     ap.add_argument("--bg-ctas", type=int, default=4, help="--reduce overlap: CTA limit of the communicator that carries the "
                     "segment overlapped with the shading backward (0 = default communicator for both segments)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")

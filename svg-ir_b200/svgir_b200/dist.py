@@ -136,7 +136,7 @@ class PeerAllReduce:
         return self.flat[:int(numel)]
 
     # ---- segment-wise exchange overlapped with the backward pass --------------------------------------------
-    BG_GRID = int(os.environ.get("SVGIR_PEER_BG_GRID", "16"))   # CTAs (= SMs) of an overlapped segment's kernel
+    BG_GRID = int(os.environ.get("SVGIR_PEER_BG_GRID", "8"))   # CTAs (= SMs) of an overlapped segment's kernel
 
     def begin_segments(self):
         """Before the backward pass: the shading kernels launched from now on leave BG_GRID SMs to the overlapped
