@@ -7,7 +7,9 @@ surfels, one 800x800 view per iteration, 64 light samples, S=4 / VS=52 G-buffer 
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU; under
                                                            torchrun every rank renders its own view and
-                                                           the per-surfel gradients are all-reduced)
+                                                           the per-surfel gradients are summed over NVLink
+                                                           peer memory inside the step's CUDA graph)
+  python bench.py --workload relight ...                   C3-eval relighting frame, ms/frame
   python bench.py --impl reference ...                     the reference path restated on the host CPU
                                                            (oracle/), bounded sample per step
   python bench.py --impl reference_cuda ...                (extra) reference CUDA rasteriser (oracle/_ref)

@@ -4,8 +4,10 @@ The reference is single-process / single-GPU (train.py:108-143 renders ONE view 
 grep for nccl|distributed finds nothing), so nothing here is ported: this is the new harness the
 north star asks for.  One process per GPU holds a full replica of the surfel parameters; a step
 draws V views and rank r renders views r, r+G, ...; the per-surfel parameter gradients are summed
-with ONE all-reduce over a flat fp32 buffer (NCCL over NVLink on the GPU box, gloo in the CPU
-tests).  Relighting sweeps shard the (view x env-map) grid round-robin with no collective.
+once per step over a flat fp32 buffer -- on the GPU box by the svgir peer-memory kernels
+(`PeerAllReduce`: the buffer is peer-mapped, NVSwitch multicast or peer loads/stores over NVLink, the
+rasteriser-side segment overlapped with the shading backward) or by NCCL, in the CPU tests by gloo.
+Relighting sweeps shard the (view x env-map) grid round-robin with no collective.
 
 PyTorch is used for the process group and device memory only.
 """
