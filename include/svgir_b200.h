@@ -92,7 +92,8 @@ typedef struct svgir_raster_state {
     uint32_t* tile_count;     /* [T] */
     uint32_t* tile_cursor;    /* [T] scratch */
     uint32_t* ranges;         /* [T,2] (start,end), (0,0) for empty tiles */
-    uint32_t* big_tiles;      /* [2*T+4] scratch: work lists of the medium / large tile sorters */
+    uint32_t* big_tiles;      /* [3*T+4] scratch: work lists of the medium / large tile sorters, then the tiles'
+                                 compositing order (heaviest first) at [2+2T, 2+3T) */
     int32_t* num_rendered;    /* [2] device: R, overflow flag */
     uint64_t* keys;           /* [cap_R] scratch, (depth_bits<<32)|surfel */
     uint32_t* point_list;     /* [cap_R] sorted surfel ids */

@@ -20,6 +20,12 @@ namespace svgir {
 #define SMALL_CAP 2048
 #define MEDIUM_CAP 16384
 
+#define ORDER_BUCKETS 512
+__device__ __forceinline__ int order_bucket(uint32_t count) {
+    const uint32_t k = count >> 3;
+    return ORDER_BUCKETS - 1 - (int)(k < ORDER_BUCKETS - 1 ? k : ORDER_BUCKETS - 1);
+}
+
 // Exclusive scan over tile counts; single CTA of 1024 threads.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* __restrict__ count,
                                                          uint32_t* __restrict__ cursor,
@@ -29,10 +35,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
     __shared__ uint32_t n_medium, n_large;
+    __shared__ uint32_t hist[ORDER_BUCKETS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) { carry_s = 0; n_medium = 0; n_large = 0; }
+    for (int i = tid; i < ORDER_BUCKETS; i += 1024) hist[i] = 0;
     __syncthreads();
-    // big[0] = #medium, big[1] = #large, big[2 .. 2+T) medium list, big[2+T .. 2+2T) large list
+    // big[0] = #medium, big[1] = #large, big[2 .. 2+T) medium list, big[2+T .. 2+2T) large list,
+    // big[2+2T .. 2+3T) compositing order of the tiles (heaviest first, see below)
     for (int base = 0; base < T; base += 1024) {
         const int t = base + tid;
         const uint32_t v = t < T ? count[t] : 0u;
@@ -64,6 +73,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
                 if (v <= MEDIUM_CAP) big[2 + atomicAdd(&n_medium, 1u)] = (uint32_t)t;
                 else big[2 + T + atomicAdd(&n_large, 1u)] = (uint32_t)t;
             }
+            atomicAdd(&hist[order_bucket(v)], 1u);
         }
         __syncthreads();
         if (tid == 1023) carry_s = start + v;
@@ -76,6 +86,28 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int T, const uint32_t* 
         big[0] = n_medium;
         big[1] = n_large;
     }
+    // Compositing order: tiles by descending instance count (counting sort on count/8, bucket 0 = heaviest). The
+    // compositors map blockIdx.x through it, so the hardware block scheduler hands out the long tiles first and the
+    // last wave of the grid consists of short ones (longest-processing-time-first; the order inside a bucket is
+    // arbitrary and only affects scheduling).
+    __syncthreads();
+    if (wid == 0) {   // exclusive scan of the histogram, 16 buckets per lane
+        uint32_t loc[ORDER_BUCKETS / 32], sum = 0;
+#pragma unroll
+        for (int i = 0; i < ORDER_BUCKETS / 32; i++) { loc[i] = sum; sum += hist[lane * (ORDER_BUCKETS / 32) + i]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        const uint32_t base = inc - sum;
+#pragma unroll
+        for (int i = 0; i < ORDER_BUCKETS / 32; i++) hist[lane * (ORDER_BUCKETS / 32) + i] = base + loc[i];
+    }
+    __syncthreads();
+    uint32_t* order = big + 2 + 2 * T;
+    for (int t = tid; t < T; t += 1024) order[atomicAdd(&hist[order_bucket(count[t])], 1u)] = (uint32_t)t;
 }
 
 // Scatter (depth_bits<<32 | surfel) into the tile buckets (duplicateWithKeys, rasterizer_impl.cu:70-111).

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
     const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
     const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
     float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures,
-    const int32_t* __restrict__ num_rendered) {
+    const int32_t* __restrict__ num_rendered, const uint32_t* __restrict__ tile_order) {
     constexpr bool GENERIC = S_T < 0;
     const int S = GENERIC ? c.S : S_T;
     const int NV = GENERIC ? c.VS / 4 : NV_T;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
 
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles first (binning.cu: tile_scan_kernel)
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     if (total == 0 || num_rendered[1]) return;  // empty tile, or the forward's bins overflowed (nothing valid)
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
     const float* __restrict__ gpix_depth, const float* __restrict__ gpix_opac,
     const float* __restrict__ gpix_feature, const float* __restrict__ gpix_vfeature,
     float* __restrict__ geo_grad, float* __restrict__ dL_dfeatures, float* __restrict__ dL_dvfeatures,
-    const int32_t* __restrict__ num_rendered) {
+    const int32_t* __restrict__ num_rendered, const uint32_t* __restrict__ tile_order) {
     using LY = LaneBwdLayout<S_T, NV_T>;
     constexpr int S = S_T, NV = NV_T;
     constexpr int SP = LY::SP, NVP = LY::NVP, STRIDE = LY::STRIDE, LCH = LY::LCH, NG = LY::NG, GS = LY::GS;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
 
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles first (binning.cu: tile_scan_kernel)
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     if (total == 0 || num_rendered[1]) return;  // empty tile, or the forward's bins overflowed (nothing valid)
@@ -690,7 +690,7 @@ static int launch_lane_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                                       (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
                                       st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
                                       g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
-                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered); }
+                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered, st.big_tiles + 2 + 2 * gx * gy); }
     return check_launch("composite_bwd", c.debug, s);
 }
 
@@ -720,7 +720,7 @@ static int launch_one_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                                       (const uint2*)st.ranges, st.point_list, st.final_T, st.final_D,
                                       st.n_contrib, g.dL_dcolor, g.dL_dnormal, g.dL_ddepth,
                                       g.dL_dopacity, g.dL_dfeature, g.dL_dvfeature, g.geo_grad,
-                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered); }
+                                      g.dL_dfeatures, g.dL_dvfeatures, st.num_rendered, st.big_tiles + 2 + 2 * gx * gy); }
     return check_launch("composite_bwd", c.debug, s);
 }
 

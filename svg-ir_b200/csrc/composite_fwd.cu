@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(TILE_PIX, S_T >= 0 && S_T <= 8 ? 4 : 1) compos
     float* __restrict__ final_T, float* __restrict__ final_D, uint32_t* __restrict__ n_contrib,
     float* __restrict__ out_color, float* __restrict__ out_normal, float* __restrict__ out_depth,
     float* __restrict__ out_opac, float* __restrict__ out_feature, float* __restrict__ out_vfeature,
-    float* __restrict__ out_weights) {
+    float* __restrict__ out_weights, const uint32_t* __restrict__ tile_order) {
     constexpr bool GENERIC = S_T < 0;
     // PACKED: the staged vfeature row is transposed to [4 vertices][NVP channels] so that channel PAIRS are
     // accumulated with one FFMA2 each (2 fused multiply-adds per issue slot)
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(TILE_PIX, S_T >= 0 && S_T <= 8 ? 4 : 1) compos
     if (num_rendered[1]) return;  // binning overflowed: nothing valid to render
     const int W = c.W, H = c.H;
     const int gx = (W + TILE - 1) / TILE;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // heaviest tiles first (binning.cu: tile_scan_kernel)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wx0 = (tile % gx) * TILE + (wid & 1) * WARP_PX_W, wy0 = (tile / gx) * TILE + (wid >> 1) * WARP_PX_H;
     const int px = wx0 + (lane & (WARP_PX_W - 1)), py = wy0 + (lane / WARP_PX_W);
@@ -337,7 +337,8 @@ static int launch_one(const svgir_raster_cfg& c, const svgir_raster_in& in, svgi
     { TimedScope ts_("composite_fwd", s); k<<<gx * gy, TILE_PIX, smem, s>>>(c, in.features, in.vfeatures, (const float4*)st.rec,
                                       (const uint2*)st.ranges, st.point_list, st.num_rendered,
                                       st.final_T, st.final_D, st.n_contrib, out.color, out.normal,
-                                      out.depth, out.opacity, out.feature, out.vfeature, out.weights); }
+                                      out.depth, out.opacity, out.feature, out.vfeature, out.weights,
+                                      st.big_tiles + 2 + 2 * gx * gy); }
     return check_launch("composite_fwd", c.debug, s);
 }
 

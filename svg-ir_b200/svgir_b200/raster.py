@@ -292,7 +292,7 @@ def preprocess(s: RasterSettings, means3D, opacities, scales=None, rotations=Non
     t["tile_count"] = torch.empty((T,), **i32)
     t["tile_cursor"] = torch.empty((T,), **i32)
     t["ranges"] = torch.empty((T, 2), **i32)
-    t["big_tiles"] = torch.empty((2 * T + 4,), **i32)
+    t["big_tiles"] = torch.empty((3 * T + 4,), **i32)   # sorter work lists + the tiles' compositing order
     t["num_rendered"] = torch.zeros((2,), **i32)
     t["final_T"] = torch.empty((H * W,), **f32)
     t["final_D"] = torch.empty((H * W,), **f32)
