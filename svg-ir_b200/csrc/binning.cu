@@ -197,10 +197,11 @@ __global__ void __launch_bounds__(256) sort_small_kernel(const uint2* __restrict
                                                          const uint64_t* __restrict__ keys,
                                                          uint32_t* __restrict__ point_list,
                                                          uint64_t* __restrict__ sorted_keys,
-                                                         const int32_t* __restrict__ num_rendered) {
+                                                         const int32_t* __restrict__ num_rendered,
+                                                         const uint32_t* __restrict__ tile_order) {
     __shared__ uint64_t buf[SMALL_CAP];
     if (num_rendered[1]) return;
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];   // fullest buckets first
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
     if (n == 0 || n > SMALL_CAP) return;
@@ -276,7 +277,7 @@ int launch_binning(const svgir_raster_cfg& c, svgir_raster_state& st, const int3
     int rc = check_launch("emit", c.debug, s);
     if (rc) return rc;
     { TimedScope ts_("sort_small", s); sort_small_kernel<<<T, 256, 0, s>>>((const uint2*)st.ranges, st.keys, st.point_list,
-                                        st.sorted_keys, st.num_rendered); }
+                                        st.sorted_keys, st.num_rendered, st.big_tiles + 2 + 2 * T); }
     { TimedScope ts_("sort_medium", s); sort_medium_kernel<<<148, 1024, MEDIUM_CAP * 8, s>>>(T, (const uint2*)st.ranges, st.big_tiles,
                                                          st.keys, st.point_list, st.sorted_keys,
                                                          st.num_rendered); }
