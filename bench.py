@@ -360,6 +360,13 @@ def run_ours(args):
                          "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
                          "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
             "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
+            # the same per-launch event times grouped by stage: svgss rasteriser forward+backward alone (BASELINE.json
+            # configs[1]'s shape), the render_equation shading, the resolve+loss tail
+            "stage_ms": {
+                "svgss_fwd_bwd": round(sum(kt[k] for k in ("preprocess", "tile_scan", "emit", "sort_small", "composite_fwd",
+                                                           "composite_bwd", "preprocess_bwd")) + kt["tile_scan"], 4),
+                "render_equation_fwd_bwd": round(kt["shade_fwd"] + kt["shade_bwd"], 4),
+                "loss_tail": round(kt["train_loss_fwd"] + kt["train_loss_bwd"], 4)},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(1, 0)
