@@ -180,3 +180,12 @@ def test_gloo_world2_gradient_allreduce():
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [2.0, 2.0]          # max over ranks
     assert sorted(r[3] for r in res) == [2, 3]        # 5 views dealt 3 + 2
+
+
+def test_peer_allreduce_needs_a_process_group_and_has_no_fallback():
+    """PeerAllReduce is the peer-memory (GPU box) exchange: outside an initialised multi-rank group it raises instead
+    of silently degrading; callers (bench.py) then choose the NCCL path explicitly."""
+    assert not dist.is_initialized()
+    with pytest.raises(RuntimeError):
+        D.PeerAllReduce(torch.device("cpu"))
+    assert D.background_group() is None   # NCCL-only helper: no group outside NCCL
