@@ -97,3 +97,21 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "liboracle" in txt or "oracle/" in txt.replace("oracle/ ", ""):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_compat_C_objects_have_the_reference_positional_arity():
+    """The narrowest drop-in seam is `from svgss_rasterization import _C` (gaussian_renderer/svgss_rasterization.py:8):
+    the `_C` objects must take the pybind modules' positional argument counts -- svgss forward 24 / backward 31
+    (svgss_rasterization/rasterize_points.h:18-82), rgss forward 23 / backward 27
+    (rgss-rasterization/rasterize_points.cu:36-60,145-173), mark_visible 3 (rasterize_points.h:84-87)."""
+    import inspect
+    import svgss_rasterization as sv
+    import rgss_rasterization as rg
+    want = {(sv, "rasterize_gaussians"): 24, (sv, "rasterize_gaussians_backward"): 31, (sv, "mark_visible"): 3,
+            (rg, "rasterize_gaussians"): 23, (rg, "rasterize_gaussians_backward"): 27, (rg, "mark_visible"): 3}
+    for (mod, name), n in want.items():
+        params = inspect.signature(getattr(mod._C, name)).parameters
+        assert len(params) == n, (mod.__name__, name, len(params), n)
+    for mod in (sv, rg):
+        for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "_RasterizeGaussians", "_C"):
+            assert hasattr(mod, name), (mod.__name__, name)
