@@ -115,3 +115,30 @@ def test_compat_C_objects_have_the_reference_positional_arity():
     for mod in (sv, rg):
         for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "_RasterizeGaussians", "_C"):
             assert hasattr(mod, name), (mod.__name__, name)
+
+
+def test_unmodified_reference_wrapper_binds_to_our_C():
+    """No-edit drop-in: with svg-ir_b200/ on sys.path the reference's OWN wrapper module
+    gaussian_renderer/svgss_rasterization.py resolves `from svgss_rasterization import _C` (its line 8) to this
+    repo's `_C` instead of JIT-compiling the reference extension. Import-level only (the reference tree exists in the
+    build container, not on the GPU box); skipped when /root/reference is absent."""
+    import importlib.util
+    import sys
+    ref = "/root/reference"
+    path = os.path.join(ref, "gaussian_renderer", "svgss_rasterization.py")
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    import svgss_rasterization as ours
+    saved_path, saved_utils = list(sys.path), {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    try:
+        sys.path.insert(1, ref)   # the wrapper imports utils.system_utils.Timing from the reference tree
+        spec = importlib.util.spec_from_file_location("_ref_svgss_wrapper", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod._C is ours._C
+        assert mod.GaussianRasterizationSettings._fields == ours.GaussianRasterizationSettings._fields[:15]
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            if k not in saved_utils:
+                del sys.modules[k]
