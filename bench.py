@@ -388,6 +388,124 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def run_c4(args):
+    """C4 (BASELINE.json configs[3]): multi-view data-parallel training -- 1M SV surfels, 8 views of 800x800 per step,
+    sharded over the ranks by view (rank r renders views r, r+N, ...; strong scaling: the step's work is fixed). Every
+    rank replays ONE captured step graph per local view, accumulating into its flat gradient bucket (zero_in_graph=
+    False), then the buckets are summed once: by the svgir peer-memory kernel (default) or NCCL (--reduce post).
+    value = view-iterations per second = 8 x steps / time. Not part of the driver's default run."""
+    import torch.distributed as dist
+    from svgir_b200 import _lib, pipeline, scene
+    from svgir_b200 import dist as svdist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    pipeline.SHADE_CULLED = bool(args.shade_all)
+    pipeline.FUSED_LOSS = not args.torch_loss
+    P, V = 1_000_000, 8
+    cloud = scene.make_surfels(P, seed=1238)
+    mats = scene.make_materials(cloud, NS, seed=1239)
+    pc = pipeline.model_from_scene(cloud, mats, dev)
+    env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+    bg = torch.zeros(3, device=dev)
+    cams = [pipeline.camera_from_scene(scene.look_at_camera(WIDTH, HEIGHT, v, V), dev) for v in range(V)]
+    rng = np.random.default_rng(1240)
+    gts = [torch.from_numpy(rng.uniform(0, 1, (3, HEIGHT, WIDTH)).astype(np.float32)).to(dev) for _ in range(2)]
+    params = pc.trainable() + [env]
+    mine = svdist.views_for_rank(V, rank, world)
+
+    peer, note = None, None
+    if world > 1 and args.reduce != "post":
+        ok = torch.ones(1, device=dev)
+        try:
+            peer = svdist.PeerAllReduce(dev)
+            bucket = svdist.FlatGradBucket(params, alloc=peer.allocate, reducer=peer.all_reduce)
+        except Exception as e:  # noqa: BLE001
+            ok.zero_()
+            note = "p2p unavailable (%s: %s); NCCL all-reduce" % (type(e).__name__, str(e)[:120])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            peer = None
+            note = note or "p2p unavailable on another rank; NCCL all-reduce"
+    if peer is None:
+        bucket = svdist.FlatGradBucket(params)
+    runner = pipeline.GraphedTrainingStep(pc, env, bg, cams[0], gts[0], bucket=bucket, zero_in_graph=False)
+
+    def step(i):
+        bucket.zero()
+        R = 0
+        for v in mine:
+            loss, res = runner(cams[v], gts[(i + v) % 2])
+            R += int(res["num_rendered"])
+        bucket.all_reduce()   # one exchange per step (no-op at N=1)
+        return loss, R
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        loss, R = step(i)
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        loss, R = step(args.warmup + i)
+    e1.record()
+    sync_all()
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    # per-kernel times of one local view, launched eagerly
+    _lib.timing_collect(reset=True)
+    _lib.timing_enable(True)
+    bucket.zero()
+    pipeline.training_step(cams[mine[0]], pc, env, bg, gts[0], zero_grad=False)
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    kt = {}
+    for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess", "preprocess_bwd", "emit", "sort_small"):
+        t, n = _lib.timing_collect(k)
+        kt[k] = round(t / max(n, 1), 4)
+    _lib.timing_collect(reset=True)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(V * args.steps / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: multi-view data-parallel stage-2 training, %dk SV surfels, %d views of %dx%d per step, Ns=%d, "
+                                   "S=%d, VS=%d" % (P // 1000, V, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT),
+                       "views_per_step": V, "views_per_rank": len(mine), "parallelism": f"view-dp{world}",
+                       "l2": "working set > L2 (per-sample light buffers 2 GB/view)", "R_last_step_local": R},
+            "clocks": clk, "gpu_launches": int(runner.launches_per_step * len(mine) * args.steps + (args.steps if peer is not None else 0)),
+            "grad_allreduce": None if world == 1 else {"bytes": bucket.nbytes, "mode": "svgir_peer_allreduce after the local views"
+                                                       if peer is not None else "one NCCL all-reduce after the local views", "note": note},
+            "kernels_ms": kt}), flush=True)
+    if world > 1:
+        runner = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+# ---------------------------------------------------------------------------------------------
 def run_relight(args):
     """C3-eval (BASELINE.json configs[2]): relighting frame = render_equation over all 300k surfels with
     Ns=384 samples under a fixed HDR env map (EnvLight semantics, scene/envmap.py:54-72) + svgss forward
@@ -694,8 +812,9 @@ def main():
     ap.add_argument("--bg-ctas", type=int, default=4, help="--reduce overlap: CTA limit of the communicator that carries the "
                     "segment overlapped with the shading backward (0 = default communicator for both segments)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="train", choices=["train", "relight"],
-                    help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64)")
+    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4"],
+                    help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64); "
+                         "c4 = 1M surfels, 8 views per step sharded over the ranks (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -704,6 +823,8 @@ def main():
         run_reference_cuda(args)
     elif args.workload == "relight":
         run_relight(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 

@@ -299,8 +299,15 @@ class GraphedTrainingStep:
     """
 
     def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
-                 gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False):
+                 gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False,
+                 zero_in_graph: bool = True):
         self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
+        # zero_in_graph=False (needs `bucket`): the graph ACCUMULATES into the bucket instead of zeroing it first, so a
+        # rank that renders several views per step replays it once per view and reduces once (C4: 8 views / step);
+        # the caller zeroes the bucket at the start of the step. A (re-)capture leaves the bucket's content untouched.
+        self.zero_in_graph = bool(zero_in_graph)
+        if not self.zero_in_graph and (bucket is None or reduce_in_graph):
+            raise ValueError("zero_in_graph=False needs a bucket and a reduction outside the graph")
         # reduce_in_graph: the segment-wise NCCL all-reduce of `bucket` is captured INSIDE the graph, overlapped
         # with the shading backward (FlatGradBucket.begin_overlap); the caller must not all-reduce again.
         self.reduce_in_graph = bool(reduce_in_graph and bucket is not None)
@@ -332,6 +339,7 @@ class GraphedTrainingStep:
 
     def _capture(self):
         cur = torch.cuda.current_stream(self.dev)
+        keep = None if self.zero_in_graph else self.bucket.flat.clone()   # accumulated gradients survive the capture
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
@@ -350,7 +358,7 @@ class GraphedTrainingStep:
         self.graph = torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(self.graph):
-            if self.bucket is not None:
+            if self.bucket is not None and self.zero_in_graph:
                 self.bucket.zero()
             with raster.count_mode("async", owner_resolves=True):
                 self.loss, self.res = training_step(self.cam, self.pc, self.env, self.bg, self.gt, zero_grad=False,
@@ -359,6 +367,8 @@ class GraphedTrainingStep:
                 self.flag_host.copy_(self.bucket.extra[0:1], non_blocking=True)
         self.launches_per_step = launch_count() - n0  # svgir kernels inside the graph
         self.captures += 1
+        if keep is not None:
+            self.bucket.flat.copy_(keep)
 
     def load_inputs(self, cam: ViewCamera, gt_image: torch.Tensor):
         c = self.cam

@@ -189,3 +189,15 @@ def test_peer_allreduce_needs_a_process_group_and_has_no_fallback():
     with pytest.raises(RuntimeError):
         D.PeerAllReduce(torch.device("cpu"))
     assert D.background_group() is None   # NCCL-only helper: no group outside NCCL
+
+
+def test_graphed_step_accumulate_mode_needs_a_bucket():
+    """GraphedTrainingStep(zero_in_graph=False) accumulates several views per step into the bucket: it needs one, and
+    the reduction must then happen outside the graph (host-side argument check, no CUDA involved)."""
+    from svgir_b200 import pipeline
+    a = torch.randn(4, 3, requires_grad=True)
+    bk = D.FlatGradBucket([a], extra_floats=1)
+    with pytest.raises(ValueError):
+        pipeline.GraphedTrainingStep(None, None, None, None, None, bucket=None, zero_in_graph=False)
+    with pytest.raises(ValueError):
+        pipeline.GraphedTrainingStep(None, None, None, None, None, bucket=bk, reduce_in_graph=True, zero_in_graph=False)
