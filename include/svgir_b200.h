@@ -429,6 +429,18 @@ typedef struct svgir_resolve_eval_out {
 int svgir_resolve_eval(int W, int H, const float* bg, const float* opacity, const float* feature,
                        const float* vfeature, const svgir_resolve_eval_out* out, void* stream);
 
+/* ---- SSIM and its gradient (written at the end of round 1, not yet run on a GPU) -----------
+ * utils/loss_utils.py:21-62 `ssim(img1, img2)`: 11-tap Gaussian window (sigma 1.5), zero padding, C1 = 0.01^2,
+ * C2 = 0.03^2, mean over [C,H,W]; called on the splatted colour and on the PBR image (svgss.py:282-293).
+ * forward: ssim_out[0] = ssim; gmaps [3,C,H,W] (optional) receives the per-pixel partials the backward needs;
+ * partials: svgir_ssim_blocks(C,H,W) floats of scratch; counter: one zero-initialised u32 (left at zero).
+ * backward: d_img1 [C,H,W] = grad_out[0] (NULL = 1) * d ssim / d img1; img2 is the ground truth (no gradient). */
+int svgir_ssim_blocks(int C, int H, int W);
+int svgir_ssim_forward(int C, int H, int W, const float* img1, const float* img2, float* ssim_out, float* gmaps,
+                       float* partials, unsigned int* counter, void* stream);
+int svgir_ssim_backward(int C, int H, int W, const float* img1, const float* img2, const float* gmaps,
+                        const float* grad_out, float* d_img1, void* stream);
+
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
  * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps
  * its flat gradient buffer in a symmetric allocation that is peer-mapped into all ranks of the box; the

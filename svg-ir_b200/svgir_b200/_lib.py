@@ -154,4 +154,5 @@ EXPORTED_SYMBOLS = [
     "svgir_sample_incident_rays", "svgir_render_equation_sh_forward", "svgir_render_equation_sh_backward",
     "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce", "svgir_resolve_eval",
     "svgir_peer_allreduce_range", "svgir_shade_reserve_sms",
+    "svgir_ssim_blocks", "svgir_ssim_forward", "svgir_ssim_backward",
 ]

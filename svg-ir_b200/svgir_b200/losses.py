@@ -141,3 +141,71 @@ def resolve_eval(opacity: torch.Tensor, feature: torch.Tensor, vfeature: torch.T
     _lib.check(L.svgir_resolve_eval(W, H, bg.data_ptr(), opacity.data_ptr(), feature.data_ptr(), vfeature.data_ptr(),
                                     C.byref(out), torch.cuda.current_stream(opacity.device).cuda_stream), "resolve_eval")
     return {n: store[i] for i, n in enumerate(names)}
+
+
+# ---- SSIM ----------------------------------------------------------------------------------------
+_SSIM_SCRATCH: dict = {}
+
+
+def _ssim_bind():
+    L = _lib.lib()
+    if not getattr(_ssim_bind, "done", False):
+        L.svgir_ssim_blocks.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.svgir_ssim_blocks.restype = C.c_int
+        L.svgir_ssim_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.svgir_ssim_forward.restype = C.c_int
+        L.svgir_ssim_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+        L.svgir_ssim_backward.restype = C.c_int
+        _ssim_bind.done = True
+    return L
+
+
+class _FusedSSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2):
+        L = _ssim_bind()
+        if img1.shape != img2.shape or img1.dim() != 3:
+            raise ValueError("fused_ssim expects two [C,H,W] images of the same shape")
+        if not img1.is_cuda:
+            raise RuntimeError("fused_ssim: CUDA tensors only (there is no CPU fallback)")
+        x, y = img1.detach().float().contiguous(), img2.detach().float().contiguous()
+        Cn, H, W = (int(v) for v in x.shape)
+        dev = x.device
+        nb = int(L.svgir_ssim_blocks(Cn, H, W))
+        key = (dev.index, nb)
+        sc = _SSIM_SCRATCH.get(key)
+        if sc is None:
+            sc = _SSIM_SCRATCH[key] = (torch.empty(nb, dtype=torch.float32, device=dev),
+                                       torch.zeros(1, dtype=torch.int32, device=dev))
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        gmaps = torch.empty((3, Cn, H, W), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.svgir_ssim_forward(Cn, H, W, x.data_ptr(), y.data_ptr(), out.data_ptr(),
+                                        gmaps.data_ptr() if gmaps is not None else None, sc[0].data_ptr(), sc[1].data_ptr(),
+                                        stream), "ssim_forward")
+        ctx.save_for_backward(x, y, gmaps)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        L = _ssim_bind()
+        x, y, gmaps = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("fused_ssim: no gradient with respect to the second (ground-truth) image")
+        if gmaps is None:
+            return None, None
+        Cn, H, W = (int(v) for v in x.shape)
+        g = grad.detach().float().reshape(1).contiguous()
+        d = torch.empty_like(x)
+        _lib.check(L.svgir_ssim_backward(Cn, H, W, x.data_ptr(), y.data_ptr(), gmaps.data_ptr(), g.data_ptr(), d.data_ptr(),
+                                         torch.cuda.current_stream(x.device).cuda_stream), "ssim_backward")
+        return d, None
+
+
+def fused_ssim(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+    """`ssim(img1, img2)` of utils/loss_utils.py:32-62 ([C,H,W] images, 11x11 Gaussian window, mean) as one CUDA kernel
+    per direction (csrc/ssim.cu). Differentiable with respect to img1; img2 is the ground truth.
+    STATUS: not yet run on a GPU (written after round 1's GPU budget was spent); tests/test_ssim_gpu.py is gated."""
+    return _FusedSSIM.apply(img1, img2)
