@@ -8,18 +8,30 @@ surfels, one 800x800 view per iteration, 64 light samples, S=4 / VS=52 G-buffer 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU; under
                                                            torchrun every rank renders its own view and
                                                            the per-surfel gradients are summed over NVLink
-                                                           peer memory inside the step's CUDA graph)
-  python bench.py --workload relight ...                   C3-eval relighting frame, ms/frame
+                                                           peer memory inside the step's CUDA graph).
+                                                           The default line also carries, measured after the
+                                                           timed region: `c4` (BASELINE configs[3]: 1M surfels,
+                                                           8 views/step, strong scaling; every N), and at N=1
+                                                           `relight` (C3-eval ms/frame), `visibility` (LBVH
+                                                           build + trace vs the reference kernels),
+                                                           `reference_cuda` (the reference CUDA extension +
+                                                           torch shading on this GPU: the denominator of the
+                                                           >=8x target) and `cpu_baseline`; at N>1
+                                                           `grad_allreduce.max_rel_err` (in-graph exchange vs
+                                                           NCCL on the same gradients). --no-extras skips them.
+  python bench.py --workload relight|c4|visibility ...     one of those workloads on its own
   python bench.py --impl reference ...                     the reference path restated on the host CPU
-                                                           (oracle/), bounded sample per step
+                                                           (oracle/), FULL steps, all host threads
   python bench.py --impl reference_cuda ...                (extra) reference CUDA rasteriser (oracle/_ref)
-                                                           + the reference's torch shading graph on the GPU
+                                                           + the torch restatement of the reference's shading
+                                                           graph (oracle/shading_oracle.py) on the GPU
 
 One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -39,7 +51,8 @@ P_SURFELS, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT, N_VIEWS = 300_000, 800, 800, 64, 
 WORKLOAD = ("C3-train: stage-2 svgss+render_equation fwd+bwd, %dk SV surfels, one %dx%d view/iter, Ns=%d, S=%d, VS=%d"
             % (P_SURFELS // 1000, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT))
 METRIC, UNIT = "fwd+bwd iters/sec at 800x800", "it/s"
-REF_TILE_STEP = 4        # --impl reference renders 1/16 of the tiles and shades 1/16 of the surfels per step
+L2_NOTE = "working set > L2 (per-sample light buffers 614 MB/iter)"
+EXTRAS_DEADLINE_S = 420   # watchdog: if an extra workload hangs, the headline line is printed without it
 
 
 def peaks():
@@ -50,37 +63,163 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def train_config(world: int) -> dict:
+    """`config` of the headline line -- identical in the repo arm and the reference arm."""
+    return {"workload": WORKLOAD, "views_per_step": world, "parallelism": f"view-dp{world}", "l2": L2_NOTE}
+
+
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons of one GPU from a thread of this process (NVML, ~3 ms period;
+    `nvidia-smi -lms` as the fallback) from start() on. mark() brackets the timed region: stop() reports the samples
+    inside it and, for context, over the whole loaded window (warm-up + timed region + what follows)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.thread = gpu_index, [], None, None
+        self.stop_flag = False
+        self.t0 = self.t1 = None
+        self.source = None
+
+    def _nvml_loop(self, R, h):
+        def const(new, old, default):
+            return getattr(R, new, getattr(R, old, default))
+        bits = [const("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                const("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                const("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                const("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        get_reasons = getattr(R, "nvmlDeviceGetCurrentClocksEventReasons", None) or R.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(R.nvmlDeviceGetMaxClockInfo(h, R.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                sm = float(R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM))
+                pw = R.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = int(get_reasons(h))
+                self.rows.append((time.perf_counter(), sm, mx, pw, [bool(rs & b) for b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), float(r[3]),
+                                  [v.lower().startswith("active") for v in r[4:8]]))
+            except Exception:
+                pass
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: resolve through the PCI bus id torch reports
+            try:
+                pr = torch.cuda.get_device_properties(self.idx)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)   # raises here, not in the thread, if NVML cannot answer
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi -lms 20"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def mark(self, begin: bool):
+        if begin:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.stop_flag = True
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        self.thread.join(timeout=1.0)
+        rows = list(self.rows)
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside if inside else rows
+
+        def summarise(rr):
+            sm = [r[1] for r in rr]
+            reasons = sorted({n for r in rr for n, v in zip(self.NAMES, r[4]) if v})
+            return (float(np.median(sm)) if sm else None, reasons, max((r[3] for r in rr), default=None))
+
+        sm_med, reasons, pw = summarise(use)
+        sm_all, reasons_all, _ = summarise(rows)
+        return {"sm_mhz": sm_med, "sm_max_mhz": max((r[2] for r in rows), default=None), "reasons": reasons,
+                "samples": len(inside), "power_w_max": pw, "source": self.source,
+                "window": "timed region" if inside else "whole run (no sample fell inside the timed region)",
+                "whole_run": {"samples": len(rows), "sm_mhz": sm_all, "reasons": reasons_all}}
+
+
+class Ctx:
+    """Per-process launch context (torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        from svgir_b200 import _lib
+        _lib.lib()  # fail loudly if the extension is missing
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_ms(self, ms: float) -> float:
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def make_peer_bucket(ctx: Ctx, make_bucket):
+    """(peer, bucket, note): the flat gradient bucket in peer-mapped memory, or (None, None, why). The ranks first AGREE
+    (MIN all-reduce) that each of them can construct a PeerAllReduce; only then do they enter allocate(), which runs
+    collectives itself (symmetric-memory rendezvous + barrier) -- a rank failing inside a collective cannot be caught
+    by the others, so nothing that may fail rank-locally is left between the agreement and the rendezvous."""
+    import torch.distributed as dist
+    from svgir_b200 import dist as svdist
+    ok = torch.ones(1, device=ctx.dev)
+    peer, note = None, None
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401  (import failures are rank-local)
+        peer = svdist.PeerAllReduce(ctx.dev)
+    except Exception as e:  # noqa: BLE001
+        ok.zero_()
+        note = "p2p unavailable (%s: %s); NCCL all-reduce" % (type(e).__name__, str(e)[:120])
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+        return None, None, note or "p2p unavailable on another rank; NCCL all-reduce"
+    return peer, make_bucket(peer), None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -98,20 +237,12 @@ def flat_grads(params):
     return torch.cat([p.grad.reshape(-1) for p in params])
 
 
-def run_ours(args):
+def measure_train(args, ctx: Ctx, clocks: ClockSampler) -> dict:
+    """The headline: C3-train, weak scaling (one view per rank per step). Returns the JSON line (a dict; on every rank)."""
     import torch.distributed as dist
-    from svgir_b200 import _lib, pipeline, shading
+    from svgir_b200 import _lib, pipeline
     from svgir_b200 import dist as svdist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()  # fail loudly if the extension is missing
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     # default: shade only the surfels that survive the rasteriser's culling (identical images and gradients,
     # tests/test_culled_shading_gpu.py); --shade-all shades every surfel in the reference's order
     pipeline.SHADE_CULLED = bool(args.shade_all)
@@ -126,33 +257,21 @@ def run_ours(args):
     cam_dev = [pipeline.camera_from_scene(c, dev) for c in cams]
     gt_dev = [torch.from_numpy(g).to(dev) for g in gts]
     params = pc.trainable() + [env]
-    # N>1: .grad of every parameter is a view into one flat buffer, reduced with ONE NCCL all-reduce
-    # per step (svgir_b200/dist.py); N=1 lets autograd hand over its gradient tensors.
-    # The bucket is laid out in two segments in the order the backward pass finishes them (rasteriser-side
-    # gradients, then shading-side ones); each segment's all-reduce is issued from inside the backward pass, so
-    # the first one travels over NVLink while the shading backward kernel is still running, and both are
-    # captured INSIDE the step's CUDA graph (--reduce post: one all-reduce after the graph instead).
+    # N>1: .grad of every parameter is a view into one flat buffer (svgir_b200/dist.py), laid out in two
+    # segments in the order the backward pass finishes them (rasteriser-side gradients, then shading-side ones).
+    #   p2p-overlap (default): the buffer lives in peer-mapped memory and svgir kernels sum it over NVLink INSIDE the
+    #       step's CUDA graph, the first segment on a side stream under the shading backward (csrc/peer_allreduce.cu)
+    #   p2p: one such kernel at the end of the step's graph;  post: one NCCL all-reduce after the graph;
+    #   overlap: NCCL, segment-wise inside the backward pass
     overlap = world > 1 and args.reduce == "overlap"
-    # --reduce p2p: the bucket lives in peer-mapped (symmetric) memory and ONE svgir kernel per rank sums it over
-    # NVLink at the end of the step's graph (csrc/peer_allreduce.cu); falls back to the NCCL all-reduce after the
-    # graph when the box cannot provide peer-mapped memory
-    peer, reduce_note = None, None
+    peer, bucket, reduce_note = None, None, None
     if world > 1 and args.reduce in ("p2p", "p2p-overlap"):
-        ok = torch.ones(1, device=dev)
-        try:
-            peer = svdist.PeerAllReduce(dev)
-            if args.reduce == "p2p":
-                bucket = svdist.FlatGradBucket(params, extra_floats=1, alloc=peer.allocate, reducer=peer.all_reduce)
-            else:   # rasteriser-side segment summed on a side stream under the shading backward
-                bucket = svdist.FlatGradBucket(params, segments=pipeline.reduce_segments(pc), extra_floats=1,
-                                               alloc=peer.allocate, segment_peer=peer)
-        except Exception as e:  # noqa: BLE001
-            ok.zero_()
-            reduce_note = "p2p unavailable (%s: %s); NCCL all-reduce after the step" % (type(e).__name__, str(e)[:120])
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) == 0.0:
-            peer, bucket = None, None
-            reduce_note = reduce_note or "p2p unavailable on another rank; NCCL all-reduce after the step"
+        if args.reduce == "p2p":
+            mk = lambda pr: svdist.FlatGradBucket(params, extra_floats=1, alloc=pr.allocate, reducer=pr.all_reduce)
+        else:
+            mk = lambda pr: svdist.FlatGradBucket(params, segments=pipeline.reduce_segments(pc), extra_floats=1,
+                                                  alloc=pr.allocate, segment_peer=pr)
+        peer, bucket, reduce_note = make_peer_bucket(ctx, mk)
     in_graph = overlap or peer is not None
     if peer is None:
         bg_group = svdist.background_group(args.bg_ctas) if overlap and args.bg_ctas > 0 else None
@@ -165,14 +284,14 @@ def run_ours(args):
     runner = None if args.eager else pipeline.GraphedTrainingStep(pc, env, bg, cam_dev[0], gt_dev[0], bucket=bucket,
                                                                          reduce_in_graph=in_graph)
 
-    def eager_step(i):
+    def eager_step(i, reduce=True):
         v = (i * world + rank) % N_VIEWS
         if bucket is None:
             return pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)])
         bucket.zero()
         loss, res = pipeline.training_step(cam_dev[v], pc, env, bg, gt_dev[i % len(gt_dev)], zero_grad=False,
-                                           overlap_bucket=bucket if in_graph else None)
-        if not in_graph:
+                                           overlap_bucket=bucket if (in_graph and reduce) else None)
+        if not in_graph and reduce:
             bucket.all_reduce()  # per-surfel gradient exchange over NVLink
         return loss, res
 
@@ -185,33 +304,25 @@ def run_ours(args):
             bucket.all_reduce()
         return loss, res
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     # ---- device-resident throughput (`value`) --------------------------------------------------
     for i in range(args.warmup):
         loss, res = step(i)
-    sync_all()
+    ctx.sync_all()
     stats = {"R": int(res["num_rendered"]), "P_vis": int(res["visibility_filter"].sum())}
     _lib.launch_count(reset=True)
     _lib.timing_collect(reset=True)
     if runner is None:
         _lib.timing_enable(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
+    ctx.sync_all()
+    clocks.mark(True)
     e0.record()
     for i in range(args.steps):
         loss, res = step(args.warmup + i)
     e1.record()
-    sync_all()
+    ctx.sync_all()
+    clocks.mark(False)
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() if runner is None else runner.launches_per_step * args.steps
     if runner is not None:
         # per-kernel device times: the same kernels on the same inputs launched one by one, each bracketed
@@ -225,11 +336,42 @@ def run_ours(args):
                                                   "preprocess_bwd", "emit", "sort_small", "tile_scan", "train_loss_fwd", "train_loss_bwd",
                                                   "peer_allreduce")}
     _lib.timing_collect(reset=True)
-    t_ms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
+    ms_max = ctx.max_ms(ms)
     value = world * args.steps / (ms_max / 1e3)
+
+    # ---- correctness of the in-graph gradient exchange (N>1) -----------------------------------------
+    # One step's LOCAL gradients (no exchange) are cloned and summed by NCCL; the same local gradients are then summed
+    # in place by the path the step graph uses (svgir peer-memory kernels segment by segment, or NCCL). Both sums see
+    # identical inputs, so the difference is association order only.
+    ar_check = None
+    if world > 1 and bucket is not None:
+        try:
+            eager_step(args.warmup, reduce=False)
+            ctx.sync_all()
+            want = bucket.flat.clone()
+            dist.all_reduce(want)
+            if bucket.segment_peer is not None:
+                nseg = len(bucket.seg_bounds)
+                for k, (lo, hi) in enumerate(bucket.seg_bounds):
+                    bucket.segment_peer.reduce_segment(k, lo, hi, last=(k == nseg - 1))
+                bucket.segment_peer.end_segments()
+            else:
+                bucket.all_reduce()
+            ctx.sync_all()
+            got = bucket.flat
+            scale = float(want.abs().max())
+            err = float((got - want).abs().max())
+            big = want.abs() > 1e-3 * scale
+            elem = float(((got - want).abs()[big] / want.abs()[big]).max()) if bool(big.any()) else 0.0
+            t = torch.tensor([err / max(scale, 1e-30), elem], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ar_check = {"max_rel_err": float(t[0]), "max_elem_rel_err": float(t[1]),
+                        "check": "one step's local gradients summed by the step's own exchange path vs an NCCL all-reduce of a "
+                                 "clone; max |diff| / max |sum| (and, for elements above 1e-3 of the max, the largest element-wise "
+                                 "relative difference), max over ranks"}
+            del want
+        except Exception as e:  # noqa: BLE001
+            ar_check = {"max_rel_err": None, "check_error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ----------------------------
     # A training iteration's INPUTS are the camera and the ground-truth image (the surfel parameters and the
@@ -257,6 +399,19 @@ def run_ours(args):
         if bucket is not None and not in_graph:
             bucket.all_reduce()
         return float(loss.item()), int(res["num_rendered"])  # D2H of the step's result
+
+    def e2e_pipelined(n):
+        """The same per-step copies and read-backs, but step k+1's inputs are uploaded on a copy stream into the
+        graph's second input slot while step k computes (GraphedTrainingStep.prefetch): what a data loader does."""
+        runner.prefetch(cam_host[rank % N_VIEWS], gt_host[0])
+        for i in range(n):
+            runner.replay_prefetched()
+            if i + 1 < n:
+                runner.prefetch(cam_host[((i + 1) * world + rank) % N_VIEWS], gt_host[(i + 1) % len(gt_host)])
+            if bucket is not None and not in_graph:
+                bucket.all_reduce()
+            R = runner.finish()
+            float(runner.loss.item()), int(R)
 
     host = {}
     for name, arr in (("xyz", cloud.means3D), ("opacity", cloud.opacity), ("scaling", cloud.scales),
@@ -288,249 +443,215 @@ def run_ours(args):
     def timed(fn, n):
         for i in range(2):
             fn(i)
-        sync_all()
+        ctx.sync_all()
         e0.record()
         for i in range(n):
             fn(2 + i)
         e1.record()
-        sync_all()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * n / (float(t.item()) / 1e3)
+        ctx.sync_all()
+        return world * n / (ctx.max_ms(e0.elapsed_time(e1)) / 1e3)
 
-    e2e_value = e2e_cold = None
+    e2e_value = e2e_cold = e2e_pipe = None
     if not args.no_e2e:
         e2e_value = timed(e2e_step, args.steps)
+        if runner is not None and hasattr(runner, "prefetch"):
+            e2e_pipelined(2)
+            ctx.sync_all()
+            e0.record()
+            e2e_pipelined(args.steps)
+            e1.record()
+            ctx.sync_all()
+            e2e_pipe = world * args.steps / (ctx.max_ms(e0.elapsed_time(e1)) / 1e3)
         e2e_cold = timed(cold_step, min(args.steps, 5))
 
-    if rank == 0:
-        pk, pk_src = peaks()
-        R, Pv = stats["R"], stats["P_vis"]
-        b_rec = 104 + 4 * S_FEAT + 4 * VS_FEAT
-        b_pix = 4 * (3 + 3 + 1 + 1 + S_FEAT + VS_FEAT // 4)
-        n_sh = P_SURFELS if args.shade_all else Pv
-        alg = {  # SURVEY.md 8(d) algorithmic bytes per launch, at this view's measured R / P_vis
-            "composite_bwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12) + Pv * 4 * (15 + S_FEAT + VS_FEAT),
-            "composite_fwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12),
-            "shade_fwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT),
-            "shade_bwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT) + n_sh * 4 * (12 + 4 + 12 + 3),
-        }
-        kt = {k: (v[0] / max(v[1], 1)) for k, v in ktimes.items()}  # avg ms per launch
-        dom = max(("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd"), key=lambda k: kt[k])
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(dom)
-        except Exception:
-            pass
-        achieved = alg[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
-        line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_step": world, "parallelism": f"view-dp{world}",
-                       "l2": "working set > L2 (per-sample light buffers 614 MB/iter)", "R": R, "P_vis": Pv,
-                       "shading": "all %d surfels (reference order)" % P_SURFELS if args.shade_all else
-                                  "the %d surfels that survive culling (preprocess runs first; images and gradients identical)" % Pv},
-            "clocks": clk,
-            "e2e": {"value": round(e2e_value, 3) if e2e_value else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": 12, "inputs": "camera matrices + ground-truth image from pinned host memory; loss + "
-                    "num_rendered read back; parameters / light buffers resident (optimiser state)"},
-            "e2e_cold": {"value": round(e2e_cold, 3) if e2e_cold else None, "unit": UNIT, "h2d_bytes_per_step": int(cold_bytes),
-                         "note": "worst case: every parameter and light buffer re-uploaded each step (eager path)"},
-            "loss_tail": "torch mirror of svgss.py:187-294 (~120 elementwise kernels)" if args.torch_loss else
-                         "fused resolve+loss kernels (csrc/resolve.cu), one per direction",
-            "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/step)" % runner.launches_per_step,
-            "kernel_timing": "CUDA events around each launch on the launching stream" + ("" if runner is None else
-                             ", separate eager pass of the same kernels/inputs right after the timed region"),
-            "gpu_launches": int(launches),
-            "grad_allreduce": None if bucket is None else {
-                "bytes": bucket.nbytes, "mode":
-                (("svgir_peer_allreduce over NVLink peer memory (%s), in the step's graph: " % (
-                    "NVSwitch multicast ld_reduce/st" if peer.multicast else "128-bit peer loads/stores")) +
-                 ("one kernel at the end of the step" if args.reduce == "p2p" else
-                  "rasteriser-side segment on a side stream (%d CTAs) under the shading backward, shading-side segment after it"
-                  % peer.BG_GRID)) if peer is not None else
-                (("2 segments issued inside the backward pass, captured in the step's graph; the overlapped one on a "
-                  "%d-CTA communicator" % args.bg_ctas if args.bg_ctas > 0 else
-                  "2 segments issued inside the backward pass, captured in the step's graph") if overlap else
-                 "one NCCL all-reduce after the step"), "note": reduce_note},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
-                         "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
-                         "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
-            "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
-            # the same per-launch event times grouped by stage: svgss rasteriser forward+backward alone (BASELINE.json
-            # configs[1]'s shape), the render_equation shading, the resolve+loss tail
-            "stage_ms": {
-                "svgss_fwd_bwd": round(sum(kt[k] for k in ("preprocess", "tile_scan", "emit", "sort_small", "composite_fwd",
-                                                           "composite_bwd", "preprocess_bwd")) + kt["tile_scan"], 4),
-                "render_equation_fwd_bwd": round(kt["shade_fwd"] + kt["shade_bwd"], 4),
-                "loss_tail": round(kt["train_loss_fwd"] + kt["train_loss_bwd"], 4)},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_sample(1, 0)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # drop the captured graph before the communicator goes away; with collectives captured INSIDE the graph
-        # (--reduce overlap) NCCL's teardown was seen to block (gpurun_out/s2), so that mode leaves without it
-        runner = None
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        if in_graph:
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+    pk, pk_src = peaks()
+    R, Pv = stats["R"], stats["P_vis"]
+    b_rec = 104 + 4 * S_FEAT + 4 * VS_FEAT
+    b_pix = 4 * (3 + 3 + 1 + 1 + S_FEAT + VS_FEAT // 4)
+    n_sh = P_SURFELS if args.shade_all else Pv
+    alg = {  # SURVEY.md 8(d) algorithmic bytes per launch, at this view's measured R / P_vis
+        "composite_bwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12) + Pv * 4 * (15 + S_FEAT + VS_FEAT),
+        "composite_fwd": R * b_rec + WIDTH * HEIGHT * (b_pix + 12),
+        "shade_fwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT),
+        "shade_bwd": n_sh * (NS * 32 + 124) + n_sh * 4 * (12 * 5 + S_FEAT) + n_sh * 4 * (12 + 4 + 12 + 3),
+    }
+    kt = {k: (v[0] / max(v[1], 1)) for k, v in ktimes.items()}  # avg ms per launch
+    dom = max(("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd"), key=lambda k: kt[k])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    achieved = alg[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
+    # the pipelined host-input leg is the end-to-end number when it ran (same bytes copied and read back per step)
+    e2e_best = max([v for v in (e2e_value, e2e_pipe) if v] or [0.0]) or None
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(world),
+        "workload_stats": {"R": R, "P_vis": Pv,
+                           "shading": "all %d surfels (reference order)" % P_SURFELS if args.shade_all else
+                           "the %d surfels that survive culling (preprocess runs first; images and gradients identical)" % Pv},
+        "clocks": None,
+        "e2e": {"value": round(e2e_best, 3) if e2e_best else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": 12, "inputs": "camera matrices + ground-truth image from pinned host memory; loss + "
+                "num_rendered read back; parameters / light buffers resident (optimiser state)",
+                "in_line": round(e2e_value, 3) if e2e_value else None,
+                "prefetched": round(e2e_pipe, 3) if e2e_pipe else None,
+                "note": "in_line: the step's inputs are copied right before its replay; prefetched: step k+1's inputs are "
+                        "uploaded on a copy stream while step k computes (same bytes, same per-step read-back); value = the better"},
+        "e2e_cold": {"value": round(e2e_cold, 3) if e2e_cold else None, "unit": UNIT, "h2d_bytes_per_step": int(cold_bytes),
+                     "note": "worst case: every parameter and light buffer re-uploaded each step (eager path)"},
+        "loss_tail": "torch mirror of svgss.py:187-294 (~120 elementwise kernels)" if args.torch_loss else
+                     "fused resolve+loss kernels (csrc/resolve.cu), one per direction",
+        "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/step)" % runner.launches_per_step,
+        "kernel_timing": "CUDA events around each launch on the launching stream" + ("" if runner is None else
+                         ", separate eager pass of the same kernels/inputs right after the timed region"),
+        "gpu_launches": int(launches),
+        "grad_allreduce": None if bucket is None else dict({
+            "bytes": bucket.nbytes, "mode":
+            (("svgir_peer_allreduce over NVLink peer memory (%s), in the step's graph: " % (
+                "NVSwitch multicast ld_reduce/st" if peer.multicast else "128-bit peer loads/stores")) +
+             ("one kernel at the end of the step" if args.reduce == "p2p" else
+              "rasteriser-side segment on a side stream (%d CTAs) under the shading backward, shading-side segment after it"
+              % peer.BG_GRID)) if peer is not None else
+            (("2 segments issued inside the backward pass, captured in the step's graph; the overlapped one on a "
+              "%d-CTA communicator" % args.bg_ctas if args.bg_ctas > 0 else
+              "2 segments issued inside the backward pass, captured in the step's graph") if overlap else
+             "one NCCL all-reduce after the step"), "note": reduce_note}, **(ar_check or {})),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+                     "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
+                     "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
+        "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
+        # the same per-launch event times grouped by stage: svgss rasteriser forward+backward alone (BASELINE.json
+        # configs[1]'s shape), the render_equation shading, the resolve+loss tail
+        "stage_ms": {
+            "svgss_fwd_bwd": round(sum(kt[k] for k in ("preprocess", "tile_scan", "emit", "sort_small", "composite_fwd",
+                                                       "composite_bwd", "preprocess_bwd")) + kt["tile_scan"], 4),
+            "render_equation_fwd_bwd": round(kt["shade_fwd"] + kt["shade_bwd"], 4),
+            "loss_tail": round(kt["train_loss_fwd"] + kt["train_loss_bwd"], 4)},
+    }
+    # release the workload before the extra configurations run
+    runner = None
+    del pc, env, cam_dev, gt_dev, params, bucket, peer, host, gt_host
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
-def run_c4(args):
+def measure_c4(args, ctx: Ctx, steps: int, warmup: int) -> dict:
     """C4 (BASELINE.json configs[3]): multi-view data-parallel training -- 1M SV surfels, 8 views of 800x800 per step,
-    sharded over the ranks by view (rank r renders views r, r+N, ...; strong scaling: the step's work is fixed). Every
+    sharded over the ranks by view (rank r renders views r, r+N, ...; STRONG scaling: the step's work is fixed). Every
     rank replays ONE captured step graph per local view, accumulating into its flat gradient bucket (zero_in_graph=
     False), then the buckets are summed once: by the svgir peer-memory kernel (default) or NCCL (--reduce post).
-    value = view-iterations per second = 8 x steps / time. Not part of the driver's default run."""
-    import torch.distributed as dist
+    value = view-iterations per second = 8 x steps / time."""
     from svgir_b200 import _lib, pipeline, scene
     from svgir_b200 import dist as svdist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     pipeline.SHADE_CULLED = bool(args.shade_all)
     pipeline.FUSED_LOSS = not args.torch_loss
     P, V = 1_000_000, 8
     cloud = scene.make_surfels(P, seed=1238)
-    mats = scene.make_materials(cloud, NS, seed=1239)
+    mats = scene.make_materials_torch(cloud, NS, 1239, dev)   # 2 GB of per-sample buffers: generated on the device
     pc = pipeline.model_from_scene(cloud, mats, dev)
-    env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+    env = mats["env_param"].clone().requires_grad_(True)
     bg = torch.zeros(3, device=dev)
     cams = [pipeline.camera_from_scene(scene.look_at_camera(WIDTH, HEIGHT, v, V), dev) for v in range(V)]
-    rng = np.random.default_rng(1240)
-    gts = [torch.from_numpy(rng.uniform(0, 1, (3, HEIGHT, WIDTH)).astype(np.float32)).to(dev) for _ in range(2)]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1240)
+    gts = [torch.rand((3, HEIGHT, WIDTH), generator=g, device=dev) for _ in range(2)]
     params = pc.trainable() + [env]
     mine = svdist.views_for_rank(V, rank, world)
 
-    peer, note = None, None
+    peer, bucket, note = None, None, None
     if world > 1 and args.reduce != "post":
-        ok = torch.ones(1, device=dev)
-        try:
-            peer = svdist.PeerAllReduce(dev)
-            bucket = svdist.FlatGradBucket(params, alloc=peer.allocate, reducer=peer.all_reduce)
-        except Exception as e:  # noqa: BLE001
-            ok.zero_()
-            note = "p2p unavailable (%s: %s); NCCL all-reduce" % (type(e).__name__, str(e)[:120])
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) == 0.0:
-            peer = None
-            note = note or "p2p unavailable on another rank; NCCL all-reduce"
-    if peer is None:
+        peer, bucket, note = make_peer_bucket(
+            ctx, lambda pr: svdist.FlatGradBucket(params, alloc=pr.allocate, reducer=pr.all_reduce))
+    if bucket is None:
         bucket = svdist.FlatGradBucket(params)
     runner = pipeline.GraphedTrainingStep(pc, env, bg, cams[0], gts[0], bucket=bucket, zero_in_graph=False)
 
     def step(i):
         bucket.zero()
         R = 0
+        loss = None
         for v in mine:
             loss, res = runner(cams[v], gts[(i + v) % 2])
             R += int(res["num_rendered"])
         bucket.all_reduce()   # one exchange per step (no-op at N=1)
         return loss, R
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         loss, R = step(i)
-    sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    ctx.sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
     e0.record()
-    for i in range(args.steps):
-        loss, R = step(args.warmup + i)
+    for i in range(steps):
+        loss, R = step(warmup + i)
     e1.record()
-    sync_all()
-    clk = clocks.stop() if rank == 0 else None
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ctx.sync_all()
+    ms = ctx.max_ms(e0.elapsed_time(e1))
+    # the exchange alone (all ranks enter together): bucket bytes / time
+    ar_ms = None
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+        ctx.sync_all()
+        e0.record()
+        for _ in range(5):
+            bucket.all_reduce()
+        e1.record()
+        ctx.sync_all()
+        ar_ms = ctx.max_ms(e0.elapsed_time(e1)) / 5
     # per-kernel times of one local view, launched eagerly
-    _lib.timing_collect(reset=True)
-    _lib.timing_enable(True)
-    bucket.zero()
-    pipeline.training_step(cams[mine[0]], pc, env, bg, gts[0], zero_grad=False)
-    torch.cuda.synchronize()
-    _lib.timing_enable(False)
     kt = {}
-    for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess", "preprocess_bwd", "emit", "sort_small"):
-        t, n = _lib.timing_collect(k)
-        kt[k] = round(t / max(n, 1), 4)
-    _lib.timing_collect(reset=True)
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": round(V * args.steps / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4: multi-view data-parallel stage-2 training, %dk SV surfels, %d views of %dx%d per step, Ns=%d, "
-                                   "S=%d, VS=%d" % (P // 1000, V, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT),
-                       "views_per_step": V, "views_per_rank": len(mine), "parallelism": f"view-dp{world}",
-                       "l2": "working set > L2 (per-sample light buffers 2 GB/view)", "R_last_step_local": R},
-            "clocks": clk, "gpu_launches": int(runner.launches_per_step * len(mine) * args.steps + (args.steps if peer is not None else 0)),
-            "grad_allreduce": None if world == 1 else {"bytes": bucket.nbytes, "mode": "svgir_peer_allreduce after the local views"
-                                                       if peer is not None else "one NCCL all-reduce after the local views", "note": note},
-            "kernels_ms": kt}), flush=True)
-    if world > 1:
-        runner = None
+    if mine:
+        _lib.timing_collect(reset=True)
+        _lib.timing_enable(True)
+        bucket.zero()
+        pipeline.training_step(cams[mine[0]], pc, env, bg, gts[0], zero_grad=False)
         torch.cuda.synchronize()
-        dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        _lib.timing_enable(False)
+        for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess", "preprocess_bwd", "emit", "sort_small"):
+            t, n = _lib.timing_collect(k)
+            kt[k] = round(t / max(n, 1), 4)
+        _lib.timing_collect(reset=True)
+    out = {
+        "metric": METRIC, "value": round(V * steps / (ms / 1e3), 3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms / steps, 4), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: multi-view data-parallel stage-2 training, %dk SV surfels, %d views of %dx%d per step, Ns=%d, "
+                               "S=%d, VS=%d" % (P // 1000, V, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT),
+                   "views_per_step": V, "views_per_rank": len(mine), "parallelism": f"view-dp{world}",
+                   "l2": "working set > L2 (per-sample light buffers 2 GB/view)"},
+        "R_last_step_local": R,
+        "gpu_launches": int(runner.launches_per_step * len(mine) * steps + (steps if peer is not None else 0)),
+        "grad_allreduce": None if world == 1 else {"bytes": bucket.nbytes, "ms": None if ar_ms is None else round(ar_ms, 4),
+                                                   "mode": "svgir_peer_allreduce after the local views"
+                                                   if peer is not None else "one NCCL all-reduce after the local views", "note": note},
+        "kernels_ms": kt}
+    runner = None
+    del pc, env, params, bucket, peer, mats
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
-def run_relight(args):
+def measure_relight(args, ctx: Ctx, steps: int, warmup: int, clocks: ClockSampler = None) -> dict:
     """C3-eval (BASELINE.json configs[2]): relighting frame = render_equation over all 300k surfels with
     Ns=384 samples under a fixed HDR env map (EnvLight semantics, scene/envmap.py:54-72) + svgss forward
     with the eval G-buffer (S=7, VS=64) at 800x800. Forward only; reports ms/frame. Under torchrun the
     view x envmap grid is sharded round-robin with no collective."""
-    import torch.distributed as dist
     from svgir_b200 import _lib, pipeline, scene, shading
     from svgir_b200 import dist as svdist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the svgir_b200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     pipeline.SHADE_CULLED = bool(args.shade_all)
-    # default: the resolve + loss tail is one fused kernel per direction (svgir_b200.losses); --torch-loss runs the torch
-    # mirror of the reference's tail instead (same loss and gradients, tests/test_fused_loss_gpu.py)
     pipeline.FUSED_LOSS = not args.torch_loss
     ns, n_env = 384, 5
     cloud = scene.make_surfels(P_SURFELS, seed=1236)
-    mats = scene.make_materials(cloud, ns, seed=1237)
+    mats = scene.make_materials_torch(cloud, ns, 1237, dev)   # 3.7 GB of per-sample buffers: generated on the device
     pc = pipeline.model_from_scene(cloud, mats, dev, requires_grad=False)
     cams = [pipeline.camera_from_scene(scene.look_at_camera(WIDTH, HEIGHT, v, N_VIEWS), dev) for v in range(N_VIEWS)]
     rng = np.random.default_rng(7)
@@ -554,33 +675,29 @@ def run_relight(args):
         e, v = grid[i % len(grid)]
         return runner(cams[v], envs[e])
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         res = frame(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ctx.sync_all()
     _lib.launch_count(reset=True)
     _lib.timing_collect(reset=True)
     if runner is None:
         _lib.timing_enable(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if clocks is not None:
+        clocks.mark(True)
     e0.record()
-    for i in range(args.steps):
-        res = frame(args.warmup + i)
+    for i in range(steps):
+        res = frame(warmup + i)
     e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clk = clocks.stop() if rank == 0 else None
-    launches = _lib.launch_count() if runner is None else runner.launches_per_frame * args.steps
+    ctx.sync_all()
+    if clocks is not None:
+        clocks.mark(False)
+    launches = _lib.launch_count() if runner is None else runner.launches_per_frame * steps
     if runner is not None:   # per-kernel times: the same frames launched eagerly, each launch bracketed by events
         _lib.timing_enable(True)
-        for i in range(min(args.steps, 5)):
-            eager_frame(args.warmup + i)
+        for i in range(min(steps, 5)):
+            eager_frame(warmup + i)
         torch.cuda.synchronize()
     _lib.timing_enable(False)
     kt = {}
@@ -588,10 +705,7 @@ def run_relight(args):
         t, n = _lib.timing_collect(k)
         kt[k] = t / max(n, 1)
     _lib.timing_collect(reset=True)
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_frame = float(t_ms.item()) / args.steps
+    ms_frame = ctx.max_ms(e0.elapsed_time(e1)) / steps
 
     # end to end: camera block + env map from pinned host memory every frame, the relit image read back to pinned
     # host memory (what eval_relighting_tensoIR.py:331-340 saves)
@@ -619,46 +733,118 @@ def run_relight(args):
 
         for i in range(2):
             e2e_frame(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        ctx.sync_all()
         e0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             e2e_frame(2 + i)
         e1.record()
-        torch.cuda.synchronize()
-        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t2.item()) / args.steps
+        ctx.sync_all()
+        e2e_ms = ctx.max_ms(e0.elapsed_time(e1)) / steps
         e2e_h2d = cam_host[0].block.numel() * 4 + env_host[0].numel() * 4
         e2e_d2h = img_host.numel() * 4
-    if rank == 0:
-        pk, pk_src = peaks()
-        # shading runs on the surfels that survive the rasteriser's culling unless --shade-all
-        n_sh = P_SURFELS if args.shade_all else int(res["visibility_filter"].sum())
-        alg = n_sh * (ns * 32 + 124) + n_sh * 4 * (12 * 5 + 7)
-        ach = alg / (kt["shade_fwd"] * 1e-3) / 1e9 if kt["shade_fwd"] > 0 else 0.0
-        print(json.dumps({
-            "metric": "relight ms/frame", "value": round(ms_frame / world, 4), "unit": "ms/frame", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_frame, 4), "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3-eval: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
-                                   "S=7/VS=64 at %dx%d, fixed HDR env map" % (ns, P_SURFELS // 1000, WIDTH, HEIGHT),
-                       "grid": "%d views x %d env maps, round-robin over ranks" % (N_VIEWS, n_env),
-                       "l2": "working set > L2 (light buffers 3.7 GB/frame)", "R": int(res["num_rendered"]),
-                       "surfels_shaded": n_sh},
-            "clocks": clk, "gpu_launches": int(launches),
-            "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/frame)" % runner.launches_per_frame,
-            "e2e": None if e2e_ms is None else {"value": round(e2e_ms / world, 4), "unit": "ms/frame", "h2d_bytes_per_step": int(e2e_h2d),
-                                                "d2h_bytes_per_step": int(e2e_d2h),
-                                                "inputs": "camera block + env map from pinned host memory; relit image read back"},
-            "roofline": {"bound": "hbm", "kernel": "shade_fwd", "achieved": round(ach, 1), "peak": pk["hbm_gbs"],
-                         "peak_source": pk_src, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
-                         "algorithmic_bytes": int(alg), "avg_ms": round(kt["shade_fwd"], 4)},
-            "kernels_ms": {k: round(v, 4) for k, v in kt.items()}}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    pk, pk_src = peaks()
+    # shading runs on the surfels that survive the rasteriser's culling unless --shade-all
+    n_sh = P_SURFELS if args.shade_all else int(res["visibility_filter"].sum())
+    alg = n_sh * (ns * 32 + 124) + n_sh * 4 * (12 * 5 + 7)
+    ach = alg / (kt["shade_fwd"] * 1e-3) / 1e9 if kt["shade_fwd"] > 0 else 0.0
+    out = {
+        "metric": "relight ms/frame", "value": round(ms_frame / world, 4), "unit": "ms/frame", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_frame, 4), "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3-eval: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
+                               "S=7/VS=64 at %dx%d, fixed HDR env map" % (ns, P_SURFELS // 1000, WIDTH, HEIGHT),
+                   "grid": "%d views x %d env maps, round-robin over ranks" % (N_VIEWS, n_env),
+                   "l2": "working set > L2 (light buffers 3.7 GB/frame)"},
+        "workload_stats": {"R": int(res["num_rendered"]), "surfels_shaded": n_sh},
+        "gpu_launches": int(launches),
+        "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/frame)" % runner.launches_per_frame,
+        "e2e": None if e2e_ms is None else {"value": round(e2e_ms / world, 4), "unit": "ms/frame", "h2d_bytes_per_step": int(e2e_h2d),
+                                            "d2h_bytes_per_step": int(e2e_d2h),
+                                            "inputs": "camera block + env map from pinned host memory; relit image read back"},
+        "roofline": {"bound": "hbm", "kernel": "shade_fwd", "achieved": round(ach, 1), "peak": pk["hbm_gbs"],
+                     "peak_source": pk_src, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None,
+                     "algorithmic_bytes": int(alg), "avg_ms": round(kt["shade_fwd"], 4)},
+        "kernels_ms": {k: round(v, 4) for k, v in kt.items()}}
+    runner = None
+    del pc, mats
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def measure_visibility(args, ctx: Ctx, reps: int = 5) -> dict:
+    """Visibility precompute (BASELINE.md 'R-bvh'): LBVH build over 300k surfels + one opacity ray per
+    (surfel, incident sample) for Ns = 64 (300k surfels) and Ns = 384 (100k surfels, one eval chunk), our kernels
+    (csrc/bvh.cu) beside the reference's (submodules/bvh/src/{construct,trace}.cu compiled into
+    oracle/_ref/libbvh_ref.so) on the same inputs. Only the reference leg touches oracle/."""
+    from svgir_b200 import bvh as svbvh, scene
+    dev = ctx.dev
+    cloud = scene.make_surfels(P_SURFELS, seed=1234)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    means, scales, rots, opac = d(cloud.means3D), d(cloud.scales), d(cloud.rotations), d(cloud.opacity)
+    normals = d(cloud.normals)
+    # Sigma^-1 = (R diag(1/s)) (R diag(1/s))^T, upper triangle (gaussian_model.py:379-382)
+    q = rots / rots.norm(dim=-1, keepdim=True)
+    r, x, y, z = q.unbind(-1)
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                      2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                      2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+    Lm = Rm * (1.0 / scales)[:, None, :]
+    Mi = Lm @ Lm.transpose(1, 2)
+    symm_inv = torch.stack([Mi[:, 0, 0], Mi[:, 0, 1], Mi[:, 0, 2], Mi[:, 1, 1], Mi[:, 1, 2], Mi[:, 2, 2]], -1).contiguous()
+    RefBvh = None
+    try:
+        from oracle import ref_cuda
+        if ref_cuda.available("bvh"):
+            RefBvh = ref_cuda.RefBvh
+    except Exception:
+        RefBvh = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, n):
+        r = fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    out = {"surfels": P_SURFELS, "note": "CUDA events, resident inputs, mean of %d repetitions after one warm-up; build = leaf "
+                                          "boxes + construct_bvh (submodules/bvh/__init__.py:29-60), trace = trace_bvh_opacity with "
+                                          "the application's 0.05 origin offset (:62-71)" % reps}
+    nodes0, aabbs0 = svbvh.leaf_aabbs(means, scales, rots)
+
+    def build_ours():
+        n_, a_ = svbvh.leaf_aabbs(means, scales, rots)
+        return svbvh.Bvh(n_, a_)
+
+    build_ms, tree = timeit(build_ours, reps)
+    out["build_ms"] = round(build_ms, 4)
+    rtree = None
+    if RefBvh is not None:
+        rb, rtree = timeit(lambda: RefBvh(nodes0, aabbs0, means, scales, rots), reps)
+        out["reference_build_ms"] = round(rb, 4)
+        out["build_speedup"] = round(rb / build_ms, 2)
+    for ns in (64, 384):
+        n_s = 100_000 if ns == 384 else P_SURFELS
+        dirs_np, _ = scene.fibonacci_hemisphere_dirs(cloud.normals[:n_s], ns)
+        dirs = torch.from_numpy(dirs_np).to(dev)
+        orig = (means[:n_s, None, :] + 0.05 * dirs).contiguous()
+        t_ms, (_, vis) = timeit(lambda: tree.trace_opacity(orig, dirs, means, symm_inv, opac, normals), reps)
+        key = "trace_ns%d" % ns
+        nr = n_s * ns
+        out[key] = {"rays": nr, "ms": round(t_ms, 4), "mrays_per_s": round(nr / t_ms / 1e3, 1)}
+        if rtree is not None:
+            r_ms, (_, rvis) = timeit(lambda: rtree.trace_opacity(orig, dirs, means, symm_inv, opac, normals), max(reps // 2, 1))
+            out[key]["reference_ms"] = round(r_ms, 4)
+            out[key]["speedup"] = round(r_ms / t_ms, 2)
+            out[key]["max_abs_diff"] = float((vis.reshape(-1) - rvis.reshape(-1)).abs().max())
+        del dirs, orig
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -672,80 +858,75 @@ def _ref_inputs():
 
 
 def reference_cpu_step(view: int) -> float:
-    """One BOUNDED SAMPLE of the workload on the host CPU with the oracle: full preprocess + binning,
-    compositing fwd+bwd of every 4th tile row/column (1/16 of the tiles), shading fwd+bwd of every
-    16th surfel. Returns seconds."""
+    """One FULL step of the workload on the host CPU with the oracle: shading fwd+bwd of every surfel (the reference's
+    order: all surfels are shaded), preprocess + binning + compositing fwd+bwd of every tile. Returns seconds."""
     from oracle import svgss as O, shading_oracle as SO
     cloud, mats, cams, gts = _ref_inputs()
     cam = cams[view % N_VIEWS]
     t0 = time.perf_counter()
-    sl = slice(view % 16, None, 16)
-    tt = {k: torch.from_numpy(np.ascontiguousarray(mats[k][sl])) for k in
+    tt = {k: torch.from_numpy(mats[k]) for k in
           ("base_color", "roughness", "shading_normals", "radiance", "visibility", "incident_dirs", "incident_areas")}
     envp = torch.from_numpy(mats["env_param"]).requires_grad_(True)
     for k in ("base_color", "roughness", "shading_normals"):
-        tt[k].requires_grad_(True)
-    vd = torch.from_numpy(cam.campos[None] - cloud.means3D[sl])
+        tt[k] = tt[k].clone().requires_grad_(True)
+    vd = torch.from_numpy(cam.campos[None] - cloud.means3D)
     vd = torch.nn.functional.normalize(vd, dim=-1)
     pbr, extra = SO.rendering_equation4(tt["base_color"], tt["roughness"], tt["shading_normals"], vd, tt["radiance"],
                                         lambda d: SO.direct_light_learnable(envp, d), tt["visibility"],
                                         tt["incident_dirs"], tt["incident_areas"])
     feats, vfeats = SO.pack_features(pbr, extra, tt["base_color"], tt["roughness"], tt["shading_normals"],
                                      torch.from_numpy(cam.viewmatrix[:3, :3].copy()), True)
-    (vfeats.sum() + feats.sum()).backward()
-    # rasteriser: features of the un-shaded surfels do not change its cost
-    rng = np.random.default_rng(view)
-    f = rng.uniform(0, 1, (P_SURFELS, S_FEAT)).astype(np.float32)
-    vf = rng.uniform(0, 1, (P_SURFELS, VS_FEAT)).astype(np.float32)
-    O.lib().oracle_set_tile_step(REF_TILE_STEP)
-    try:
-        fw = O.forward(cam, cloud.means3D, cloud.opacity, cloud.scales, cloud.rotations, f, vf, shs=cloud.shs)
-        g = [np.full(fw[k].shape, 1.0 / (HEIGHT * WIDTH), np.float32) for k in
-             ("color", "normal_img", "depth", "opacity", "feature", "vfeature")]
-        O.backward(fw, *g)
-    finally:
-        O.lib().oracle_set_tile_step(1)
+    f = np.ascontiguousarray(feats.detach().numpy())
+    vf = np.ascontiguousarray(vfeats.detach().numpy())
+    O.lib().oracle_set_tile_step(1)
+    fw = O.forward(cam, cloud.means3D, cloud.opacity, cloud.scales, cloud.rotations, f, vf, shs=cloud.shs)
+    g = [np.full(fw[k].shape, 1.0 / (HEIGHT * WIDTH), np.float32) for k in
+         ("color", "normal_img", "depth", "opacity", "feature", "vfeature")]
+    bw = O.backward(fw, *g)
+    # `features` (mean visibility / mean cached radiance) carry no trainable input: the gradient flows through vfeatures
+    torch.autograd.backward([vfeats],
+                            [torch.from_numpy(np.ascontiguousarray(bw["dL_dvfeatures"], dtype=np.float32).reshape(vfeats.shape))])
     return time.perf_counter() - t0
 
 
-def cpu_reference_sample(steps: int, warmup: int) -> dict:
+def cpu_reference_run(steps: int, warmup: int) -> dict:
     torch.set_num_threads(os.cpu_count() or 1)
     for i in range(warmup):
         reference_cpu_step(i)
     ts = [reference_cpu_step(warmup + i) for i in range(steps)]
-    frac = 1.0 / (REF_TILE_STEP * REF_TILE_STEP)
     t = float(np.mean(ts))
-    return {"value": round(frac / t, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": ("oracle (C + torch-CPU restatement of the reference path) on 1/%d of the step: all %dk surfels "
-                       "preprocessed+binned, every %dth tile row/col composited fwd+bwd, every 16th surfel shaded fwd+bwd; "
-                       "%.2f s per sample, value = sample fraction / time" % (REF_TILE_STEP ** 2, P_SURFELS // 1000,
-                                                                               REF_TILE_STEP, t)),
-            "sample_seconds": round(t, 3)}
+    return {"value": round(1.0 / t, 6), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": ("oracle (C + torch-CPU restatement of the reference path): %d FULL step(s) of the workload -- all %dk surfels "
+                       "shaded fwd+bwd (torch CPU, all threads), preprocessed and binned, every tile composited fwd+bwd (C, OpenMP); "
+                       "%.2f s per step" % (steps, P_SURFELS // 1000, t)),
+            "step_seconds": round(t, 3)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_sample(args.steps, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cb = cpu_reference_run(args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["sample_seconds"] * 1e3, 2),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["step_seconds"] * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
+            "config": train_config(world), "cpu_baseline": cb,
+            "note": "rank 0 only: one view per step on the host CPU, every step a full step; warm-up capped at 1 step",
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_reference_cuda(args):
-    """Extra arm: the reference's own CUDA rasteriser (oracle/_ref, unmodified sources) plus the
-    reference's torch shading graph, both on this GPU (BASELINE.md 'R-step')."""
+def measure_reference_cuda(steps: int, warmup: int) -> dict:
+    """The reference's own CUDA rasteriser (oracle/_ref, unmodified sources, sm_100 build) plus the torch shading graph of
+    the reference (its restatement oracle/shading_oracle.py, pinned to goldens from the reference's rendering_equation4:
+    /root/reference is not on the GPU box), both on this GPU (BASELINE.md 'R-step'): the denominator of the >=8x target."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import ref_cuda, shading_oracle as SO
     if not (torch.cuda.is_available() and ref_cuda.available()):
-        print(json.dumps({"impl": "reference_cuda", "unavailable": "needs a GPU and oracle/_ref/libsvgss_ref.so"}))
-        return
-    dev = torch.device("cuda:0")
-    cloud, mats, cams, gts = build_host_workload()
+        return {"impl": "reference_cuda", "unavailable": "needs a GPU and oracle/_ref/libsvgss_ref.so"}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cloud, mats, cams, gts = _ref_inputs()
     d = lambda a: torch.from_numpy(a).to(dev)
     t = {k: d(v) for k, v in mats.items()}
     geo = dict(means3D=d(cloud.means3D), opacity=d(cloud.opacity), scales=d(cloud.scales), rotations=d(cloud.rotations),
@@ -777,20 +958,120 @@ def run_reference_cuda(args):
         g = r.backward(*gpix)
         torch.autograd.backward([vfeats], [g["dL_dvfeatures"]])
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"impl": "reference_cuda", "metric": METRIC, "value": round(args.steps / (ms / 1e3), 3), "unit": UNIT,
-                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-                      "config": {"workload": WORKLOAD}, "note": "reference CUDA rasteriser (sm_100 build of the unmodified "
-                      "sources) + reference torch shading graph on the same B200"}), flush=True)
+    out = {"impl": "reference_cuda", "metric": METRIC, "value": round(steps / (ms / 1e3), 3), "unit": UNIT,
+           "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3),
+           "config": {"workload": WORKLOAD}, "note": "reference CUDA rasteriser (sm_100 build of the unmodified sources, "
+           "oracle/_ref/libsvgss_ref.so) + the torch restatement of the reference's shading graph (oracle/shading_oracle.py; "
+           "the reference Python cannot travel to the GPU box) on the same B200, same inputs as the headline"}
+    del t, geo, r
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def finish_process(ctx: Ctx):
+    """Leave without tearing NCCL down: with collectives / peer kernels captured in CUDA graphs the communicator's
+    destructor was seen to block (gpurun_out/s2)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if ctx.world > 1:
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        os._exit(0)
+
+
+def run_ours(args):
+    ctx = Ctx()
+    clocks = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        clocks.start()   # before the warm-up, so that samples exist by the time the (short) timed region runs
+    line = measure_train(args, ctx, clocks)
+    if ctx.rank == 0:
+        line["clocks"] = clocks.stop()
+
+    printed = threading.Event()
+
+    def emit():
+        if not printed.is_set():
+            printed.set()
+            if ctx.rank == 0:
+                print(json.dumps(line), flush=True)
+
+    def watchdog():
+        line["extras_error"] = "an extra workload did not finish within %d s; the headline is unaffected" % EXTRAS_DEADLINE_S
+        emit()
+        os._exit(0)
+
+    if not args.no_extras:
+        timer = threading.Timer(EXTRAS_DEADLINE_S, watchdog)
+        timer.daemon = True
+        timer.start()
+
+        def extra(name, fn):
+            t0 = time.perf_counter()
+            try:
+                r = fn()
+            except Exception as e:  # noqa: BLE001
+                r = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if isinstance(r, dict):
+                r["wall_s"] = round(time.perf_counter() - t0, 1)
+            line[name] = r
+
+        # every N: C4 (1M surfels, 8 views/step, strong scaling) so that its efficiency can be read from the scaling run
+        extra("c4", lambda: {k: v for k, v in measure_c4(args, ctx, steps=5, warmup=3).items()
+                             if k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "grad_allreduce",
+                                      "kernels_ms", "gpu_launches", "R_last_step_local")})
+        if ctx.world == 1:
+            extra("relight", lambda: {k: v for k, v in measure_relight(args, ctx, steps=10, warmup=3).items()
+                                      if k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "workload_stats", "e2e",
+                                               "roofline", "kernels_ms", "launch_mode")})
+            extra("visibility", lambda: measure_visibility(args, ctx))
+
+            def refcuda():
+                r = measure_reference_cuda(steps=5, warmup=2)
+                if r.get("value"):
+                    r["ratio"] = round(line["value"] / r["value"], 2)
+                    if line["e2e"]["value"]:
+                        r["e2e_ratio"] = round(line["e2e"]["value"] / r["value"], 2)
+                return r
+            extra("reference_cuda", refcuda)
+        timer.cancel()
+    if ctx.world == 1 and not args.no_cpu_baseline and ctx.rank == 0:
+        line["cpu_baseline"] = cpu_reference_run(2, 0)
+    emit()
+    finish_process(ctx)
+
+
+def run_workload(args):
+    ctx = Ctx()
+    clocks = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        clocks.start()
+    if args.workload == "relight":
+        out = measure_relight(args, ctx, args.steps, args.warmup, clocks)
+    elif args.workload == "c4":
+        clocks.mark(True)
+        out = measure_c4(args, ctx, args.steps, args.warmup)
+        clocks.mark(False)
+    else:
+        out = {"metric": "visibility precompute (LBVH build + opacity trace)", "n_gpus": 1, "visibility": measure_visibility(args, ctx)}
+    if ctx.rank == 0:
+        out["clocks"] = clocks.stop()
+        print(json.dumps(out), flush=True)
+    finish_process(ctx)
 
 
 def main():
@@ -801,32 +1082,33 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys of the default line (c4, relight, visibility, "
+                    "reference_cuda)")
     ap.add_argument("--shade-all", action="store_true", help="shade culled surfels too (reference order: shading before the rasteriser)")
     ap.add_argument("--torch-loss", action="store_true", help="resolve + loss tail in torch (the reference's ~120 kernels) instead of the fused kernels")
     ap.add_argument("--reduce", default="p2p-overlap", choices=["overlap", "post", "p2p", "p2p-overlap"],
                     help="N>1 gradient exchange. p2p-overlap (default): svgir kernels over NVLink peer memory inside the step's graph, "
-                         "the rasteriser-side segment on a side stream under the shading backward, the shading-side segment after it "
-                         "(B200 x8: 3021 it/s = 96.5%% of 8 x N=1); p2p: one such kernel at the end of the step (2891 it/s); both fall "
-                         "back to `post` if the box has no peer-mapped memory. post: one NCCL all-reduce after the graph (2739 it/s). "
-                         "overlap: NCCL, segment-wise inside the backward pass (slower: the NCCL kernel takes SMs from the shading backward)")
+                         "the rasteriser-side segment on a side stream under the shading backward, the shading-side segment after it; "
+                         "p2p: one such kernel at the end of the step; both fall back to `post` if the box has no peer-mapped "
+                         "memory. post: one NCCL all-reduce after the graph. overlap: NCCL, segment-wise inside the backward pass "
+                         "(slower: the NCCL kernel takes SMs from the shading backward)")
     ap.add_argument("--bg-ctas", type=int, default=4, help="--reduce overlap: CTA limit of the communicator that carries the "
                     "segment overlapped with the shading backward (0 = default communicator for both segments)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4"],
-                    help="train = C3-train fwd+bwd it/s (headline); relight = C3-eval forward ms/frame (Ns=384, S=7, VS=64); "
-                         "c4 = 1M surfels, 8 views per step sharded over the ranks (strong scaling)")
+    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4", "visibility"],
+                    help="train = C3-train fwd+bwd it/s (headline, plus the extra keys); relight = C3-eval forward ms/frame (Ns=384, "
+                         "S=7, VS=64); c4 = 1M surfels, 8 views per step sharded over the ranks (strong scaling); visibility = LBVH "
+                         "build + opacity trace vs the reference kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference_cuda":
-        run_reference_cuda(args)
-    elif args.workload == "relight":
-        run_relight(args)
-    elif args.workload == "c4":
-        run_c4(args)
-    else:
+        print(json.dumps(measure_reference_cuda(args.steps, args.warmup)), flush=True)
+    elif args.workload == "train":
         run_ours(args)
+    else:
+        run_workload(args)
 
 
 if __name__ == "__main__":

@@ -135,6 +135,15 @@ int svgir_raster_preprocess(const svgir_raster_cfg* cfg, const svgir_raster_in* 
 int svgir_raster_render(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
                         svgir_raster_state* state, svgir_raster_out* out, void* stream);
 
+/* The two halves of svgir_raster_render as separate calls, so that a caller can run the binning on one stream while
+ * the shading that produces in->features / in->vfeatures runs on another (binning needs the geometry only):
+ * svgir_raster_bin = duplicateWithKeys + sort + ranges; svgir_raster_composite = the forward compositing kernel
+ * (+ the rgss screen-space kernels). render == bin followed by composite. */
+int svgir_raster_bin(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                     svgir_raster_state* state, svgir_raster_out* out, void* stream);
+int svgir_raster_composite(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                           svgir_raster_state* state, svgir_raster_out* out, void* stream);
+
 /* Pixel gradients in, per-surfel gradients out (RasterizeGaussiansBackwardCUDA,
  * rasterize_points.cu:147-265; Rasterizer::backward rasterizer_impl.cu:386-523). */
 typedef struct svgir_raster_grads {
@@ -166,6 +175,29 @@ int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in
                           const svgir_raster_state* state, const int32_t* radii,
                           svgir_raster_grads* g, void* stream);
 
+/* The two halves of svgir_raster_backward for a caller that owns the step (no autograd in between):
+ * svgir_raster_backward_composite runs the backward compositing kernel only (fills geo_grad / dL_dfeatures /
+ * dL_dvfeatures, which the caller zero-filled); svgir_raster_backward_params turns geo_grad into PARAMETER
+ * gradients for the surfels of state->vis_list only (culled surfels are skipped, not zero-filled) and ADDS them
+ * into the caller's gradient buffers -- the .grad tensors of the optimiser, or one rank's slice of the flat
+ * data-parallel bucket -- so that a step rendering several views accumulates without extra kernels. d_means3D is
+ * updated with fp32 atomics (the shading backward adds the view-direction term into the same rows, possibly at
+ * the same time on another stream). NULL pointers are skipped. Does nothing when the forward's bins overflowed
+ * (state->num_rendered[1] != 0): an overflowed step contributes exactly zero and is re-run by its owner. */
+typedef struct svgir_param_grads {
+    float* d_means3D;    /* [P,3]   += (atomic) */
+    float* d_opacities;  /* [P,1]   += */
+    float* d_scales;     /* [P,3]   += */
+    float* d_rotations;  /* [P,4]   += */
+    float* d_sh;         /* [P,M,3] += */
+    float* d_means2D;    /* [P,3]   += screen-space gradient (densification statistic, gaussian_model.py:1270-1276) */
+} svgir_param_grads;
+int svgir_raster_backward_composite(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                                    const svgir_raster_state* state, svgir_raster_grads* g, void* stream);
+int svgir_raster_backward_params(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                                 const svgir_raster_state* state, const float* geo_grad,
+                                 const svgir_param_grads* pg, void* stream);
+
 /* mark_visible (rasterize_points.cu:267-286). svgss: all false (rasterizer_impl.cu:54-66);
  * rgss: frustum test z > 0.2 (rgss auxiliary.h:146-171). present is uint8/bool [P]. */
 int svgir_mark_visible(int variant, int P, const float* means3D, const float* viewmatrix,
@@ -185,7 +217,15 @@ typedef struct svgir_shade_cfg {
     int32_t env_mode;         /* 0: learnable map -- softplus(param), result x2 (direct_light_map.py:83,106);
                                  1: fixed linear map as given (EnvLight after its 32x64 resize), x1 */
     int32_t debug;
+    int32_t flags;            /* SVGIR_SHADE_* bits */
+    int32_t reserved_;
 } svgir_shade_cfg;
+#define SVGIR_SHADE_ENV_READY 1   /* env_act_scratch already holds the activated map (a forward call of this step
+                                     wrote it): skip the activation kernel */
+#define SVGIR_SHADE_ACCUMULATE 2  /* backward: ADD into d_base_color / d_roughness / d_metallic / d_normals instead
+                                     of overwriting them (caller-zeroed .grad buffers, multi-view accumulation) */
+#define SVGIR_SHADE_VIEW_4X4 4    /* in->view3x3 points at the 4x4 world-view matrix (row stride 4) instead of a
+                                     contiguous [3,3] copy of its rotation block */
 
 typedef struct svgir_shade_in {
     const float* base_color;     /* [N,12] */
@@ -207,6 +247,13 @@ typedef struct svgir_shade_in {
      * that culled surfels -- which no pixel reads and whose gradients are zero -- cost nothing. */
     const int32_t* surfel_list;  /* [<=N] surfel indices, or NULL = all N surfels */
     const int32_t* surfel_count; /* [1] device-side length of surfel_list */
+    /* Fused view directions: with viewdirs == NULL the kernels evaluate normalize(campos - means3D[n]) themselves
+     * (gaussian_renderer/svgss.py:95: F.normalize(camera_center - means3D)), and the backward adds the resulting
+     * position gradient into svgir_shade_grads.d_means3D instead of writing d_viewdirs. */
+    const float* means3D;        /* [N,3] or NULL */
+    const float* campos;         /* [3] device, or NULL */
+    const int32_t* skip_flag;    /* optional device flag: the backward does nothing when *skip_flag != 0 (the
+                                    rasteriser's binning-overflow flag: an overflowed step contributes zero) */
 } svgir_shade_in;
 
 typedef struct svgir_shade_out {
@@ -252,6 +299,7 @@ typedef struct svgir_shade_grads {
     const float* sum_indirect;  /* [N,12] or NULL; required when g_direct / g_indirect are given */
     float* d_env_scratch;       /* [env_h,env_w,4] scratch (library zeroes it); required with d_env */
     int32_t g_row_stride, g_mean_vis_stride, g_mean_stride, reserved_;
+    float* d_means3D;           /* [N,3] += (atomic) -d/d(campos - means3D); required when in->viewdirs is NULL */
 } svgir_shade_grads;
 
 int svgir_shade_forward(const svgir_shade_cfg* cfg, const svgir_shade_in* in, const svgir_shade_out* out,

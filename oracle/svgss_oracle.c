@@ -370,8 +370,9 @@ static inline int eval_pair(int variant, float px, float py, const float* xy, co
         float dist = fmaf(dy, dx * (con[1] + con[1]), fmaf(dx, dx * con[0], dy * (dy * con[2])));
         power = dist * -0.5f;
     } else {
-        /* rgss forward.cu:433: -0.5f*(a dx^2 + c dy^2) - b dx dy */
-        power = -0.5f * (con[0] * dx * dx + con[2] * dy * dy) - con[1] * dx * dy;
+        /* rgss forward.cu:433 / backward.cu:581: -0.5f*(a dx^2 + c dy^2) - b dx dy, contraction as compiled
+         * (SASS of the sm_100 build: two FFMAs, products rounded first) */
+        power = fmaf(fmaf(dx, dx * con[0], dy * (dy * con[2])), -0.5f, -(dy * (dx * con[1])));
     }
     if (power > 0.0f) return 0;
     float G = expf(power);

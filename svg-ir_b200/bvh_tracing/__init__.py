@@ -9,7 +9,7 @@ Everything runs in libsvgir_b200.so; there is no CPU fallback.
 """
 from __future__ import annotations
 
-import weakref
+from collections import OrderedDict
 
 import torch
 
@@ -19,10 +19,14 @@ from svgir_b200 import bvh as _bvh
 class _CModule:
     """bvh_tracing._C"""
 
-    def __init__(self):
-        # trees by the identity of the returned `nodes` tensor, so that trace_bvh_opacity(nodes, aabbs, ...)
-        # finds the packed traversal records create_bvh built
-        self._trees = weakref.WeakValueDictionary()
+    def __init__(self, capacity: int = 8):
+        # The reference's RayTracer keeps only the `nodes` / `aabbs` tensors (submodules/bvh/__init__.py:59-60), so
+        # trace_bvh_opacity(nodes, aabbs, ...) must find the packed traversal records create_bvh built from the
+        # tensor alone: a small LRU of strongly held trees keyed by the storage address, each remembering the
+        # tensor it was built for. Holding `nodes` alive means its address cannot be recycled while the entry
+        # exists; a hit is validated by identity of the storage, shape and version.
+        self._trees: "OrderedDict[int, object]" = OrderedDict()
+        self._capacity = capacity
 
     def create_bvh(self, means3D, scales, rotations, nodes, aabbs):
         """src/bvh.cu:9-27: nodes / aabbs are updated in place and returned with the Morton codes."""
@@ -31,14 +35,20 @@ class _CModule:
             nodes.copy_(tree.nodes)
             aabbs.copy_(tree.aabbs)
         tree._owner_nodes = nodes
+        tree._owner_version = nodes._version
+        self._trees.pop(nodes.data_ptr(), None)
         self._trees[nodes.data_ptr()] = tree
-        self._last = tree
+        while len(self._trees) > self._capacity:
+            self._trees.popitem(last=False)
         return nodes, aabbs, tree.morton
 
     def _find(self, nodes, aabbs):
         tree = self._trees.get(nodes.data_ptr())
-        if tree is None or tree.P != (nodes.shape[0] + 1) // 2:
-            raise RuntimeError("trace_bvh_opacity: `nodes` was not produced by this module's create_bvh")
+        if (tree is None or tree.P != (nodes.shape[0] + 1) // 2 or tuple(nodes.shape) != tuple(tree._owner_nodes.shape) or
+                nodes._version != tree._owner_version):
+            raise RuntimeError("trace_bvh_opacity: `nodes` was not produced by this module's create_bvh (or was modified "
+                               "since, or more than %d trees were built after it)" % self._capacity)
+        self._trees.move_to_end(nodes.data_ptr())
         return tree
 
     def trace_bvh_opacity(self, nodes, aabbs, rays_o, rays_d, means3D, covs3D, opacities, normals):

@@ -188,6 +188,58 @@ int svgir_raster_render(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
     return rc;
 }
 
+int svgir_raster_bin(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                     svgir_raster_state* st, svgir_raster_out* out, void* stream) {
+    int rc = validate(cfg, in, false);   // binning reads the geometry only
+    if (rc) return rc;
+    if (!st || !out || !st->keys || !st->point_list || !out->radii) { set_error("state/out buffers missing"); return SVGIR_ERR_INVALID; }
+    if (cfg->P == 0) return SVGIR_OK;
+    return launch_binning(*cfg, *st, out->radii, (cudaStream_t)stream);
+}
+
+int svgir_raster_composite(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                           svgir_raster_state* st, svgir_raster_out* out, void* stream) {
+    int rc = validate(cfg, in);
+    if (rc) return rc;
+    if (!st || !out || !st->point_list || !st->final_T || !out->color) { set_error("state/out buffers missing"); return SVGIR_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cfg->P == 0) return SVGIR_OK;
+    rc = launch_composite_fwd(*cfg, *in, *st, *out, s);
+    if (rc) return rc;
+    if (cfg->variant == SVGIR_VARIANT_RGSS && cfg->computer_pseudo_normal) {
+        if (!out->pseudo_normal || !out->surface_xyz) { set_error("pseudo_normal/surface_xyz buffers missing"); return SVGIR_ERR_INVALID; }
+        rc = launch_pseudo_normal(*cfg, *out, s);
+    }
+    return rc;
+}
+
+int svgir_raster_backward_composite(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                                    const svgir_raster_state* st, svgir_raster_grads* g, void* stream) {
+    int rc = validate(cfg, in);
+    if (rc) return rc;
+    if (!st || !g || !g->geo_grad || !g->dL_dcolor) { set_error("state/grad buffers missing"); return SVGIR_ERR_INVALID; }
+    if (cfg->P == 0) return SVGIR_OK;
+    return launch_composite_bwd(*cfg, *in, *st, *g, (cudaStream_t)stream);
+}
+
+int svgir_raster_backward_params(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
+                                 const svgir_raster_state* st, const float* geo_grad,
+                                 const svgir_param_grads* pg, void* stream) {
+    int rc = validate(cfg, in, false);
+    if (rc) return rc;
+    if (!st || !pg || !geo_grad || !st->vis_list || !st->vis_count || !st->num_rendered || !st->cov3D || !st->clamped) {
+        set_error("backward_params: needs geo_grad, the visible-surfel list of the forward and the forward's state");
+        return SVGIR_ERR_INVALID;
+    }
+    if ((in->shs && !pg->d_sh) || (in->scales && (!pg->d_scales || !pg->d_rotations)) || !pg->d_means3D || !pg->d_opacities ||
+        ((uintptr_t)pg->d_rotations & 15)) {
+        set_error("backward_params: d_means3D, d_opacities, d_sh (with shs), d_scales + d_rotations (with scales; d_rotations 16-byte aligned) are required");
+        return SVGIR_ERR_INVALID;
+    }
+    if (cfg->P == 0) return SVGIR_OK;
+    return launch_preprocess_bwd_params(*cfg, *in, *st, geo_grad, *pg, (cudaStream_t)stream);
+}
+
 int svgir_raster_backward(const svgir_raster_cfg* cfg, const svgir_raster_in* in,
                           const svgir_raster_state* st, const int32_t* radii,
                           svgir_raster_grads* g, void* stream) {

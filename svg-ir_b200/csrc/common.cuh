@@ -115,7 +115,9 @@ __device__ __forceinline__ bool eval_alpha(float px, float py, float mx, float m
         float dist = fma_(e.dy, mul_(e.dx, add_(cy, cy)), fma_(e.dx, mul_(e.dx, cx), mul_(e.dy, mul_(e.dy, cz))));
         power = mul_(dist, -0.5f);
     } else {
-        power = -0.5f * (cx * e.dx * e.dx + cz * e.dy * e.dy) - cy * e.dx * e.dy;
+        // rgss forward.cu:433 / backward.cu:581 as the reference's sm_100 build contracts it (read from its SASS:
+        // FMUL dy*cz, FMUL dx*cx, FMUL dx*cy, FMUL dy*(dy*cz), FMUL dy*(dx*cy), FFMA dx*(dx*cx)+.., FFMA (..)*-0.5 - ..)
+        power = fma_(fma_(e.dx, mul_(e.dx, cx), mul_(e.dy, mul_(e.dy, cz))), -0.5f, -mul_(e.dy, mul_(e.dx, cy)));
     }
     if (power > 0.0f) return false;
     e.G = expf(power);
@@ -176,5 +178,7 @@ int launch_composite_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
 int launch_preprocess_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                           const svgir_raster_state& st, const int32_t* radii, svgir_raster_grads& g,
                           cudaStream_t s);
+int launch_preprocess_bwd_params(const svgir_raster_cfg& c, const svgir_raster_in& in, const svgir_raster_state& st,
+                                 const float* geo_grad, const svgir_param_grads& pg, cudaStream_t s);
 
 }  // namespace svgir

@@ -26,15 +26,28 @@ __device__ __constant__ float bSHC3[7] = {-0.5900435899266435f, 2.89061144264055
                                           -0.4570457994644658f, 1.445305721320277f,
                                           -0.5900435899266435f};
 
-template <bool RGSS>
+// ACC = false: the reference-shaped call (svgir_raster_backward): one thread per surfel of [0,P), every output row is
+//   written (zeros for culled surfels).
+// ACC = true (svgir_raster_backward_params): one thread per entry of the visible-surfel list; parameter gradients are
+//   ADDED into caller-zeroed buffers (`pg`), the API-level intermediates (dL_dcolors, dL_dcov3D, ...) are not
+//   materialised, and an overflowed forward contributes nothing.
+#define PB_STORE(ptr, val) do { if (ACC) *(ptr) += (val); else *(ptr) = (val); } while (0)
+template <bool RGSS, bool ACC>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const svgir_raster_cfg c, const svgir_raster_in in, const float* __restrict__ cov3Ds,
     const uint8_t* __restrict__ clamped, const int32_t* __restrict__ radii,
-    const float* __restrict__ geo_grad, svgir_raster_grads g) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* __restrict__ geo_grad, svgir_raster_grads g, const svgir_param_grads pg,
+    const int32_t* __restrict__ vis_list, const int32_t* __restrict__ vis_count,
+    const int32_t* __restrict__ num_rendered) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ACC) {
+        if (num_rendered[1] != 0 || idx >= min(__ldg(vis_count), c.P)) return;
+        idx = __ldg(vis_list + idx);
+        g.dL_dsh = pg.d_sh; g.dL_dscales = pg.d_scales; g.dL_drotations = pg.d_rotations;
+    }
     if (idx >= c.P) return;
     const int M = c.M;
-    const bool visible = radii[idx] > 0;
+    const bool visible = ACC || radii[idx] > 0;
     if (!visible) {
         // reference leaves the torch::zeros initialisation untouched for culled surfels
 #pragma unroll
@@ -61,16 +74,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const float dcol[3] = {g1.z, g1.w, g2.x};
     const float dnrm[3] = {g2.y, g2.z, g2.w};
     const float ddep = g3.x;
-    g.dL_dmeans2D[3 * idx] = dm2x; g.dL_dmeans2D[3 * idx + 1] = dm2y; g.dL_dmeans2D[3 * idx + 2] = 0.f;
-    g.dL_dopacities[idx] = dopac;
+    if (ACC) {
+        if (pg.d_means2D) { pg.d_means2D[3 * idx] += dm2x; pg.d_means2D[3 * idx + 1] += dm2y; }
+        if (pg.d_opacities) pg.d_opacities[idx] += dopac;
+    } else {
+        g.dL_dmeans2D[3 * idx] = dm2x; g.dL_dmeans2D[3 * idx + 1] = dm2y; g.dL_dmeans2D[3 * idx + 2] = 0.f;
+        g.dL_dopacities[idx] = dopac;
 #pragma unroll
-    for (int i = 0; i < 3; i++) g.dL_dcolors[3 * idx + i] = dcol[i];
-    if (g.dL_dconic) {
+        for (int i = 0; i < 3; i++) g.dL_dcolors[3 * idx + i] = dcol[i];
+    }
+    if (!ACC && g.dL_dconic) {
         g.dL_dconic[4 * idx] = dcon[0]; g.dL_dconic[4 * idx + 1] = dcon[1];
         g.dL_dconic[4 * idx + 2] = 0.f; g.dL_dconic[4 * idx + 3] = dcon[2];
     }
-    if (g.dL_dnormal3) for (int i = 0; i < 3; i++) g.dL_dnormal3[3 * idx + i] = dnrm[i];
-    if (g.dL_ddepths) g.dL_ddepths[idx] = ddep;
+    if (!ACC && g.dL_dnormal3) for (int i = 0; i < 3; i++) g.dL_dnormal3[3 * idx + i] = dnrm[i];
+    if (!ACC && g.dL_ddepths) g.dL_ddepths[idx] = ddep;
 
     const float* __restrict__ V = c.viewmatrix;
     const float* __restrict__ PV = c.projmatrix;
@@ -124,8 +142,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 #pragma unroll
         for (int i = 0; i < 6; i++) dcv[i] = 0.f;
     }
+    if (!ACC) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) g.dL_dcov3D[6 * idx + i] = dcv[i];
+        for (int i = 0; i < 6; i++) g.dL_dcov3D[6 * idx + i] = dcv[i];
+    }
     const float dL_dT00 = 2 * TV0[0] * dL_da + TV1[0] * dL_db;
     const float dL_dT01 = 2 * TV0[1] * dL_da + TV1[1] * dL_db;
     const float dL_dT02 = 2 * TV0[2] * dL_da + TV1[2] * dL_db;
@@ -166,13 +186,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         const int D = c.sh_degree;
         int nco = 1;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) dsh[ch] = bSHC0 * dRGB[ch];
+        for (int ch = 0; ch < 3; ch++) PB_STORE(dsh + ch, bSHC0 * dRGB[ch]);
         if (D > 0) {
             nco = 4;
             const float w1 = -bSHC1 * y, w2 = bSHC1 * z, w3 = -bSHC1 * x;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                dsh[3 + ch] = w1 * dRGB[ch]; dsh[6 + ch] = w2 * dRGB[ch]; dsh[9 + ch] = w3 * dRGB[ch];
+                PB_STORE(dsh + 3 + ch, w1 * dRGB[ch]); PB_STORE(dsh + 6 + ch, w2 * dRGB[ch]); PB_STORE(dsh + 9 + ch, w3 * dRGB[ch]);
                 dRx[ch] = -bSHC1 * sh[9 + ch];
                 dRy[ch] = -bSHC1 * sh[3 + ch];
                 dRz[ch] = bSHC1 * sh[6 + ch];
@@ -184,8 +204,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
                 const float w7 = bSHC2[3] * xz, w8 = bSHC2[4] * (xx - yy);
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
-                    dsh[12 + ch] = w4 * dRGB[ch]; dsh[15 + ch] = w5 * dRGB[ch]; dsh[18 + ch] = w6 * dRGB[ch];
-                    dsh[21 + ch] = w7 * dRGB[ch]; dsh[24 + ch] = w8 * dRGB[ch];
+                    PB_STORE(dsh + 12 + ch, w4 * dRGB[ch]); PB_STORE(dsh + 15 + ch, w5 * dRGB[ch]); PB_STORE(dsh + 18 + ch, w6 * dRGB[ch]);
+                    PB_STORE(dsh + 21 + ch, w7 * dRGB[ch]); PB_STORE(dsh + 24 + ch, w8 * dRGB[ch]);
                     const float* s = sh + ch;
                     dRx[ch] += bSHC2[0] * y * s[12] + bSHC2[2] * 2.f * -x * s[18] + bSHC2[3] * z * s[21] + bSHC2[4] * 2.f * x * s[24];
                     dRy[ch] += bSHC2[0] * x * s[12] + bSHC2[1] * z * s[15] + bSHC2[2] * 2.f * -y * s[18] + bSHC2[4] * 2.f * -y * s[24];
@@ -200,9 +220,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
                     const float w14 = bSHC3[5] * z * (xx - yy), w15 = bSHC3[6] * x * (xx - 3.f * yy);
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++) {
-                        dsh[27 + ch] = w9 * dRGB[ch]; dsh[30 + ch] = w10 * dRGB[ch]; dsh[33 + ch] = w11 * dRGB[ch];
-                        dsh[36 + ch] = w12 * dRGB[ch]; dsh[39 + ch] = w13 * dRGB[ch]; dsh[42 + ch] = w14 * dRGB[ch];
-                        dsh[45 + ch] = w15 * dRGB[ch];
+                        PB_STORE(dsh + 27 + ch, w9 * dRGB[ch]); PB_STORE(dsh + 30 + ch, w10 * dRGB[ch]); PB_STORE(dsh + 33 + ch, w11 * dRGB[ch]);
+                        PB_STORE(dsh + 36 + ch, w12 * dRGB[ch]); PB_STORE(dsh + 39 + ch, w13 * dRGB[ch]); PB_STORE(dsh + 42 + ch, w14 * dRGB[ch]);
+                        PB_STORE(dsh + 45 + ch, w15 * dRGB[ch]);
                         const float* s = sh + ch;
                         dRx[ch] += (bSHC3[0] * s[27] * 3.f * 2.f * xy + bSHC3[1] * s[30] * yz +
                                     bSHC3[2] * s[33] * -2.f * xy + bSHC3[3] * s[36] * -3.f * 2.f * xz +
@@ -219,7 +239,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
                 }
             }
         }
-        for (int i = 3 * nco; i < 3 * M; i++) dsh[i] = 0.f;
+        if (!ACC) for (int i = 3 * nco; i < 3 * M; i++) dsh[i] = 0.f;
         const float ddx = dRx[0] * dRGB[0] + dRx[1] * dRGB[1] + dRx[2] * dRGB[2];
         const float ddy = dRy[0] * dRGB[0] + dRy[1] * dRGB[1] + dRy[2] * dRGB[2];
         const float ddz = dRz[0] * dRGB[0] + dRz[1] * dRGB[1] + dRz[2] * dRGB[2];
@@ -228,11 +248,18 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         dm[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv32;
         dm[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * inv32;
         dm[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * inv32;
-    } else {
+    } else if (!ACC) {
         for (int i = 0; i < 3 * M; i++) g.dL_dsh[(size_t)idx * 3 * M + i] = 0.f;
     }
+    if (ACC) {
+        if (pg.d_means3D) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) g.dL_dmeans3D[3 * idx + i] = dm[i];
+            for (int i = 0; i < 3; i++) atomicAdd(pg.d_means3D + 3 * idx + i, dm[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) g.dL_dmeans3D[3 * idx + i] = dm[i];
+    }
 
     if (in.scales) {
         // computeCov3D backward (backward.cu:326-432)
@@ -262,9 +289,9 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         float ds[3];
 #pragma unroll
         for (int cc2 = 0; cc2 < 3; cc2++) ds[cc2] = Rm[0][cc2] * dM[0][cc2] + Rm[1][cc2] * dM[1][cc2] + Rm[2][cc2] * dM[2][cc2];
-        g.dL_dscales[3 * idx] = ds[0];
-        g.dL_dscales[3 * idx + 1] = ds[1];
-        g.dL_dscales[3 * idx + 2] = surface ? 0.f : ds[2];
+        PB_STORE(g.dL_dscales + 3 * idx, ds[0]);
+        PB_STORE(g.dL_dscales + 3 * idx + 1, ds[1]);
+        PB_STORE(g.dL_dscales + 3 * idx + 2, surface ? 0.f : ds[2]);
         float dRt[3][3];
 #pragma unroll
         for (int cc2 = 0; cc2 < 3; cc2++)
@@ -278,8 +305,15 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         dq.y = 2 * y * (dRt[1][0] + dRt[0][1]) + 2 * z * (dRt[2][0] + dRt[0][2]) + 2 * r * (dRt[1][2] - dRt[2][1]) - 4 * x * (dRt[2][2] + dRt[1][1]);
         dq.z = 2 * x * (dRt[1][0] + dRt[0][1]) + 2 * r * (dRt[2][0] - dRt[0][2]) + 2 * z * (dRt[1][2] + dRt[2][1]) - 4 * y * (dRt[2][2] + dRt[0][0]);
         dq.w = 2 * r * (dRt[0][1] - dRt[1][0]) + 2 * x * (dRt[2][0] + dRt[0][2]) + 2 * y * (dRt[1][2] + dRt[2][1]) - 4 * z * (dRt[1][1] + dRt[0][0]);
-        reinterpret_cast<float4*>(g.dL_drotations)[idx] = dq;
-    } else {
+        if (ACC) {
+            float4* dst = reinterpret_cast<float4*>(g.dL_drotations) + idx;
+            float4 o = *dst;
+            o.x += dq.x; o.y += dq.y; o.z += dq.z; o.w += dq.w;
+            *dst = o;
+        } else {
+            reinterpret_cast<float4*>(g.dL_drotations)[idx] = dq;
+        }
+    } else if (!ACC) {
 #pragma unroll
         for (int i = 0; i < 3; i++) g.dL_dscales[3 * idx + i] = 0.f;
 #pragma unroll
@@ -291,10 +325,24 @@ int launch_preprocess_bwd(const svgir_raster_cfg& c, const svgir_raster_in& in,
                           const svgir_raster_state& st, const int32_t* radii, svgir_raster_grads& g,
                           cudaStream_t s) {
     const int grid = (c.P + 255) / 256;
+    const svgir_param_grads none = {};
     if (c.variant == SVGIR_VARIANT_RGSS)
-        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<true><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g); }
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<true, false><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g, none, nullptr, nullptr, nullptr); }
     else
-        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<false><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g); }
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<false, false><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, radii, g.geo_grad, g, none, nullptr, nullptr, nullptr); }
+    return check_launch("preprocess_bwd", c.debug, s);
+}
+
+// svgir_raster_backward_params: visible surfels only, gradients added into the caller's buffers. The grid covers P
+// (the list length is only known on the device); threads beyond the list return at once.
+int launch_preprocess_bwd_params(const svgir_raster_cfg& c, const svgir_raster_in& in, const svgir_raster_state& st,
+                                 const float* geo_grad, const svgir_param_grads& pg, cudaStream_t s) {
+    const int grid = (c.P + 255) / 256;
+    svgir_raster_grads g = {};
+    if (c.variant == SVGIR_VARIANT_RGSS)
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<true, true><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, nullptr, geo_grad, g, pg, st.vis_list, st.vis_count, st.num_rendered); }
+    else
+        { TimedScope ts_("preprocess_bwd", s); preprocess_bwd_kernel<false, true><<<grid, 256, 0, s>>>(c, in, st.cov3D, st.clamped, nullptr, geo_grad, g, pg, st.vis_list, st.vis_count, st.num_rendered); }
     return check_launch("preprocess_bwd", c.debug, s);
 }
 

@@ -104,6 +104,10 @@ struct ShadeArgs {
     const float* areas;       // [N,Ns]
     const int32_t* list;       // optional work list: shade only surfels list[0 .. *list_count)
     const int32_t* list_count;
+    const float* means3D;      // viewdirs == nullptr: view vector = campos - means3D[n] (normalised in the kernel)
+    const float* campos;
+    const int32_t* skip_flag;  // backward only: return immediately when *skip_flag != 0
+    int view_stride;           // row stride of view3x3: 3, or 4 when it points at the 4x4 world-view matrix itself
 };
 
 // Surfel handled by work slot `slot` (identity without a work list); a.N once the work is exhausted.
@@ -175,8 +179,13 @@ struct RawSurfel { float vx, vy, vz, nx, ny, nz, rough, met, base; };
 
 template <bool MET>
 __device__ __forceinline__ void fetch_surfel(const ShadeArgs& a, int n, int lane, RawSurfel& r) {
-    const float* vd = a.viewdirs + (size_t)n * 3;
-    r.vx = __ldg(vd); r.vy = __ldg(vd + 1); r.vz = __ldg(vd + 2);
+    if (a.viewdirs) {
+        const float* vd = a.viewdirs + (size_t)n * 3;
+        r.vx = __ldg(vd); r.vy = __ldg(vd + 1); r.vz = __ldg(vd + 2);
+    } else {   // svgss.py:95: viewdirs = normalize(camera_center - means3D); the kernels normalise
+        const float* m = a.means3D + (size_t)n * 3;
+        r.vx = __ldg(a.campos) - __ldg(m); r.vy = __ldg(a.campos + 1) - __ldg(m + 1); r.vz = __ldg(a.campos + 2) - __ldg(m + 2);
+    }
     const int v = lane & 3;
     const float* nn = a.normals + ((size_t)n * 4 + v) * 3;
     r.nx = __ldg(nn); r.ny = __ldg(nn + 1); r.nz = __ldg(nn + 2);
@@ -421,7 +430,8 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
                 float* pk = out.pack + (size_t)n * out.row_stride;
                 pk[lane] = base;
                 const int j = lane >> 2;  // view-space axis; n_view[v][j] = sum_i N[v][i] R[i][j], R row-major [3,3]
-                pk[12 + lane] = sc.nx * a.view3x3[j] + sc.ny * a.view3x3[3 + j] + sc.nz * a.view3x3[6 + j];
+                const int vs = a.view_stride;
+                pk[12 + lane] = sc.nx * a.view3x3[j] + sc.ny * a.view3x3[vs + j] + sc.nz * a.view3x3[2 * vs + j];
                 if (lane < 4) pk[24 + lane] = sc.rough;
             }
         } else if (lane == 24) {
@@ -454,6 +464,8 @@ struct ShadeGradsK {
     float* d_radiance;                           // [N,Ns,3] or null
     float* d_visibility;                         // [N,Ns] or null
     float* d_env_acc;                            // [He,We,4] zeroed accumulator of the env gradient, or null
+    float* d_means3D;                            // fused view directions: [N,3] += -(gradient of the raw view vector)
+    int accumulate;                              // += into d_base_color / d_roughness / d_metallic / d_normals
 };
 
 // Env-map gradient scatter. sm_100 has no native shared-memory float atomic (atomicAdd on shared
@@ -503,6 +515,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
     extern __shared__ __align__(16) float smem_b[];
     constexpr int WPC = SHB_THREADS / 32;
     constexpr int NACC = MET ? 10 : 7;   // per-vertex partial sums kept by every lane
+    if (a.skip_flag && __ldg(a.skip_flag) != 0) return;   // the step's binning overflowed: contribute nothing
     const int nenv = a.He * a.We * 3;
     float* vu_all = smem_b;                                         // [WPC][4][VU_FLOATS]
     float* env_s = smem_b + WPC * 4 * VU_FLOATS;                    // activated env (if it fits)
@@ -744,14 +757,17 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
                 float val = tot + d_nov * cc * Vk - (d_c + d_nov * nvr) * cc * Nk / nl2;
                 if (g.g_pack) {  // packed view-space normals: n_view[v][j] = sum_i N[v][i] R[i][j]
                     const float* gp = g.g_pack + (size_t)n * g.g_row_stride + 12;
-                    val += gp[v] * a.view3x3[3 * slot] + gp[4 + v] * a.view3x3[3 * slot + 1] + gp[8 + v] * a.view3x3[3 * slot + 2];
+                    const float* vr = a.view3x3 + a.view_stride * slot;
+                    val += gp[v] * vr[0] + gp[4 + v] * vr[1] + gp[8 + v] * vr[2];
                 }
-                g.d_normals[((size_t)n * 4 + v) * 3 + slot] = val;
+                float* dst = g.d_normals + ((size_t)n * 4 + v) * 3 + slot;
+                *dst = g.accumulate ? *dst + val : val;
                 dvu = d_nov * cc * Nk;     // vertex-level N~.V term of dV component `slot`
             } else if (slot == 4) {
                 float val = d_a2 * 4.f * rgh * rgh * rgh + d_k * (2.f * rgh + 2.f) * 0.125f;
                 if (g.g_pack) val += g.g_pack[(size_t)n * g.g_row_stride + 24 + v];
-                g.d_roughness[(size_t)n * 4 + v] = val;
+                float* dst = g.d_roughness + (size_t)n * 4 + v;
+                *dst = g.accumulate ? *dst + val : val;
             }
             // fold the vertex-level view terms into the per-sample ones: component = slot (0..2)
             dV[0] += slot == 0 ? dvu : 0.f;
@@ -770,22 +786,27 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
                 dm = dfd * (-base * (1.f / PI_F));
                 if (MET) { db += dF0 * met; dm += dF0 * (base - 0.04f); }   // dF0 already carries the 1/Ns of the upstream
                 db += gc.pk_base;
-                g.d_base_color[(size_t)n * 12 + lane] = db;
+                float* dst = g.d_base_color + (size_t)n * 12 + lane;
+                *dst = g.accumulate ? *dst + db : db;
             }
             if (MET && g.d_metallic) {  // uniform branch: all lanes shuffle; lanes v, 4+v, 8+v hold the 3 channels
                 const float t = dm + __shfl_down_sync(full, dm, 4) + __shfl_down_sync(full, dm, 8);
-                if (lane < 4) g.d_metallic[(size_t)n * 4 + lane] = t;
+                if (lane < 4) {
+                    float* dst = g.d_metallic + (size_t)n * 4 + lane;
+                    *dst = g.accumulate ? *dst + t : t;
+                }
             }
         }
         // view direction: summed over the warp, then through the normalisation V = vd/|vd|
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dV[ch] = warp_sum(dV[ch]);
-        if (lane == 0) {
+        if (lane < 3) {
             const float vdot = Vx * dV[0] + Vy * dV[1] + Vz * dV[2];
-            float* o = g.d_viewdirs + (size_t)n * 3;
-            o[0] = (dV[0] - Vx * vdot) * inv_vlen;
-            o[1] = (dV[1] - Vy * vdot) * inv_vlen;
-            o[2] = (dV[2] - Vz * vdot) * inv_vlen;
+            const float Vk = lane == 0 ? Vx : (lane == 1 ? Vy : Vz);
+            const float dk = lane == 0 ? dV[0] : (lane == 1 ? dV[1] : dV[2]);
+            const float val = (dk - Vk * vdot) * inv_vlen;   // gradient of the un-normalised view vector
+            if (a.viewdirs) g.d_viewdirs[(size_t)n * 3 + lane] = val;
+            else atomicAdd(g.d_means3D + (size_t)n * 3 + lane, -val);   // view vector = campos - means3D
         }
         n = n_next; n_next = n_next2; slot += stride;
     }
@@ -892,13 +913,15 @@ void svgir_shade_reserve_sms(int n) { g_reserved_sms = n < 0 ? 0 : (n > 100 ? 10
 
 static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, ShadeArgs& a, cudaStream_t s) {
     if (!c || !in || c->N < 0 || c->Ns <= 0 || c->env_h <= 0 || c->env_w <= 0) { set_error("shade: bad cfg"); return SVGIR_ERR_INVALID; }
-    if (!in->base_color || !in->roughness || !in->normals || !in->viewdirs || !in->radiance || !in->visibility ||
+    if (!in->base_color || !in->roughness || !in->normals || !in->radiance || !in->visibility ||
         !in->incident_dirs || !in->incident_areas || !in->env || !in->env_act_scratch) {
         set_error("shade: missing input");
         return SVGIR_ERR_INVALID;
     }
+    if (!in->viewdirs && !(in->means3D && in->campos)) { set_error("shade: provide viewdirs, or means3D + campos"); return SVGIR_ERR_INVALID; }
     const int nenv = c->env_h * c->env_w * 3;
-    { TimedScope ts_("env_activate", s); env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, in->env, in->env_act_scratch, c->env_mode); }
+    if (!(c->flags & SVGIR_SHADE_ENV_READY))
+        { TimedScope ts_("env_activate", s); env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, in->env, in->env_act_scratch, c->env_mode); }
     a.N = c->N; a.Ns = c->Ns; a.He = c->env_h; a.We = c->env_w;
     a.env_scale = c->env_mode == 0 ? 2.0f : 1.0f;
     a.env_act = in->env_act_scratch; a.transform = in->env_transform; a.view3x3 = in->view3x3;
@@ -906,6 +929,8 @@ static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, Sha
     a.normals = in->normals; a.viewdirs = in->viewdirs; a.radiance = in->radiance;
     a.visibility = in->visibility; a.dirs = in->incident_dirs; a.areas = in->incident_areas;
     a.list = in->surfel_list; a.list_count = in->surfel_list ? in->surfel_count : nullptr;
+    a.means3D = in->means3D; a.campos = in->campos; a.skip_flag = in->skip_flag;
+    a.view_stride = (c->flags & SVGIR_SHADE_VIEW_4X4) ? 4 : 3;
     if (in->surfel_list && !in->surfel_count) { set_error("shade: surfel_list needs surfel_count"); return SVGIR_ERR_INVALID; }
     return SVGIR_OK;
 }
@@ -937,7 +962,10 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
     ShadeArgs a;
     int rc = shade_prepare(c, in, a, s);
     if (rc) return rc;
-    if (!gr || !gr->d_base_color || !gr->d_roughness || !gr->d_normals || !gr->d_viewdirs) { set_error("shade_backward: missing buffers"); return SVGIR_ERR_INVALID; }
+    if (!gr || !gr->d_base_color || !gr->d_roughness || !gr->d_normals || !(in->viewdirs ? gr->d_viewdirs : gr->d_means3D)) {
+        set_error("shade_backward: missing buffers (d_viewdirs with viewdirs, d_means3D with means3D + campos)");
+        return SVGIR_ERR_INVALID;
+    }
     if (gr->g_pack && !in->view3x3) { set_error("shade_backward: packed pass-through columns need view3x3"); return SVGIR_ERR_INVALID; }
     if (!gr->sum_direct) { set_error("shade_backward: sum_direct (saved by svgir_shade_forward) is required"); return SVGIR_ERR_INVALID; }
     if ((gr->g_direct || gr->g_indirect) && !gr->sum_indirect) { set_error("shade_backward: g_direct/g_indirect need the split sums (sum_indirect)"); return SVGIR_ERR_INVALID; }
@@ -947,7 +975,8 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
                   gr->g_row_stride > 0 ? gr->g_row_stride : 12, gr->g_mean_vis_stride > 0 ? gr->g_mean_vis_stride : 1,
                   gr->g_mean_stride > 0 ? gr->g_mean_stride : 3, in->env,
                   gr->d_base_color, gr->d_roughness, gr->d_metallic, gr->d_normals, gr->d_viewdirs,
-                  gr->d_radiance, gr->d_visibility, gr->d_env ? gr->d_env_scratch : nullptr};
+                  gr->d_radiance, gr->d_visibility, gr->d_env ? gr->d_env_scratch : nullptr,
+                  gr->d_means3D, (c->flags & SVGIR_SHADE_ACCUMULATE) ? 1 : 0};
     const int ntex = a.He * a.We;
     if (gr->d_env) {
         if (!gr->d_env_scratch) { set_error("shade_backward: d_env needs d_env_scratch [env_h*env_w*4]"); return SVGIR_ERR_INVALID; }

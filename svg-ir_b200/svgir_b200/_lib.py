@@ -65,6 +65,11 @@ class RasterGrads(C.Structure):
         "dL_dscales", "dL_drotations", "dL_dconic", "dL_dnormal3", "dL_ddepths")]
 
 
+class ParamGrads(C.Structure):
+    """svgir_param_grads: parameter-gradient buffers svgir_raster_backward_params adds into."""
+    _fields_ = [(n, c_fp) for n in ("d_means3D", "d_opacities", "d_scales", "d_rotations", "d_sh", "d_means2D")]
+
+
 _lib = None
 
 
@@ -97,13 +102,19 @@ def lib() -> C.CDLL:
             "There is no CPU / PyTorch fallback for this path.")
     L = C.CDLL(_SO)
     L.svgir_last_error.restype = C.c_char_p
-    for name in ("svgir_raster_preprocess", "svgir_raster_render"):
+    for name in ("svgir_raster_preprocess", "svgir_raster_render", "svgir_raster_bin", "svgir_raster_composite"):
         getattr(L, name).argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
                                      C.POINTER(RasterOut), C.c_void_p]
         getattr(L, name).restype = C.c_int
     L.svgir_raster_backward.argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
                                         C.c_void_p, C.POINTER(RasterGrads), C.c_void_p]
     L.svgir_raster_backward.restype = C.c_int
+    L.svgir_raster_backward_composite.argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
+                                                  C.POINTER(RasterGrads), C.c_void_p]
+    L.svgir_raster_backward_composite.restype = C.c_int
+    L.svgir_raster_backward_params.argtypes = [C.POINTER(RasterCfg), C.POINTER(RasterIn), C.POINTER(RasterState),
+                                               C.c_void_p, C.POINTER(ParamGrads), C.c_void_p]
+    L.svgir_raster_backward_params.restype = C.c_int
     L.svgir_mark_visible.argtypes = [C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
     L.svgir_mark_visible.restype = C.c_int
     L.svgir_timing_enable.argtypes = [C.c_int]
@@ -155,4 +166,5 @@ EXPORTED_SYMBOLS = [
     "svgir_train_loss_blocks", "svgir_train_loss_forward", "svgir_train_loss_backward", "svgir_peer_allreduce", "svgir_resolve_eval",
     "svgir_peer_allreduce_range", "svgir_shade_reserve_sms",
     "svgir_ssim_blocks", "svgir_ssim_forward", "svgir_ssim_backward",
+    "svgir_raster_bin", "svgir_raster_composite", "svgir_raster_backward_composite", "svgir_raster_backward_params",
 ]

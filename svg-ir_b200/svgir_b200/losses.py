@@ -206,6 +206,5 @@ class _FusedSSIM(torch.autograd.Function):
 
 def fused_ssim(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
     """`ssim(img1, img2)` of utils/loss_utils.py:32-62 ([C,H,W] images, 11x11 Gaussian window, mean) as one CUDA kernel
-    per direction (csrc/ssim.cu). Differentiable with respect to img1; img2 is the ground truth.
-    STATUS: not yet run on a GPU (written after round 1's GPU budget was spent); tests/test_ssim_gpu.py is gated."""
+    per direction (csrc/ssim.cu). Differentiable with respect to img1; img2 is the ground truth."""
     return _FusedSSIM.apply(img1, img2)

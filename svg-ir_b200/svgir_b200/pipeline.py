@@ -103,7 +103,8 @@ def camera_from_scene(cam, device) -> ViewCamera:
 
 
 def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
-    d = lambda a: torch.from_numpy(a).to(device)
+    """`mats` from scene.make_materials (numpy) or scene.make_materials_torch (tensors already on the device)."""
+    d = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(a)).to(device)
     m = SurfelModel(d(cloud.means3D), d(cloud.opacity), d(cloud.scales), d(cloud.rotations), d(cloud.shs),
                     d(mats["base_color"]), d(mats["roughness"]), d(mats["shading_normals"]), d(mats["radiance"]),
                     d(mats["visibility"]), d(mats["incident_dirs"]), d(mats["incident_areas"]))
@@ -282,16 +283,24 @@ def reduce_segments(pc: SurfelModel) -> list:
     return [[1, 2, 3, 4], [0, 5, 6, 7, 8]]
 
 
+# GraphedTrainingStep default: True = the step is the fixed kernel sequence of fused_step.FusedTrainStep (no autograd
+# between the kernels, one arena memset, binning / parameter backward on a side stream); False = `training_step`
+# (the autograd mirror of the reference's control flow) is what gets captured.
+FUSED_STEP = True
+
+
 class GraphedTrainingStep:
-    """`training_step` captured ONCE into a CUDA graph and replayed: one cudaGraphLaunch per iteration
+    """One training iteration captured ONCE into a CUDA graph and replayed: one cudaGraphLaunch per iteration
     instead of ~150 host-side launches and tensor allocations, and no mid-step device->host read
     (the reference blocks on num_rendered inside every forward, rasterizer_impl.cu:311, and again at
-    svgss.py:186). The rasteriser runs in its "async" count mode inside the graph: the binning buffers
-    have a fixed capacity (2x the largest num_rendered seen), the (num_rendered, overflow) pair lands
-    in pinned host memory, and __call__ checks it after the replay -- on overflow the capacity is
-    raised, the graph re-captured and the SAME step re-run, so the results are always those of a
-    complete render. Per-step inputs (camera matrices, ground-truth image) are copied into static
+    svgss.py:186). The binning buffers have a fixed capacity (2x the largest num_rendered seen), the
+    (num_rendered, overflow) pair lands in pinned host memory, and __call__ checks it after the replay -- on
+    overflow the capacity is raised, the graph re-captured and the SAME step re-run, so the results are always
+    those of a complete render. Per-step inputs (camera matrices, ground-truth image) are copied into static
     device buffers; results and .grad tensors are static buffers overwritten by the next call.
+
+    What is captured: `fused_step.FusedTrainStep` (default, `fused=True`: a fixed sequence of svgir kernels, see
+    that module) or `training_step` (`fused=False`: the autograd path, ~55 extra torch kernels per step).
 
     The camera intrinsics (H, W, tan_fov) are baked into the graph; a different value re-captures.
     With `bucket` (dist.FlatGradBucket) the .grad views are zeroed inside the graph and accumulated
@@ -300,19 +309,24 @@ class GraphedTrainingStep:
 
     def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
                  gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False,
-                 zero_in_graph: bool = True):
+                 zero_in_graph: bool = True, fused: Optional[bool] = None):
         self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
         # zero_in_graph=False (needs `bucket`): the graph ACCUMULATES into the bucket instead of zeroing it first, so a
         # rank that renders several views per step replays it once per view and reduces once (C4: 8 views / step);
-        # the caller zeroes the bucket at the start of the step. A (re-)capture leaves the bucket's content untouched.
+        # the caller zeroes the bucket at the start of the step. A (re-)capture leaves the bucket's content untouched,
+        # and a replay whose binning overflowed adds exactly zero (every backward kernel returns at once when the
+        # overflow flag is set), so re-running the step after the re-capture gives the complete sum.
         self.zero_in_graph = bool(zero_in_graph)
         if not self.zero_in_graph and (bucket is None or reduce_in_graph):
             raise ValueError("zero_in_graph=False needs a bucket and a reduction outside the graph")
-        # reduce_in_graph: the segment-wise NCCL all-reduce of `bucket` is captured INSIDE the graph, overlapped
-        # with the shading backward (FlatGradBucket.begin_overlap); the caller must not all-reduce again.
+        # reduce_in_graph: the segment-wise all-reduce of `bucket` is captured INSIDE the graph, overlapped
+        # with the shading backward; the caller must not all-reduce again.
         self.reduce_in_graph = bool(reduce_in_graph and bucket is not None)
         if self.reduce_in_graph and bucket.extra is None:
             raise ValueError("reduce_in_graph needs FlatGradBucket(..., extra_floats>=1) for the overflow flag")
+        self.fused = FUSED_STEP if fused is None else bool(fused)
+        if self.fused and self.reduce_in_graph and getattr(bucket, "segment_peer", None) is None:
+            self.fused = False   # NCCL collectives inside the step are issued through the autograd hooks
         self.flag_host = torch.zeros((1,), dtype=torch.float32).pin_memory() if self.reduce_in_graph else None
         dev = pc.xyz.device
         self.dev = dev
@@ -323,9 +337,12 @@ class GraphedTrainingStep:
         self.graph = None
         self.loss = None
         self.res = None
+        self.fs = None
         self.captures = 0
         self.launches_per_step = 0
         self.warmup = warmup
+        self._copy_stream = None
+        self._staged = self._consumed = None
 
     def _params(self):
         return self.pc.trainable() + [self.env]
@@ -337,7 +354,56 @@ class GraphedTrainingStep:
             for t in self._params():
                 t.grad = None
 
+    # ---- fused path ---------------------------------------------------------------------------------------------
+    def _capture_fused(self):
+        from . import fused_step
+        cur = torch.cuda.current_stream(self.dev)
+        keep = None if self.zero_in_graph else self.bucket.flat.clone()   # accumulated gradients survive the capture
+        if self.fs is None:
+            self.fs = fused_step.FusedTrainStep(self.pc, self.env, self.bg, self.cam, self.gt, bucket=self.bucket,
+                                                zero_grads=self.zero_in_graph, reduce_in_step=self.reduce_in_graph)
+            if self.bucket is None:
+                self.bucket_private = self.fs.bucket
+        fs = self.fs
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fs.calibrate()                      # sizes the bins for this camera (one host sync)
+            for _ in range(max(self.warmup, 1)):  # eager: lazy initialisations (function attributes, streams)
+                fs.enqueue()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = fs.enqueue()
+        if self.flag_host is not None:
+            self.flag_host = fs.flag_host
+        self.res = fs.result
+        self.launches_per_step = fs.launches
+        self.captures += 1
+        if keep is not None:
+            self.bucket.flat.copy_(keep)
+
+    def _finish_fused(self) -> int:
+        fs = self.fs
+        for _ in range(4):
+            torch.cuda.current_stream(self.dev).synchronize()
+            R, overflow = fs.read_count()
+            if not overflow and not (self.reduce_in_graph and float(self.flag_host[0]) > 0):
+                return R
+            # this rank or (flag summed over ranks) another one overflowed: every rank re-captures and re-runs
+            # together -- the step's all-reduce lives in the graph, so the replays must stay matched across ranks
+            if overflow:
+                fs.grow(R)
+            self.graph = None
+            self._capture_fused()
+            self.graph.replay()
+        raise RuntimeError("GraphedTrainingStep: binning capacity did not converge")
+
+    # ---- autograd path ------------------------------------------------------------------------------------------
     def _capture(self):
+        if self.fused:
+            return self._capture_fused()
         cur = torch.cuda.current_stream(self.dev)
         keep = None if self.zero_in_graph else self.bucket.flat.clone()   # accumulated gradients survive the capture
         side = torch.cuda.Stream(self.dev)
@@ -370,14 +436,18 @@ class GraphedTrainingStep:
         if keep is not None:
             self.bucket.flat.copy_(keep)
 
-    def load_inputs(self, cam: ViewCamera, gt_image: torch.Tensor):
+    def _check_intrinsics(self, cam: ViewCamera):
         c = self.cam
         if (cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy) != (c.image_height, c.image_width, c.tanfovx, c.tanfovy):
             self.cam = ViewCamera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,
                                   c.world_view_transform, c.full_proj_transform, c.camera_center, c.patch_bbox,
                                   c.prcppoint, block=c.block)
-            c = self.cam
             self.graph = None
+            self.fs = None   # intrinsics are baked into the fused step's kernel arguments
+        return self.cam
+
+    def load_inputs(self, cam: ViewCamera, gt_image: torch.Tensor):
+        c = self._check_intrinsics(cam)
         if cam.block is not None and c.block is not None:
             c.block.copy_(cam.block, non_blocking=True)   # one copy for all per-view constants
             if gt_image is not self.gt:
@@ -403,9 +473,50 @@ class GraphedTrainingStep:
             self.finish()
         return self.loss, self.res
 
+    # ---- host inputs one step ahead -----------------------------------------------------------------------------
+    def prefetch(self, cam: ViewCamera, gt_image: torch.Tensor):
+        """Uploads the NEXT step's inputs (camera block + ground-truth image, typically pinned host memory) into
+        a staging slot on a copy stream, so the host->device transfer overlaps the step that is running.
+        `replay_prefetched()` then moves the slot into the graph's static inputs (a device-to-device copy
+        at the head of the step) and replays."""
+        if cam.block is None:
+            raise ValueError("prefetch needs a blocked camera (pipeline.blocked_camera)")
+        self._check_intrinsics(cam)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+            self._stage_cam = torch.empty_like(self.cam.block)
+            self._stage_gt = torch.empty_like(self.gt)
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)   # the slot's previous content has been moved into the static inputs
+        with torch.cuda.stream(cs):
+            self._stage_cam.copy_(cam.block, non_blocking=True)
+            self._stage_gt.copy_(gt_image, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(cs)
+
+    def replay_prefetched(self, check: bool = False):
+        if self._staged is None:
+            raise RuntimeError("replay_prefetched: call prefetch() first")
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self._staged)
+        self.cam.block.copy_(self._stage_cam, non_blocking=True)
+        self.gt.copy_(self._stage_gt, non_blocking=True)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+        self._staged = None
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        if check:
+            self.finish()
+        return self.loss, self.res
+
     def finish(self) -> int:
         """Waits for the last replay and returns its num_rendered; on overflow re-captures with larger
         bins and re-runs the step."""
+        if self.fused:
+            return self._finish_fused()
         st = self.res["raster_state"]
         for _ in range(4):
             torch.cuda.current_stream(self.dev).synchronize()

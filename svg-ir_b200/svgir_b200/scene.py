@@ -174,3 +174,52 @@ def make_materials(cloud: SurfelCloud, sample_num: int, seed: int = 4321, env_hw
         radiance=f32(0.2 * rng.uniform(0, 1, (P, sample_num, 3))),
         env_param=f32(3.0 * rng.uniform(0, 1, (1, env_hw[0], env_hw[1], 3))),
     )
+
+
+def make_materials_torch(cloud: SurfelCloud, sample_num: int, seed: int, device, env_hw=(32, 64)) -> dict:
+    """`make_materials` with the big per-sample buffers ([P,Ns,*]: 32 B per sample) generated directly on `device`
+    by torch -- same distributions and the same incident-direction formula, different random bits. For workloads
+    where no CPU oracle looks at the inputs (the 1M-surfel / Ns=384 bench configurations), where building
+    2-4 GB with numpy and copying it would dominate the run."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    P = cloud.P
+    f32 = dict(dtype=torch.float32, device=device)
+    n = torch.from_numpy(cloud.normals).to(device)
+    sn = n[:, None, :] + 0.1 * torch.randn((P, 4, 3), generator=g, **f32)
+    sn = sn / sn.norm(dim=-1, keepdim=True)
+    # fibonacci_sphere_sampling(random_rotate=False) + rotation_between_z, as fibonacci_hemisphere_dirs above
+    delta = math.pi * (3.0 - math.sqrt(5.0))
+    idx = torch.arange(sample_num, **f32)[None]
+    z = torch.clamp_min(1 - 2 * idx / (2 * sample_num - 1), math.sin(10 / 180 * math.pi))
+    rad = torch.sqrt(1 - z * z)
+    theta = delta * idx
+    zs = torch.stack([torch.sin(theta) * rad, torch.cos(theta) * rad, z], dim=-2)  # [1,3,S]
+    v1, v2 = -n[:, 1], n[:, 0]
+    cp1 = torch.clamp_min(n[:, 2] + 1, 1e-7)
+    R = torch.zeros((P, 3, 3), **f32)
+    R[:, 0, 0] = 1 + (-v2 * v2) / cp1
+    R[:, 0, 1] = (v1 * v2) / cp1
+    R[:, 0, 2] = v2
+    R[:, 1, 0] = (v1 * v2) / cp1
+    R[:, 1, 1] = 1 + (-v1 * v1) / cp1
+    R[:, 1, 2] = -v1
+    R[:, 2, 0] = -v2
+    R[:, 2, 1] = v1
+    R[:, 2, 2] = 1 + (-v2 * v2 - v1 * v1) / cp1
+    flip = (n[:, 2] + 1 > 0)[:, None, None]
+    R = torch.where(flip, R, -torch.eye(3, **f32)[None])
+    dirs = R @ zs
+    dirs = dirs / dirs.norm(dim=-2, keepdim=True).clamp_min(1e-12)
+    dirs = dirs.transpose(1, 2).contiguous()
+    return dict(
+        base_color=0.03 + 0.77 * torch.rand((P, 12), generator=g, **f32),
+        roughness=0.09 + 0.9 * torch.rand((P, 4), generator=g, **f32),
+        shading_normals=sn.contiguous(),
+        incident_dirs=dirs,
+        incident_areas=torch.full((P, sample_num, 1), 2 * math.pi, **f32),
+        visibility=(torch.rand((P, sample_num, 1), generator=g, **f32) > 0.3).float(),
+        radiance=0.2 * torch.rand((P, sample_num, 3), generator=g, **f32),
+        env_param=3.0 * torch.rand((1, env_hw[0], env_hw[1], 3), generator=g, **f32),
+    )

@@ -26,13 +26,19 @@ c_fp = C.c_void_p
 
 class ShadeCfg(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ns", C.c_int32), ("env_h", C.c_int32), ("env_w", C.c_int32),
-                ("env_mode", C.c_int32), ("debug", C.c_int32)]
+                ("env_mode", C.c_int32), ("debug", C.c_int32), ("flags", C.c_int32), ("reserved_", C.c_int32)]
+
+
+SHADE_ENV_READY = 1    # SVGIR_SHADE_ENV_READY: env_act_scratch already holds the activated map
+SHADE_ACCUMULATE = 2   # SVGIR_SHADE_ACCUMULATE: backward adds into the d_* parameter-gradient buffers
+SHADE_VIEW_4X4 = 4     # SVGIR_SHADE_VIEW_4X4: view3x3 points at the 4x4 world-view matrix itself
 
 
 class ShadeIn(C.Structure):
     _fields_ = [(n, c_fp) for n in ("base_color", "roughness", "metallic", "normals", "viewdirs", "radiance",
                                     "visibility", "incident_dirs", "incident_areas", "env", "env_transform",
-                                    "env_act_scratch", "view3x3", "surfel_list", "surfel_count")]
+                                    "env_act_scratch", "view3x3", "surfel_list", "surfel_count",
+                                    "means3D", "campos", "skip_flag")]
 
 
 class ShadeOut(C.Structure):
@@ -48,7 +54,8 @@ class ShadeGrads(C.Structure):
                                     "d_base_color", "d_roughness", "d_metallic", "d_normals", "d_viewdirs",
                                     "d_radiance", "d_visibility", "d_env", "g_pack", "sum_direct", "sum_indirect",
                                     "d_env_scratch")] + \
-               [(n, C.c_int32) for n in ("g_row_stride", "g_mean_vis_stride", "g_mean_stride", "reserved_")]
+               [(n, C.c_int32) for n in ("g_row_stride", "g_mean_vis_stride", "g_mean_stride", "reserved_")] + \
+               [("d_means3D", c_fp)]
 
 
 _bound = False

@@ -35,7 +35,8 @@ def test_struct_layouts_match_header_sizes(tmp_path):
              ("svgir_raster_state", _lib.RasterState), ("svgir_raster_out", _lib.RasterOut),
              ("svgir_raster_grads", _lib.RasterGrads), ("svgir_shade_cfg", shading.ShadeCfg),
              ("svgir_shade_in", shading.ShadeIn), ("svgir_shade_out", shading.ShadeOut),
-             ("svgir_shade_grads", shading.ShadeGrads), ("svgir_peer_comm", _lib.PeerComm)]
+             ("svgir_shade_grads", shading.ShadeGrads), ("svgir_peer_comm", _lib.PeerComm),
+             ("svgir_param_grads", _lib.ParamGrads)]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "svgir_b200.h"\nint main(void){' +
                    "".join('printf("%%zu\\n", sizeof(%s));' % n for n, _ in pairs) + "return 0;}\n")

@@ -35,26 +35,38 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-20))
 
 
-def test_graphed_step_matches_eager():
+def _same_images(res_g, res_e, fused):
+    """The autograd path replays the eager kernels on the eager inputs: bit-equal. The fused step evaluates the view
+    direction inside the shading kernel (normalised once instead of twice): the shaded channels agree to ~1 ulp of the
+    direction, the SH colour image (no shading input) stays bit-equal."""
+    assert torch.equal(res_g["render"], res_e["render"])
+    if fused:
+        torch.testing.assert_close(res_g["raw_vfeature"], res_e["raw_vfeature"], rtol=1e-5, atol=1e-6)
+    else:
+        assert torch.equal(res_g["raw_vfeature"], res_e["raw_vfeature"])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_graphed_step_matches_eager(fused):
     pipeline, cloud, mats, cams, gts, dev = _setup()
     bg = torch.zeros(3, device=dev)
     pc_e, env_e = _model(pipeline, cloud, mats, dev)
     pc_g, env_g = _model(pipeline, cloud, mats, dev)
-    runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0])
+    runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0], fused=fused)
     for i in (0, 1, 2, 3, 1):
         loss_e, res_e = pipeline.training_step(cams[i], pc_e, env_e, bg, gts[i % 2])
         loss_g, res_g = runner(cams[i], gts[i % 2])
         assert int(res_g["num_rendered"]) == int(res_e["num_rendered"])
-        assert torch.equal(res_g["render"], res_e["render"])
-        assert torch.equal(res_g["raw_vfeature"], res_e["raw_vfeature"])
-        assert abs(float(loss_g) - float(loss_e)) <= 1e-6 * abs(float(loss_e))
+        _same_images(res_g, res_e, fused)
+        assert abs(float(loss_g) - float(loss_e)) <= (2e-6 if fused else 1e-6) * abs(float(loss_e))
         for a, b in zip(_grads(pc_g, env_g), _grads(pc_e, env_e)):
             assert _rel(a, b) < 1e-3
     assert runner.captures == 1
     assert runner.launches_per_step >= 10
 
 
-def test_graphed_step_overflow_recaptures():
+@pytest.mark.parametrize("fused", [True, False])
+def test_graphed_step_overflow_recaptures(fused):
     from svgir_b200 import raster
     pipeline, cloud, mats, cams, gts, dev = _setup(P=6000, W=160, H=128)
     bg = torch.zeros(3, device=dev)
@@ -66,7 +78,7 @@ def test_graphed_step_overflow_recaptures():
     raster.ASYNC_SLACK, raster.ASYNC_MARGIN = 1.0, 16
     raster._CAP_HINT.clear()
     try:
-        runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0])
+        runner = pipeline.GraphedTrainingStep(pc_g, env_g, bg, cams[0], gts[0], fused=fused)
         runner(cams[0], gts[0])
         assert runner.captures == 1
         R0 = int(runner.res["num_rendered"])

@@ -102,12 +102,14 @@ def test_rgss_package_returns_reference_tuple_and_trains():
     assert vis.dtype == torch.bool and vis.shape == (3000,)
 
 
-def test_rgss_against_reference_kernels_when_present():
+@pytest.mark.parametrize("P,W", [(60000, 400), (300000, 800)], ids=["60k-400", "C2-300k-800"])
+def test_rgss_against_reference_kernels_when_present(P, W):
+    """Second id = BASELINE.json configs[1] (C2): stage 1, 300k surfels, one 800x800 view, fwd+bwd."""
     from oracle import ref_cuda
     if not ref_cuda.available("rgss"):
         pytest.skip("oracle/_ref/librgss_ref.so not in this snapshot")
-    W = H = 400
-    case = util.make_case(60000, W, H, S=5, VS=0, seed=22)
+    H = W
+    case = util.make_case(P, W, H, S=5, VS=0, seed=22)
     g = util.pixel_grads(case)
     out, st, bw = _run_ours(case, g, computer_pseudo_normal=True)
     t = util.to_cuda(case)
@@ -127,12 +129,14 @@ def test_rgss_against_reference_kernels_when_present():
     assert bool((r.state("point_list", (R,), torch.int32) == st.t["point_list"][:R]).all())
     assert bool((r.state("ranges", (T, 2), torch.int32) == st.t["ranges"]).all())
     assert bool((r.state("n_contrib", (H * W,), torch.int32) == st.t["n_contrib"]).all())
-    errs = {k: float((out[k] - rout[k]).abs().max()) for k in ("color", "normal", "opacity", "feature")}
-    # depth = D / (1 - T) (rgss forward.cu:529): the division amplifies the last-bit differences of the blended
-    # sum D by 1/opacity, so the 1e-5 budget is applied to the blended quantity D = depth * opacity.
-    errs["depth*opacity"] = float(((out["depth"] - rout["depth"]) * rout["opacity"]).abs().max())
-    # surface_xyz divides the normalised depth by the opacity once more (rgss forward.cu:538-560)
-    errs["surface_xyz*opacity^2"] = float(((out["surface_xyz"] - rout["surface_xyz"]) * rout["opacity"] ** 2).abs().max())
+    # the alpha chain replays the reference build's contraction (common.cuh: eval_alpha<RGSS>), so the blended images,
+    # the normalised depth D / (1 - T) (rgss forward.cu:529) and the back-projected surface position are held to the
+    # plain 1e-5 absolute budget (round 1 applied it to depth * opacity)
+    errs = {k: float((out[k] - rout[k]).abs().max()) for k in ("color", "normal", "opacity", "feature", "depth")}
+    # surface_xyz divides the normalised depth by the opacity once more (rgss forward.cu:538-560): |xyz| reaches 1e3 where
+    # the opacity is ~1/255, so its budget is relative
+    sx = (out["surface_xyz"] - rout["surface_xyz"]).abs() / (1.0 + rout["surface_xyz"].abs())
+    errs["surface_xyz(rel)"] = float(sx.max())
     assert all(v <= 1e-5 for v in errs.values()), str(errs)
     # pseudo normal: normalised cross product of Sobel differences -- ill-conditioned where the surface
     # position is flat/background; compare where the reference's own vector is well defined
