@@ -329,7 +329,11 @@ def measure_train(args, ctx: Ctx, clocks: ClockSampler) -> dict:
         # by CUDA events on the launching stream (events cannot be timed inside a replayed graph)
         _lib.timing_enable(True)
         for i in range(min(args.steps, 8)):
-            eager_step(args.warmup + i)
+            if runner.fused:   # the step's own kernel sequence, launched outside the graph
+                runner.load_inputs(cam_dev[((args.warmup + i) * world + rank) % N_VIEWS], gt_dev[i % len(gt_dev)])
+                runner.fs.enqueue()
+            else:
+                eager_step(args.warmup + i)
         torch.cuda.synchronize()
     _lib.timing_enable(False)
     ktimes = {k: _lib.timing_collect(k) for k in ("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd", "preprocess",
@@ -351,6 +355,7 @@ def measure_train(args, ctx: Ctx, clocks: ClockSampler) -> dict:
             want = bucket.flat.clone()
             dist.all_reduce(want)
             if bucket.segment_peer is not None:
+                bucket.segment_peer.begin_segments()
                 nseg = len(bucket.seg_bounds)
                 for k, (lo, hi) in enumerate(bucket.seg_bounds):
                     bucket.segment_peer.reduce_segment(k, lo, hi, last=(k == nseg - 1))
