@@ -86,11 +86,13 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    // try_wait suspends the warp in hardware up to the time hint; the polling loop around it only runs when the
+    // hardware returns early. Replacing it by a nanosleep back-off measured slower (profiles/r02/composite_bwd_experiments.txt)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   // suspend-time hint: sleep, do not spin
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
         "@p bra MBAR_DONE;\n"
         "bra MBAR_WAIT;\n"
         "MBAR_DONE:\n"

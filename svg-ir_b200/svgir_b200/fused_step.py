@@ -18,9 +18,9 @@ one stream. `FusedTrainStep` is the same iteration for a caller that owns the wh
     memory, N > 1) on the side stream under the shading backward. Forks and joins are events, so the whole step
     captures into one CUDA graph (pipeline.GraphedTrainingStep).
 
-Same arithmetic as the autograd path: identical kernels; the only numerical difference is the view direction, which
-is normalised once (in the kernel) instead of twice (torch, then the kernel): <= 1 ulp on the direction.
-tests/test_fused_step_gpu.py compares loss, images and every gradient with `pipeline.training_step`.
+Same arithmetic as the autograd path (pipeline.FUSED_VIEWDIRS: it evaluates the view direction inside the shading
+kernel too): identical kernels on identical inputs, bit-identical images; gradients differ by the order of the atomic
+additions only. tests/test_fused_step_gpu.py compares loss, images and every gradient with `pipeline.training_step`.
 """
 from __future__ import annotations
 

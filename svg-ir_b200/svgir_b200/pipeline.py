@@ -114,6 +114,8 @@ def model_from_scene(cloud, mats, device, requires_grad=True) -> SurfelModel:
     return m
 
 
+FUSED_VIEWDIRS = True
+
 # render_view, eval branch: True = the G-buffer resolve tail runs as one CUDA kernel (losses.resolve_eval) when no
 # gradient is being recorded; False = the torch mirror of gaussian_renderer/svgss.py:187-262.
 FUSED_RESOLVE = True
@@ -145,12 +147,21 @@ def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: 
         raster_settings = raster_settings._replace(prestate=prestate)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
 
-    viewdirs = torch.nn.functional.normalize(cam.camera_center - means3D, dim=-1)
-    # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel
-    features, vfeatures = shading.shade_and_pack(
-        pc.base_color, pc.roughness, pc.shading_normal, viewdirs, pc.radiance, env_light, pc.visibility,
-        pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
-        work=work)
+    # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel. FUSED_VIEWDIRS: the view
+    # direction F.normalize(camera_center - means3D) of svgss.py:95 is evaluated inside the kernel (and its gradient
+    # returned for means3D) instead of by torch ops around it -- the same code path fused_step.FusedTrainStep uses,
+    # so both give bit-identical images; False = torch normalise, then the kernel (the reference's op order)
+    if FUSED_VIEWDIRS:
+        features, vfeatures = shading.shade_and_pack(
+            pc.base_color, pc.roughness, pc.shading_normal, None, pc.radiance, env_light, pc.visibility,
+            pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
+            work=work, means3D=means3D, campos=cam.camera_center)
+    else:
+        viewdirs = torch.nn.functional.normalize(cam.camera_center - means3D, dim=-1)
+        features, vfeatures = shading.shade_and_pack(
+            pc.base_color, pc.roughness, pc.shading_normal, viewdirs, pc.radiance, env_light, pc.visibility,
+            pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
+            work=work)
 
     raw = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=pc.shs, colors_precomp=None, opacities=pc.opacity,

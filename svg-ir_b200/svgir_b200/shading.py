@@ -210,12 +210,16 @@ class _ShadePackedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
-                incident_areas, env, metallic, view3x3, env_mode, transform, is_training, debug, work=None):
+                incident_areas, env, metallic, view3x3, env_mode, transform, is_training, debug, work=None,
+                means3D=None, campos=None):
         if not base_color.is_cuda:
             raise RuntimeError("svgir_b200 shading needs CUDA tensors (no CPU fallback)")
         L = _L()
         dev = base_color.device
         N, Ns = incident_dirs.shape[0], incident_dirs.shape[1]
+        if viewdirs is None and (means3D is None or campos is None):
+            raise ValueError("shade_and_pack: pass viewdirs, or means3D + campos (the kernel then evaluates "
+                             "normalize(campos - means3D), gaussian_renderer/svgss.py:95)")
         if work is not None:
             wl, wc = work
             if wl.dtype != torch.int32 or wc.dtype != torch.int32 or wl.numel() < N or not wl.is_contiguous():
@@ -224,7 +228,8 @@ class _ShadePackedFn(torch.autograd.Function):
         t = dict(base_color=_c(base_color), roughness=_c(roughness), normals=_c(normals), viewdirs=_c(viewdirs),
                  radiance=_c(radiance), visibility=_c(visibility), incident_dirs=_c(incident_dirs),
                  incident_areas=_c(incident_areas), env=_c(env), metallic=_c(metallic), transform=_c(transform),
-                 view3x3=_c(view3x3))
+                 view3x3=_c(view3x3), means3D=_c(means3D) if viewdirs is None else None,
+                 campos=_c(campos) if viewdirs is None else None)
         He, We = t["env"].shape[0], t["env"].shape[1]
         f32 = dict(dtype=torch.float32, device=dev)
         S, VS = (4, 52) if is_training else (7, 64)
@@ -235,7 +240,8 @@ class _ShadePackedFn(torch.autograd.Function):
         cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
                       _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]),
-                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None)
+                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None,
+                      _p(t["means3D"]), _p(t["campos"]), None)
         vp, fp = vfeats.data_ptr(), feats.data_ptr()
         # sums saved for backward: un-split total in training (only pbr / diffuse carry gradients there)
         sums = torch.empty((1 if is_training else 2, N, 12), **f32)
@@ -251,9 +257,11 @@ class _ShadePackedFn(torch.autograd.Function):
         ctx.cfg = (N, Ns, He, We, int(env_mode), int(bool(debug)), bool(is_training))
         ctx.has = (metallic is not None, transform is not None)
         ctx.work = work
-        ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], t["viewdirs"], t["radiance"],
+        ctx.fused_view = viewdirs is None
+        vsrc = t["viewdirs"] if viewdirs is not None else t["means3D"]
+        ctx.save_for_backward(*[x for x in (t["base_color"], t["roughness"], t["normals"], vsrc, t["radiance"],
                                             t["visibility"], t["incident_dirs"], t["incident_areas"], t["env"],
-                                            t["view3x3"], sums, t["metallic"], t["transform"]) if x is not None])
+                                            t["view3x3"], sums, t["metallic"], t["transform"], t["campos"]) if x is not None])
         return feats, vfeats
 
     @staticmethod
@@ -264,6 +272,9 @@ class _ShadePackedFn(torch.autograd.Function):
         rest = saved[11:]
         metallic = rest.pop(0) if ctx.has[0] else None
         transform = rest.pop(0) if ctx.has[1] else None
+        means3D = campos = None
+        if ctx.fused_view:   # the fourth saved tensor is means3D; the view direction is evaluated in the kernel
+            means3D, viewdirs, campos = viewdirs, None, rest.pop(0)
         N, Ns, He, We, env_mode, debug, is_training = ctx.cfg
         dev = base_color.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -276,7 +287,8 @@ class _ShadePackedFn(torch.autograd.Function):
         d_base = alloc((N, 12), **f32)
         d_rough = alloc((N, 4), **f32)
         d_norm = alloc((N, 4, 3), **f32)
-        d_view = alloc((N, 3), **f32)
+        d_view = alloc((N, 3), **f32) if not ctx.fused_view else None
+        d_xyz = torch.zeros((N, 3), **f32) if ctx.fused_view else None   # the kernel ADDS -d/d(campos - means3D)
         d_rad = alloc((N, Ns, 3), **f32) if need[4] else None
         d_vis = alloc(tuple(visibility.shape), **f32) if need[5] else None
         d_env = torch.zeros((He, We, 3), **f32) if need[8] else None
@@ -285,7 +297,8 @@ class _ShadePackedFn(torch.autograd.Function):
         cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
         cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
                       _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), _p(view3x3),
-                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None)
+                      _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None,
+                      _p(means3D), _p(campos), None)
         vp, fp = g_vfeats.data_ptr(), g_feats.data_ptr()
         if is_training:
             gin = (vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None)
@@ -293,24 +306,29 @@ class _ShadePackedFn(torch.autograd.Function):
             gin = (vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None)
         cg = ShadeGrads(*gin, _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad), _p(d_vis),
                         _p(d_env), vp + 4 * 12, _p(sums[0]), _p(sums[1]) if sums.shape[0] > 1 else None,
-                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, VS, S, S, 0)
+                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, VS, S, S, 0, _p(d_xyz))
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
         if need[6] or need[7]:
             raise NotImplementedError("svgir_b200 shading: no gradients w.r.t. incident_dirs / incident_areas")
-        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None, None, None, None)
+        return (d_base, d_rough, d_norm, d_view, d_rad, d_vis, None, None, d_env, d_met, None, None, None, None, None, None,
+                d_xyz, None)
 
 
 def shade_and_pack(base_color, roughness, normals, viewdirs, radiance, env_light, visibility, incident_dirs,
-                   incident_areas, view3x3, is_training=True, metallic=None, debug=False, work=None):
+                   incident_areas, view3x3, is_training=True, metallic=None, debug=False, work=None,
+                   means3D=None, campos=None):
     """(features [N,S], vfeatures [N,VS]) exactly as render_view packs them (svgss.py:141-166), computed by
     one fused kernel. view3x3 = world_view_transform[:3,:3].
     work = (surfel_list int32 [N], count int32 [1]) restricts shading (and its backward) to the listed
-    surfels -- e.g. the rasteriser's list of surfels that survive culling; all other rows are zero."""
+    surfels -- e.g. the rasteriser's list of surfels that survive culling; all other rows are zero.
+    viewdirs=None with means3D [N,3] + campos [3]: the kernels evaluate normalize(campos - means3D) (svgss.py:95)
+    themselves and the backward returns the resulting gradient for means3D (no torch normalise / backward kernels)."""
     env, mode, tr = env_of(env_light)
     return _ShadePackedFn.apply(base_color, roughness, normals, viewdirs, radiance, visibility, incident_dirs,
-                                incident_areas, env, metallic, view3x3, mode, tr, bool(is_training), debug, work)
+                                incident_areas, env, metallic, view3x3, mode, tr, bool(is_training), debug, work,
+                                means3D, campos)
 
 
 class _DirectLightFn(torch.autograd.Function):
