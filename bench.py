@@ -211,7 +211,8 @@ def make_peer_bucket(ctx: Ctx, make_bucket):
     ok = torch.ones(1, device=ctx.dev)
     peer, note = None, None
     try:
-        import torch.distributed._symmetric_memory  # noqa: F401  (import failures are rank-local)
+        import importlib
+        importlib.import_module("torch.distributed._symmetric_memory")   # import failures are rank-local
         peer = svdist.PeerAllReduce(ctx.dev)
     except Exception as e:  # noqa: BLE001
         ok.zero_()

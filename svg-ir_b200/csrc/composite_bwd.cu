@@ -312,7 +312,12 @@ __global__ void __launch_bounds__(TILE_PIX) composite_bwd_kernel(
 // so it goes straight to L2 as one scalar and one 128-bit fire-and-forget reduction instruction per
 // (warp, instance) -- no warp-private accumulators, no flush pass, one barrier pair per 32 instances, and
 // 46 KB instead of 81 KB of shared memory per CTA (4 resident CTAs per SM instead of 2).
+#ifndef LBATCH
 #define LBATCH 32
+#endif
+#ifndef LMINB
+#define LMINB 3
+#endif
 #ifndef LSTAGES
 #define LSTAGES 3   // staging ring depth of the lane kernel
 #endif
@@ -334,7 +339,7 @@ struct LaneBwdLayout {
 };
 
 template <int S_T, int NV_T, bool RGSS>
-__global__ void __launch_bounds__(TILE_PIX, 3) composite_bwd_lane_kernel(
+__global__ void __launch_bounds__(TILE_PIX, LMINB) composite_bwd_lane_kernel(
     const svgir_raster_cfg c, const float* __restrict__ features, const float* __restrict__ vfeatures,
     const float4* __restrict__ rec, const uint2* __restrict__ ranges,
     const uint32_t* __restrict__ point_list, const float* __restrict__ final_T,

@@ -205,9 +205,32 @@ def _peer_worker(rank, world, port, q):
                 pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v % 2], zero_grad=False)
             runner_s(cams[views[rank]], gts[views[rank] % 2])
             torch.cuda.synchronize()
-            assert sorted(bucket_s.overlap_log) == [0, 1], bucket_s.overlap_log
+            assert runner_s.fused, "the peer-segment exchange is part of the fused step (fused_step.FusedTrainStep)"
             for a, b in zip(params_s, pc_e.trainable() + [env_e]):
                 step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+        # matched re-capture of the fused step: rank 1 re-captures with no slack in its bins, then the surfels grow 1.2x
+        # -- rank 1 overflows, rank 0 does not; the flag summed with the last gradient segment makes BOTH re-run
+        from svgir_b200 import raster
+        caps = runner_s.captures
+        old = (raster.ASYNC_SLACK, raster.ASYNC_MARGIN)
+        if rank == 1:
+            raster._CAP_HINT.clear()   # the eager reference steps above left a roomy capacity hint for this shape
+            raster.ASYNC_SLACK, raster.ASYNC_MARGIN = 1.0, 16
+        runner_s.graph, runner_s.fs = None, None
+        runner_s(cams[rank], gts[rank])
+        raster.ASYNC_SLACK, raster.ASYNC_MARGIN = old
+        with torch.no_grad():
+            pc_s.scaling.mul_(1.2)
+            pc_e.scaling.mul_(1.2)
+        runner_s(cams[rank], gts[rank])
+        torch.cuda.synchronize()
+        assert runner_s.captures - caps == 2, (rank, runner_s.captures - caps)
+        for t in pc_e.trainable() + [env_e]:
+            t.grad = None
+        for v in range(world):
+            pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v], zero_grad=False)
+        for a, b in zip(params_s, pc_e.trainable() + [env_e]):
+            step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
         q.put((rank, out, step_worst, None))
         torch.cuda.synchronize()
         dist.barrier()
