@@ -419,14 +419,25 @@ int svgir_render_equation_sh_backward(const svgir_req_sh_cfg* cfg, const svgir_r
  * Replaces the torch code between the rasteriser's forward and backward: gaussian_renderer/svgss.py:187-233
  * (divide feature/vfeature by opacity.clamp_min(1e-5), split, "pbr" = rgb_to_srgb(pbr*o + (1-o)*bg),
  * utils/graphics_utils.py:198-213) and the L1 terms of calculate_loss (svgss.py:280-294,
- * utils/loss_utils.py:33-34) plus the 0.02-weighted normal-consistency term (svgss.py:313):
- *   loss = mean|color-gt| + lambda_pbr*mean|pbr_srgb-gt| + lambda_normal*mean(1 - <n_shade, geo_normal>).
+ * utils/loss_utils.py:33-34) plus the 0.02-weighted surface term (svgss.py:300-313):
+ *   loss = mean|color-gt| + lambda_pbr*mean|pbr_srgb-gt| + lambda_normal*L_n,
+ *   normal_mode 1 (the reference's term): L_n = cos_loss(n_shade, depth2normal(depth, mask, camera))
+ *       = mean over the pixels with cos < 1 of (1 - <n_shade, d2n>)   (utils/loss_utils.py:117-119),
+ *       d2n = normalised sum of the four cross products of the back-projected depth differences to the upper / left /
+ *       lower / right neighbour, replicate padding, masked (utils/image_utils.py:61-125); its gradient flows into the
+ *       shading normal AND into the rendered depth;
+ *   normal_mode 0 (round-1 stand-in, kept for A/B): L_n = mean(1 - <n_shade, geo_normal>) over all pixels.
  * All images are channel-major [C,H,W] fp32 device pointers (the rasteriser's raw outputs). */
 typedef struct svgir_train_loss_cfg {
     int32_t W, H, S, NV;            /* raw G-buffer: feature [S,H,W], vfeature [NV,H,W] (NV = VS/4) */
     int32_t pbr_ch, normal_ch;      /* first vfeature channel of pbr (0) and of the shading normal (6), svgss.py:210-213 */
     float lambda_pbr, lambda_normal;
     const float* bg;                /* [3] device */
+    int32_t normal_mode;            /* see above */
+    /* depth2normal camera terms (image_utils.py:73-81): x is divided by focal_x = fov2focal(FoVy, H) and y by
+     * focal_y = fov2focal(FoVx, W) -- the reference's own pairing --, the principal point is prcppoint * (W, H) */
+    float inv_focal_x, inv_focal_y, cx, cy;
+    int32_t reserved_;
 } svgir_train_loss_cfg;
 
 typedef struct svgir_train_loss_in {
@@ -435,25 +446,47 @@ typedef struct svgir_train_loss_in {
     const float* opacity;     /* [1,H,W] */
     const float* vfeature;    /* [NV,H,W] raw (opacity-premultiplied) */
     const float* gt;          /* [3,H,W] */
+    const float* depth;       /* [1,H,W] rasteriser's depth output; required with normal_mode 1 */
+    const float* mask;        /* [1,H,W] image mask (nonzero = inside), or NULL = all ones */
 } svgir_train_loss_in;
 
 typedef struct svgir_train_loss_grads {   /* dL/d(rasteriser outputs); every element of a non-NULL image is written */
     float* color;       /* [3,H,W] */
     float* geo_normal;  /* [3,H,W] */
-    float* depth;       /* [1,H,W] (zeros; may be NULL) */
+    float* depth;       /* [1,H,W] (zeros in normal_mode 0, may then be NULL; required with normal_mode 1) */
     float* opacity;     /* [1,H,W] */
     float* feature;     /* [S,H,W] (zeros; may be NULL) */
     float* vfeature;    /* [NV,H,W] */
 } svgir_train_loss_grads;
 
 int svgir_train_loss_blocks(int W, int H);
-/* loss[4] = total, l1, l1_pbr, normal term; partials: 3*svgir_train_loss_blocks floats of scratch;
- * counter: one zero-initialised u32 (left at zero on return). Deterministic summation order. */
+/* loss[8] = total, l1, l1_pbr, normal term, number of pixels in the normal term's mean, 3 unused; partials:
+ * 4*svgir_train_loss_blocks floats of scratch; counter: one zero-initialised u32 (left at zero on return).
+ * Deterministic summation order. */
 int svgir_train_loss_forward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in, float* loss,
                              float* partials, unsigned int* counter, void* stream);
-/* grad_loss: device scalar dL/dloss (NULL = 1). */
+/* grad_loss: device scalar dL/dloss (NULL = 1). loss: the buffer svgir_train_loss_forward filled (normal_mode 1
+ * reads the pixel count of the cos_loss mean from loss[4]; may be NULL in normal_mode 0). */
 int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in,
-                              const float* grad_loss, const svgir_train_loss_grads* g, void* stream);
+                              const float* grad_loss, const float* loss, const svgir_train_loss_grads* g, void* stream);
+
+/* ---- smoothness terms of calculate_loss (gaussian_renderer/svgss.py:366-390) --------------------------------
+ * first_order_edge_aware_loss(data * mask, img * mask) (utils/loss_utils.py:103-104): with the normalised Sobel
+ * gradient of kornia.filters.spatial_gradient (order 1; kernels / 8, replicate padding),
+ *   loss = mean over [C,H,W] of |d/dx data| exp(-|d/dx img|) + |d/dy data| exp(-|d/dy img|).
+ * data, img [C,H,W]; mask [1,H,W] or NULL. forward: loss_out[0]; partials = svgir_edge_aware_blocks floats,
+ * counter one zero-initialised u32. backward: d_data [C,H,W] = grad_out[0] (NULL = 1) * dloss/ddata (img: no gradient;
+ * the library zero-fills d_data, then scatters). */
+int svgir_edge_aware_blocks(int C, int H, int W);
+int svgir_edge_aware_forward(int C, int H, int W, const float* data, const float* img, const float* mask,
+                             float* loss_out, float* partials, unsigned int* counter, void* stream);
+int svgir_edge_aware_backward(int C, int H, int W, const float* data, const float* img, const float* mask,
+                              const float* grad_out, float* d_data, void* stream);
+/* tv_loss (utils/loss_utils.py:112-116) of x[c][h][w] addressed with element strides (sc, sh, sw), so the env map
+ * [He,We,3] is read in place as env.permute(2,0,1) (svgss.py:388): mean((x[h+1]-x[h])^2) + mean((x[w+1]-x[w])^2).
+ * One launch computes loss_out[0] and, if d_x is not NULL, d_x (same strides) = grad_out[0] (NULL = 1) * dloss/dx. */
+int svgir_tv_loss(int C, int H, int W, long long sc, long long sh, long long sw, const float* x, const float* grad_out,
+                  float* loss_out, float* d_x, void* stream);
 
 /* ---- G-buffer resolve of an evaluation / relighting frame -----------------------------------------
  * The torch tail of render_view's eval branch (gaussian_renderer/svgss.py:187-262 with is_training=False:

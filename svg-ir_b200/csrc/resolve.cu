@@ -60,6 +60,55 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return r;  // valid in warp 0
 }
 
+// ---- depth2normal (utils/image_utils.py:61-125) -------------------------------------------------------------------
+// Camera-space position of pixel (x, y): ((x - cx) d / focal_x, (y - cy) d / focal_y, d). With replicate padding the
+// neighbour of a border pixel is the pixel itself. p_c = P_c m_c; p_k = (P_k - p_c) m_k for k = up, left, bottom,
+// right; n = p_u x p_l + p_r x p_u + p_b x p_r + p_l x p_b; d2n = n / max(|n|, 1e-12) * m_c.
+struct D2N {
+    int iu, il, ib, ir;            // pixel indices of the four (clamped) neighbours
+    float mc, mu, ml, mb, mr;      // masks as 0 / 1
+    float pu[3], pl[3], pb[3], pr[3];
+    float n[3], len;               // un-normalised normal and max(|n|, eps)
+    float out[3];                  // d2n
+};
+
+__device__ __forceinline__ void cam_pos(const svgir_train_loss_cfg& c, const svgir_train_loss_in& in, int x, int y, float P[3]) {
+    const float d = in.depth[(size_t)y * c.W + x];
+    P[0] = ((float)x - c.cx) * d * c.inv_focal_x;
+    P[1] = ((float)y - c.cy) * d * c.inv_focal_y;
+    P[2] = d;
+}
+__device__ __forceinline__ float mask_at(const svgir_train_loss_in& in, int idx) {
+    return in.mask ? (in.mask[idx] != 0.f ? 1.f : 0.f) : 1.f;
+}
+__device__ __forceinline__ void cross3(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ void d2n_eval(const svgir_train_loss_cfg& c, const svgir_train_loss_in& in, int x, int y, D2N& r) {
+    const int W = c.W, H = c.H;
+    const int yu = max(y - 1, 0), yb = min(y + 1, H - 1), xl = max(x - 1, 0), xr = min(x + 1, W - 1);
+    r.iu = yu * W + x; r.il = y * W + xl; r.ib = yb * W + x; r.ir = y * W + xr;
+    r.mc = mask_at(in, y * W + x); r.mu = mask_at(in, r.iu); r.ml = mask_at(in, r.il);
+    r.mb = mask_at(in, r.ib); r.mr = mask_at(in, r.ir);
+    float Pc[3], Pu[3], Pl[3], Pb[3], Pr[3];
+    cam_pos(c, in, x, y, Pc); cam_pos(c, in, x, yu, Pu); cam_pos(c, in, xl, y, Pl);
+    cam_pos(c, in, x, yb, Pb); cam_pos(c, in, xr, y, Pr);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float pc = Pc[k] * r.mc;
+        r.pu[k] = (Pu[k] - pc) * r.mu; r.pl[k] = (Pl[k] - pc) * r.ml;
+        r.pb[k] = (Pb[k] - pc) * r.mb; r.pr[k] = (Pr[k] - pc) * r.mr;
+    }
+    float a[3], b[3], d[3], e[3];
+    cross3(r.pu, r.pl, a); cross3(r.pr, r.pu, b); cross3(r.pb, r.pr, d); cross3(r.pl, r.pb, e);
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.n[k] = ((a[k] + b[k]) + d[k]) + e[k];
+    r.len = fmaxf(sqrtf(r.n[0] * r.n[0] + r.n[1] * r.n[1] + r.n[2] * r.n[2]), 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.out[k] = r.n[k] / r.len * r.mc;
+}
+
 __global__ void __launch_bounds__(LOSS_THREADS) train_loss_fwd_kernel(const svgir_train_loss_cfg c, const svgir_train_loss_in in,
                                                                       float* __restrict__ loss, float* __restrict__ partials,
                                                                       unsigned int* __restrict__ counter) {
@@ -68,7 +117,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_fwd_kernel(const svgi
     const size_t HW = (size_t)c.W * c.H;
     const size_t p = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
     const float bg[3] = {c.bg[0], c.bg[1], c.bg[2]};
-    float l1 = 0.f, l1p = 0.f, nn = 0.f;
+    float l1 = 0.f, l1p = 0.f, nn = 0.f, cnt = 0.f;
     if (p < HW) {
         PixelTerms t;
         pixel_terms(c, in, HW, p, bg, t);
@@ -80,13 +129,22 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_fwd_kernel(const svgi
             l1p += fabsf(t.s[k] - g);
             dot += t.shn[k] * in.geo_normal[k * HW + p];
         }
-        nn = 1.0f - dot;
+        if (c.normal_mode == 0) {
+            nn = 1.0f - dot;
+            cnt = 1.f;
+        } else {   // cos_loss(n_shade, depth2normal(depth)): only pixels with cos < cos(0) = 1 enter the mean
+            D2N r;
+            d2n_eval(c, in, (int)(p % c.W), (int)(p / c.W), r);
+            const float cs = (t.shn[0] * r.out[0] + t.shn[1] * r.out[1]) + t.shn[2] * r.out[2];
+            if (cs < 1.0f) { nn = 1.0f - cs; cnt = 1.f; }
+        }
     }
-    const float a = block_sum(l1, red), b = block_sum(l1p, red), d = block_sum(nn, red);
+    const float a = block_sum(l1, red), b = block_sum(l1p, red), d = block_sum(nn, red), e = block_sum(cnt, red);
     if (threadIdx.x == 0) {
-        partials[3 * blockIdx.x + 0] = a;
-        partials[3 * blockIdx.x + 1] = b;
-        partials[3 * blockIdx.x + 2] = d;
+        partials[4 * blockIdx.x + 0] = a;
+        partials[4 * blockIdx.x + 1] = b;
+        partials[4 * blockIdx.x + 2] = d;
+        partials[4 * blockIdx.x + 3] = e;
         __threadfence();
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
@@ -94,17 +152,19 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_fwd_kernel(const svgi
     if (!last) return;
     __threadfence();
     // last block: fixed-order sum of the per-block partials (deterministic across runs)
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += LOSS_THREADS) {
-        s0 += __ldcg(partials + 3 * i);
-        s1 += __ldcg(partials + 3 * i + 1);
-        s2 += __ldcg(partials + 3 * i + 2);
+        s0 += __ldcg(partials + 4 * i);
+        s1 += __ldcg(partials + 4 * i + 1);
+        s2 += __ldcg(partials + 4 * i + 2);
+        s3 += __ldcg(partials + 4 * i + 3);
     }
-    s0 = block_sum(s0, red); s1 = block_sum(s1, red); s2 = block_sum(s2, red);
+    s0 = block_sum(s0, red); s1 = block_sum(s1, red); s2 = block_sum(s2, red); s3 = block_sum(s3, red);
     if (threadIdx.x == 0) {
         const float n3 = 3.0f * (float)HW;
-        const float t0 = s0 / n3, t1 = s1 / n3, t2 = s2 / (float)HW;
-        loss[1] = t0; loss[2] = t1; loss[3] = t2;
+        // an empty selection gives torch's mean of an empty tensor: NaN (loss_utils.py:119)
+        const float t0 = s0 / n3, t1 = s1 / n3, t2 = s2 / s3;
+        loss[1] = t0; loss[2] = t1; loss[3] = t2; loss[4] = s3;
         loss[0] = t0 + c.lambda_pbr * t1 + c.lambda_normal * t2;
         *counter = 0;  // ready for the next launch (CUDA-graph replay)
     }
@@ -112,6 +172,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_fwd_kernel(const svgi
 
 __global__ void __launch_bounds__(LOSS_THREADS) train_loss_bwd_kernel(const svgir_train_loss_cfg c, const svgir_train_loss_in in,
                                                                       const float* __restrict__ grad_loss,
+                                                                      const float* __restrict__ loss,
                                                                       const svgir_train_loss_grads g) {
     const size_t HW = (size_t)c.W * c.H;
     const size_t p = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x;
@@ -120,9 +181,21 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_bwd_kernel(const svgi
     const float bg[3] = {c.bg[0], c.bg[1], c.bg[2]};
     PixelTerms t;
     pixel_terms(c, in, HW, p, bg, t);
-    const float k1 = up / (3.0f * (float)HW), kp = up * c.lambda_pbr / (3.0f * (float)HW), kn = -up * c.lambda_normal / (float)HW;
+    const float k1 = up / (3.0f * (float)HW), kp = up * c.lambda_pbr / (3.0f * (float)HW);
+    float kn = -up * c.lambda_normal / (float)HW;
     float go = 0.f, ginv = 0.f;
     float gvf_pbr[3], gvf_shn[3];
+    // the other factor of the normal term: the rasteriser's geometric normal (mode 0) or depth2normal (mode 1)
+    float nref[3] = {0.f, 0.f, 0.f};
+    bool active = true;
+    D2N r;
+    if (c.normal_mode != 0) {
+        d2n_eval(c, in, (int)(p % c.W), (int)(p / c.W), r);
+        const float cs = (t.shn[0] * r.out[0] + t.shn[1] * r.out[1]) + t.shn[2] * r.out[2];
+        active = cs < 1.0f;
+        kn = active ? -up * c.lambda_normal / loss[4] : 0.f;
+        nref[0] = r.out[0]; nref[1] = r.out[1]; nref[2] = r.out[2];
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float gt = in.gt[k * HW + p];
@@ -133,9 +206,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_bwd_kernel(const svgi
         const float gx = t.pass[k] ? gs * srgb_slope(t.x[k]) : 0.f;
         const float gpbr = gx * t.o;
         go += gx * (t.pbr[k] - bg[k]);
-        const float gn = in.geo_normal[k * HW + p];
+        const float gn = c.normal_mode == 0 ? in.geo_normal[k * HW + p] : nref[k];
         const float gshn = kn * gn;
-        g.geo_normal[k * HW + p] = kn * t.shn[k];
+        g.geo_normal[k * HW + p] = c.normal_mode == 0 ? kn * t.shn[k] : 0.f;
         gvf_pbr[k] = gpbr * t.inv;
         gvf_shn[k] = gshn * t.inv;
         // d(1/max(o,eps)): VF_k = raw_k * inv
@@ -143,7 +216,48 @@ __global__ void __launch_bounds__(LOSS_THREADS) train_loss_bwd_kernel(const svgi
     }
     if (t.o >= 1e-5f) go -= ginv * t.inv * t.inv;
     g.opacity[p] = go;
-    if (g.depth) g.depth[p] = 0.f;
+    if (c.normal_mode == 0) {
+        if (g.depth) g.depth[p] = 0.f;
+    } else if (active && r.mc != 0.f) {
+        // d(1 - cos)/d(d2n) = -n_shade; through the normalisation, the four cross products and the back-projection
+        // into the depth of this pixel and of its four neighbours (g.depth was zero-filled by the launcher)
+        float dn[3];
+        {
+            const float dh[3] = {kn * t.shn[0] * r.mc, kn * t.shn[1] * r.mc, kn * t.shn[2] * r.mc};
+            const float il = 1.0f / r.len;
+            const float nh[3] = {r.n[0] * il, r.n[1] * il, r.n[2] * il};
+            const float dd = nh[0] * dh[0] + nh[1] * dh[1] + nh[2] * dh[2];
+            const bool clamped = r.len <= 1e-12f;   // n / eps: linear
+#pragma unroll
+            for (int k = 0; k < 3; k++) dn[k] = clamped ? dh[k] * il : (dh[k] - nh[k] * dd) * il;
+        }
+        float dpu[3], dpl[3], dpb[3], dpr[3], t0[3], t1[3];
+        cross3(r.pl, dn, t0); cross3(dn, r.pr, t1);      // n = pu x pl + pr x pu + ...
+#pragma unroll
+        for (int k = 0; k < 3; k++) dpu[k] = t0[k] + t1[k];
+        cross3(dn, r.pu, t0); cross3(r.pb, dn, t1);      // ... pu x pl + pl x pb
+#pragma unroll
+        for (int k = 0; k < 3; k++) dpl[k] = t0[k] + t1[k];
+        cross3(r.pr, dn, t0); cross3(dn, r.pl, t1);      // pb x pr + pl x pb
+#pragma unroll
+        for (int k = 0; k < 3; k++) dpb[k] = t0[k] + t1[k];
+        cross3(r.pu, dn, t0); cross3(dn, r.pb, t1);      // pr x pu + pb x pr
+#pragma unroll
+        for (int k = 0; k < 3; k++) dpr[k] = t0[k] + t1[k];
+        float dPc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dpu[k] *= r.mu; dpl[k] *= r.ml; dpb[k] *= r.mb; dpr[k] *= r.mr;
+            dPc[k] = -(((dpu[k] + dpl[k]) + dpb[k]) + dpr[k]) * r.mc;
+        }
+        const int x = (int)(p % c.W), y = (int)(p / c.W);
+        auto push = [&](int idx, const float dP[3]) {
+            const int qx = idx % c.W, qy = idx / c.W;
+            const float v = ((float)qx - c.cx) * c.inv_focal_x * dP[0] + ((float)qy - c.cy) * c.inv_focal_y * dP[1] + dP[2];
+            if (v != 0.f) atomicAdd(g.depth + idx, v);
+        };
+        push(y * c.W + x, dPc); push(r.iu, dpu); push(r.il, dpl); push(r.ib, dpb); push(r.ir, dpr);
+    }
     if (g.feature)
         for (int k = 0; k < c.S; k++) g.feature[(size_t)k * HW + p] = 0.f;
     for (int k = 0; k < c.NV; k++) {
@@ -165,6 +279,7 @@ static int check_cfg(const svgir_train_loss_cfg* c, const svgir_train_loss_in* i
         set_error("train_loss: null input pointer");
         return SVGIR_ERR_INVALID;
     }
+    if (c->normal_mode != 0 && !in->depth) { set_error("train_loss: normal_mode 1 (depth2normal) needs the depth image"); return SVGIR_ERR_INVALID; }
     return SVGIR_OK;
 }
 
@@ -187,7 +302,8 @@ extern "C" int svgir_train_loss_forward(const svgir_train_loss_cfg* cfg, const s
 }
 
 extern "C" int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const svgir_train_loss_in* in,
-                                         const float* grad_loss, const svgir_train_loss_grads* g, void* stream) {
+                                         const float* grad_loss, const float* loss, const svgir_train_loss_grads* g,
+                                         void* stream) {
     using namespace svgir;
     int rc = check_cfg(cfg, in);
     if (rc) return rc;
@@ -197,7 +313,11 @@ extern "C" int svgir_train_loss_backward(const svgir_train_loss_cfg* cfg, const 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = svgir_train_loss_blocks(cfg->W, cfg->H);
-    { TimedScope ts_("train_loss_bwd", s); train_loss_bwd_kernel<<<nb, LOSS_THREADS, 0, s>>>(*cfg, *in, grad_loss, *g); }
+    if (cfg->normal_mode != 0) {
+        if (!loss || !g->depth) { set_error("train_loss_backward: normal_mode 1 needs the forward's loss buffer and a depth gradient image"); return SVGIR_ERR_INVALID; }
+        if (cudaMemsetAsync(g->depth, 0, sizeof(float) * (size_t)cfg->W * cfg->H, s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+    }
+    { TimedScope ts_("train_loss_bwd", s); train_loss_bwd_kernel<<<nb, LOSS_THREADS, 0, s>>>(*cfg, *in, grad_loss, loss, *g); }
     return check_launch("train_loss_bwd", false, s);
 }
 

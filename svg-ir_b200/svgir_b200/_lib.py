@@ -167,4 +167,5 @@ EXPORTED_SYMBOLS = [
     "svgir_peer_allreduce_range", "svgir_shade_reserve_sms",
     "svgir_ssim_blocks", "svgir_ssim_forward", "svgir_ssim_backward",
     "svgir_raster_bin", "svgir_raster_composite", "svgir_raster_backward_composite", "svgir_raster_backward_params",
+    "svgir_edge_aware_blocks", "svgir_edge_aware_forward", "svgir_edge_aware_backward", "svgir_tv_loss",
 ]

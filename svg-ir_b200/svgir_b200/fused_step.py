@@ -63,7 +63,8 @@ class FusedTrainStep:
 
     def __init__(self, pc, env_param: torch.Tensor, bg: torch.Tensor, cam, gt_image: torch.Tensor, bucket=None,
                  lambda_pbr: float = 1.0, lambda_normal: float = 0.02, zero_grads: bool = True,
-                 reduce_in_step: bool = False, capacity: Optional[int] = None):
+                 reduce_in_step: bool = False, capacity: Optional[int] = None, surface_term: str = "depth2normal",
+                 image_mask: Optional[torch.Tensor] = None):
         """pc: pipeline.SurfelModel; cam: pipeline.ViewCamera whose tensors are the step's STATIC camera inputs (copy a
         new view into cam.block before each step); gt_image: the static ground-truth buffer [3,H,W].
         bucket: dist.FlatGradBucket over pc.trainable() + [env_param] (default: a private one, so that all parameter
@@ -143,7 +144,7 @@ class FusedTrainStep:
                     "depth": torch.zeros((1, H, W), **f32), "opacity": torch.zeros((1, H, W), **f32),
                     "feature": torch.zeros((S, H, W), **f32), "vfeature": torch.zeros((NV, H, W), **f32)}
         self.gimg = {"color": torch.empty((3, H, W), **f32), "normal": torch.empty((3, H, W), **f32),
-                     "depth": torch.zeros((1, H, W), **f32), "opacity": torch.empty((1, H, W), **f32),
+                     "depth": torch.zeros((1, H, W), **f32), "opacity": torch.empty((1, H, W), **f32),  # depth: surface term
                      "feature": torch.zeros((S, H, W), **f32), "vfeature": torch.empty((NV, H, W), **f32)}
         self.feats = torch.zeros((P, S), **f32)
         self.vfeats = torch.zeros((P, VS), **f32)
@@ -152,12 +153,13 @@ class FusedTrainStep:
         self.env_act = torch.empty((He, We, 3), **f32)
         self.env_scratch = torch.empty((He, We, 4), **f32)
         self.sums = torch.empty((P, 12), **f32)
-        self.loss_out = torch.zeros(4, **f32)
+        self.loss_out = torch.zeros(8, **f32)
         nblk = int(self.L.svgir_train_loss_blocks(W, H))
-        self.loss_partials = torch.empty(3 * nblk, **f32)
+        self.loss_partials = torch.empty(4 * nblk, **f32)
         self.loss_counter = torch.zeros(1, **i32)
-        self.count_host = torch.zeros((2,), dtype=torch.int32).pin_memory()
-        self.flag_host = torch.zeros((1,), dtype=torch.float32).pin_memory() if self.reduce_in_step else None
+        # landing buffers of copies that are captured into CUDA graphs: never recycled (raster.pinned_forever)
+        self.count_host = raster.pinned_forever((2,), torch.int32)
+        self.flag_host = raster.pinned_forever((1,), torch.float32) if self.reduce_in_step else None
 
         # ---- C structs (pointers are static, so they are built once) ------------------------------------------------
         from .pipeline import _config_tensor
@@ -212,10 +214,18 @@ class FusedTrainStep:
                                      self.sums.data_ptr(), None, VS, S, S, 0)
         self._bind_grads()
 
-        self.lcfg = losses.TrainLossCfg(W, H, 0, NV, 0, 6, float(lambda_pbr), float(lambda_normal), self.bg.data_ptr())
+        # image loss: L1 terms + the reference's surface term cos_loss(normal, depth2normal(depth)) (svgss.py:280-313)
+        from .pipeline import camera_d2n_terms
+        ifx, ify, cx, cy = camera_d2n_terms(cam)
+        mode = losses.NORMAL_D2N if surface_term == "depth2normal" else losses.NORMAL_GEO
+        self.image_mask = image_mask.to(**f32).contiguous() if image_mask is not None else None
+        self.lcfg = losses.TrainLossCfg(W, H, 0, NV, 0, 6, float(lambda_pbr), float(lambda_normal), self.bg.data_ptr(),
+                                        mode, ifx, ify, cx, cy, 0)
         self.lin = losses.TrainLossIn(self.img["color"].data_ptr(), self.img["normal"].data_ptr(), self.img["opacity"].data_ptr(),
-                                      self.img["vfeature"].data_ptr(), self.gt.data_ptr())
-        self.lgr = losses.TrainLossGrads(self.gimg["color"].data_ptr(), self.gimg["normal"].data_ptr(), None,
+                                      self.img["vfeature"].data_ptr(), self.gt.data_ptr(), self.img["depth"].data_ptr(),
+                                      self.image_mask.data_ptr() if self.image_mask is not None else None)
+        self.lgr = losses.TrainLossGrads(self.gimg["color"].data_ptr(), self.gimg["normal"].data_ptr(),
+                                         self.gimg["depth"].data_ptr() if mode == losses.NORMAL_D2N else None,
                                          self.gimg["opacity"].data_ptr(), None, self.gimg["vfeature"].data_ptr())
         self.cap = 0
         self._alloc_bins(capacity if capacity else raster._CAP_HINT.get((dev.index, P, W, H), 0))
@@ -303,8 +313,8 @@ class FusedTrainStep:
             self.count_host.copy_(self.t["num_rendered"], non_blocking=True)
             chk(L.svgir_train_loss_forward(C.byref(self.lcfg), C.byref(self.lin), self.loss_out.data_ptr(),
                                            self.loss_partials.data_ptr(), self.loss_counter.data_ptr(), cs), "train_loss_forward")
-            chk(L.svgir_train_loss_backward(C.byref(self.lcfg), C.byref(self.lin), None, C.byref(self.lgr), cs),
-                "train_loss_backward")
+            chk(L.svgir_train_loss_backward(C.byref(self.lcfg), C.byref(self.lin), None, self.loss_out.data_ptr(),
+                                            C.byref(self.lgr), cs), "train_loss_backward")
             chk(L.svgir_raster_backward_composite(cfg, cin, cst, C.byref(self.rgrads), cs), "raster_backward_composite")
             # parameter backward of the rasteriser (+ the all-reduce of its gradient segment) on the side stream, under the
             # shading backward

@@ -225,11 +225,34 @@ def render_view(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Ten
     return res
 
 
-def image_loss(res: dict, gt_image: torch.Tensor, lambda_pbr: float = 1.0) -> torch.Tensor:
-    """The L1 part of calculate_loss (svgss.py:280-294) on the splatted colour and the PBR image;
-    SSIM / smoothness terms are application-side torch code."""
-    return (res["render"] - gt_image).abs().mean() + lambda_pbr * (res["pbr"] - gt_image).abs().mean() + \
-        0.02 * (1.0 - (res["normal"] * res["geo_normal"]).sum(0)).mean()
+def image_loss(res: dict, gt_image: torch.Tensor, lambda_pbr: float = 1.0, cam: Optional[ViewCamera] = None,
+               image_mask: Optional[torch.Tensor] = None, lambda_normal: float = 0.02) -> torch.Tensor:
+    """The part of calculate_loss (gaussian_renderer/svgss.py:265-313) that drives the hot path: the L1 terms on the
+    splatted colour and the PBR image (:280-294) and the 0.02-weighted surface term
+    cos_loss(rendered_normal, depth2normal(rendered_depth, image_mask, camera)) (:300-313) -- torch mirror of the
+    reference's ops (losses.depth2normal_torch / cos_loss_torch). With cam=None the round-1 stand-in
+    mean(1 - <normal, geo_normal>) is used instead of the surface term (A/B only). The SSIM, edge-aware and TV terms
+    are losses.fused_ssim / fused_edge_aware / fused_tv."""
+    l = (res["render"] - gt_image).abs().mean() + lambda_pbr * (res["pbr"] - gt_image).abs().mean()
+    if cam is None:
+        return l + lambda_normal * (1.0 - (res["normal"] * res["geo_normal"]).sum(0)).mean()
+    H, W = int(cam.image_height), int(cam.image_width)
+    d2n = losses.depth2normal_torch(res["depth"], image_mask, H, W, camera_d2n_terms(cam))
+    return l + lambda_normal * losses.cos_loss_torch(res["normal"], d2n)
+
+
+def camera_d2n_terms(cam: ViewCamera):
+    """depth2normal's camera terms (losses.d2n_camera_terms) of a ViewCamera; its principal point is read on the host
+    once per camera object (prcppoint is (0.5, 0.5) for every TensoIR camera)."""
+    t = getattr(cam, "_d2n_terms", None)
+    if t is None:
+        pp = [float(v) for v in cam.prcppoint.detach().cpu().tolist()] if not torch.cuda.is_current_stream_capturing() else [0.5, 0.5]
+        t = losses.d2n_camera_terms(int(cam.image_height), int(cam.image_width), cam.tanfovx, cam.tanfovy, pp)
+        try:
+            cam._d2n_terms = t
+        except Exception:
+            pass
+    return t
 
 
 def render_raw(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: torch.Tensor, scaling_modifier=1.0,
@@ -268,11 +291,12 @@ def training_step(cam: ViewCamera, pc: SurfelModel, env_param: torch.Tensor, bg,
     if fused_loss:
         res = render_raw(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
         loss, terms = losses.fused_train_loss(res["render"], res["geo_normal"], res["opacity"], res["raw_vfeature"],
-                                              gt_image, bg, lambda_pbr=1.0, lambda_normal=0.02)
+                                              gt_image, bg, lambda_pbr=1.0, lambda_normal=0.02, depth=res["depth"],
+                                              cam_terms=camera_d2n_terms(cam))
         res["loss_terms"] = terms
     else:
         res = render_view(cam, pc, (env_param, shading.MODE_LEARNABLE), bg, is_training=True)
-        loss = image_loss(res, gt_image)
+        loss = image_loss(res, gt_image, cam=cam)
     if overlap_bucket is not None:
         st = res.get("raster_state")
         if overlap_bucket.extra is not None and st is not None:
@@ -338,7 +362,7 @@ class GraphedTrainingStep:
         self.fused = FUSED_STEP if fused is None else bool(fused)
         if self.fused and self.reduce_in_graph and getattr(bucket, "segment_peer", None) is None:
             self.fused = False   # NCCL collectives inside the step are issued through the autograd hooks
-        self.flag_host = torch.zeros((1,), dtype=torch.float32).pin_memory() if self.reduce_in_graph else None
+        self.flag_host = raster.pinned_forever((1,), torch.float32) if self.reduce_in_graph else None
         dev = pc.xyz.device
         self.dev = dev
         self.cam = blocked_camera(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy,

@@ -101,11 +101,24 @@ _PINNED_NEXT = 0
 _CAPTURE_SLOTS: list = []  # dedicated pinned slots for forwards captured into CUDA graphs (allocated before capture)
 
 
+_PINNED_FOREVER: list = []
+
+
+def pinned_forever(shape, dtype) -> torch.Tensor:
+    """Page-locked landing buffer for copies that get captured into CUDA graphs. It is never returned to torch's
+    caching host allocator: the allocator records an event on every stream that used a block and queries it before
+    re-using the block, and an event recorded on a CAPTURING stream cannot be queried (cudaErrorInvalidValue at some
+    later, unrelated pin_memory() call). A few bytes per graph are kept for the life of the process instead."""
+    t = torch.zeros(shape, dtype=dtype).pin_memory()
+    _PINNED_FOREVER.append(t)
+    return t
+
+
 def prepare_capture(n_forwards: int = 1):
     """Call BEFORE capturing `n_forwards` async forwards into a CUDA graph: page-locked memory cannot be
     allocated while a stream is capturing, and a graph's landing slot must never be recycled."""
     for _ in range(n_forwards):
-        _CAPTURE_SLOTS.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+        _CAPTURE_SLOTS.append(pinned_forever((2,), torch.int32))
 
 
 def _pinned_slot(capturing: bool) -> torch.Tensor:
