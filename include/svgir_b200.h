@@ -522,6 +522,50 @@ int svgir_ssim_forward(int C, int H, int W, const float* img1, const float* img2
 int svgir_ssim_backward(int C, int H, int W, const float* img1, const float* img2, const float* gmaps,
                         const float* grad_out, float* d_img1, void* stream);
 
+/* ---- optimiser step and densification ----------------------------------------------------
+ * Fused Adam: all parameter groups of torch.optim.Adam(l, eps=1e-15) (scene/gaussian_model.py:737-773) in one launch,
+ * gradients read in place from the flat gradient bucket, NaN gradients replaced on the fly as
+ * replace_nangrad_to_zero does (:775-795; nan_fix != 0: NaN -> nan_value). step = 1, 2, ... (bias correction). */
+#define SVGIR_ADAM_MAX_GROUPS 16
+typedef struct svgir_adam_group {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    long long numel;
+    float lr;
+    int32_t nan_fix;
+    float nan_value;
+    int32_t reserved_;
+} svgir_adam_group;
+int svgir_adam_step(const svgir_adam_group* groups /* host */, int n_groups, float beta1, float beta2, float eps, int step,
+                    void* stream);
+
+/* add_densification_stats (gaussian_model.py:1270-1276): weights_accum += weights; for radii > 0:
+ * xyz_grad_accum += |viewspace_grad.xy|, denom += 1 (and max_radii2D = max(max_radii2D, radii) if given, train.py). */
+int svgir_densify_stats(int P, const float* viewspace_grad /* [P,3] */, const int32_t* radii, const float* weights,
+                        float* weights_accum, float* xyz_grad_accum, float* denom, float* max_radii2D, void* stream);
+
+/* densify_and_prune (gaussian_model.py:1136-1250) as device-side compaction. decide: per-surfel flags and output
+ * counts (keep / clone / split, each after the final prune mask); the caller scans the three count arrays
+ * (inclusive, int64); index: source row + kind of every row of the new model laid out as the reference leaves it --
+ * surviving originals, clones, first split copies, second split copies; gather_rows: any [P,K] fp32 tensor -> [P',K]
+ * (new rows zero / constant filled on request: Adam moments, statistics); split: positions and scales of the split
+ * children from caller-drawn N(0,1) samples [2 nC, 3]. */
+typedef struct svgir_densify_cfg {
+    int32_t P;
+    float grad_threshold, grad_normal_threshold, percent_dense, extent, min_opacity, weights_threshold;
+    int32_t use_screen_size;   /* max_screen_size given: also prune max(scaling) > 0.1 extent (:1237-1239) */
+} svgir_densify_cfg;
+int svgir_densify_decide(const svgir_densify_cfg* cfg, const float* xyz_grad_accum, const float* normal_grad_accum /* or NULL */,
+                         const float* denom, const float* scaling_raw /* [P,3] log-scales */, const float* opacity_raw /* [P] logits */,
+                         const float* weights_accum, uint8_t* flags, int32_t* keep, int32_t* nclone, int32_t* nsplit, void* stream);
+int svgir_densify_index(int P, const int32_t* keep, const int32_t* nclone, const int32_t* nsplit, const int64_t* keep_scan,
+                        const int64_t* clone_scan, const int64_t* split_scan, long long nA, long long nB, long long nC,
+                        int32_t* src /* [nA+nB+2nC] */, uint8_t* kind, void* stream);
+int svgir_gather_rows(long long n_rows, int K, const float* src_rows, const int32_t* index, const uint8_t* kind /* or NULL */,
+                      int zero_new, float new_value, float* dst, void* stream);
+int svgir_densify_split(long long n_new, long long first_split, const int32_t* src, const uint8_t* kind, const float* xyz_old,
+                        const float* scaling_old, const float* rotation_old, const float* normal_samples, float* xyz_new,
+                        float* scaling_new, void* stream);
+
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
  * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps
  * its flat gradient buffer in a symmetric allocation that is peer-mapped into all ranks of the box; the

@@ -168,4 +168,6 @@ EXPORTED_SYMBOLS = [
     "svgir_ssim_blocks", "svgir_ssim_forward", "svgir_ssim_backward",
     "svgir_raster_bin", "svgir_raster_composite", "svgir_raster_backward_composite", "svgir_raster_backward_params",
     "svgir_edge_aware_blocks", "svgir_edge_aware_forward", "svgir_edge_aware_backward", "svgir_tv_loss",
+    "svgir_adam_step", "svgir_densify_stats", "svgir_densify_decide", "svgir_densify_index", "svgir_gather_rows",
+    "svgir_densify_split",
 ]

@@ -1,0 +1,127 @@
+"""Fused Adam and the densification kernels (csrc/optim.cu via svgir_b200.optim). Adam is checked against the reference's
+own optimiser -- torch.optim.Adam(eps=1e-15) preceded by replace_nangrad_to_zero's patches (scene/gaussian_model.py:
+769-795); densification against the torch-CPU restatement of gaussian_model.py:1005-1276 (oracle/optim_oracle.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fused_adam_matches_torch_adam_with_nan_patches():
+    from svgir_b200 import optim
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    shapes = {"xyz": (1001, 3), "scaling": (1001, 3), "f_rest": (1001, 15, 3), "opacity": (1001, 1), "roughness": (1001, 4)}
+    lrs = {"xyz": 1.6e-4, "scaling": 5e-3, "f_rest": 1.25e-4, "opacity": 5e-2, "roughness": 1e-2}
+    ref = {k: torch.randn(s, generator=g).requires_grad_(True) for k, s in shapes.items()}
+    ours = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in ref.items()}
+    opt_ref = torch.optim.Adam([{"params": [ref[k]], "lr": lrs[k], "name": k} for k in shapes], lr=1e-4, eps=1e-15)
+    opt = optim.FusedAdam([{"params": [ours[k]], "lr": lrs[k], "name": k} for k in shapes], lr=1e-4, eps=1e-15)
+    for it in range(6):
+        for k in shapes:
+            gr = torch.randn(shapes[k], generator=g) * (10.0 ** (-it))
+            if it == 2:
+                gr.view(-1)[::97] = float("nan")
+            ours[k].grad = gr.to(dev)
+            gp = gr.clone()
+            gp[torch.isnan(gp)] = optim.NAN_FIX[k]              # replace_nangrad_to_zero
+            ref[k].grad = gp
+        if it == 3:
+            opt.set_lr("xyz", 0.7e-4)
+            for grp in opt_ref.param_groups:
+                if grp["name"] == "xyz":
+                    grp["lr"] = 0.7e-4
+        opt_ref.step()
+        opt.step()
+    for k in shapes:
+        torch.testing.assert_close(ours[k].detach().cpu(), ref[k].detach(), rtol=2e-6, atol=1e-7)
+        st = opt_ref.state[ref[k]]
+        # the first moment is a running difference of O(1) terms: elements that nearly cancel carry an absolute error of
+        # a few ulp of the largest term (lerp on the CPU vs. fused multiply-adds here), hence the absolute part
+        torch.testing.assert_close(opt.state[k]["exp_avg"].cpu(), st["exp_avg"], rtol=2e-6, atol=2e-7 * float(st["exp_avg"].abs().max()))
+        torch.testing.assert_close(opt.state[k]["exp_avg_sq"].cpu(), st["exp_avg_sq"], rtol=4e-6, atol=1e-20)
+    sd = opt.state_dict()
+    assert len(sd["state"]) == 5 and sd["param_groups"][0]["name"] == "xyz"
+
+
+def _model(P, g):
+    return {"xyz": torch.randn(P, 3, generator=g), "scaling": torch.log(0.002 + 0.05 * torch.rand(P, 3, generator=g)),
+            "rotation": torch.randn(P, 4, generator=g), "opacity": torch.randn(P, 1, generator=g) * 3.0,
+            "f_dc": torch.randn(P, 1, 3, generator=g), "f_rest": torch.randn(P, 15, 3, generator=g),
+            "normal": torch.randn(P, 12, generator=g), "base_color": torch.rand(P, 12, generator=g),
+            "roughness": torch.rand(P, 4, generator=g)}
+
+
+@pytest.mark.parametrize("max_screen_size", [None, 20])
+def test_densify_and_prune_matches_restatement(max_screen_size):
+    from oracle import optim_oracle as OO
+    from svgir_b200 import optim
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    P = 5003
+    t = _model(P, g)
+    stats = {"weights_accum": torch.rand(P, 1, generator=g) * 2e-5 * (torch.rand(P, 1, generator=g) > 0.5) + 1.0 * (torch.rand(P, 1, generator=g) > 0.3),
+             "xyz_gradient_accum": torch.rand(P, 1, generator=g) * 1e-3, "normal_gradient_accum": torch.zeros(P, 1),
+             "denom": torch.randint(0, 4, (P, 1), generator=g).float()}
+    moments = {k: (torch.randn(v.shape, generator=g), torch.rand(v.shape, generator=g)) for k, v in t.items()}
+    args = dict(max_grad=2e-4, min_opacity=0.05, extent=2.5, max_screen_size=max_screen_size, max_grad_normal=1e-8 + 1.0,
+                percent_dense=0.01, weights_threshold=1e-5)
+    # how many get split is decided by the data: ask the oracle first with dummy samples to size z
+    grads = (stats["xyz_gradient_accum"] / stats["denom"]).nan_to_num(0.0).squeeze(-1)
+    n_split = int(((grads >= args["max_grad"]) & (torch.exp(t["scaling"]).max(1).values > 0.01 * 2.5)).sum())
+    z = torch.randn(2 * n_split, 3, generator=g)
+    want_t, want_m, _ = OO.densify_and_prune(t, moments, {k: v.clone() for k, v in stats.items()}, z=z, **args)
+
+    tc = {k: v.to(dev).contiguous() for k, v in t.items()}
+    opt = optim.FusedAdam([{"params": [tc[k].requires_grad_(True)], "lr": 1e-3, "name": k} for k in tc])
+    for k in tc:
+        opt.state[k] = {"exp_avg": moments[k][0].to(dev), "exp_avg_sq": moments[k][1].to(dev)}
+    st = optim.DensificationState(P, dev)
+    st.weights_accum.copy_(stats["weights_accum"]); st.xyz_gradient_accum.copy_(stats["xyz_gradient_accum"]); st.denom.copy_(stats["denom"])
+    # the split children of the SURVIVING split set: the kernel consumes z rows in the order of its new rows; build that
+    # order from the oracle's convention (all selected once, then all again) restricted to children that survive the prune
+    out, new_stats, info = optim.densify_and_prune(tc, st, optimizer=opt, normal_samples=None if n_split == 0 else _z_for_kernel(
+        t, stats, args, z, n_split), **args)
+    assert info["n_after"] == want_t["xyz"].shape[0], (info, want_t["xyz"].shape)
+    assert info["cloned"] > 0 and info["split"] > 0 and info["kept"] < P
+    for k in t:
+        a, b = out[k].detach().cpu(), want_t[k]
+        if k in ("xyz", "scaling"):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+        else:
+            assert torch.equal(a, b), k
+        assert torch.equal(opt.state[k]["exp_avg"].cpu(), want_m[k][0]) and torch.equal(opt.state[k]["exp_avg_sq"].cpu(), want_m[k][1]), k
+        assert opt.param_groups[[g_["name"] for g_ in opt.param_groups].index(k)]["params"][0] is out[k]
+    assert float(new_stats.weights_accum.abs().sum()) == 0.0 and new_stats.denom.shape == (info["n_after"], 1)
+
+
+def _z_for_kernel(t, stats, args, z, n_split):
+    """Rows of z for the split children that survive the final prune, in the kernel's new-row order (first copies of the
+    surviving split surfels, then second copies). A child is pruned on opacity / size only (weights_accum = 1)."""
+    grads = (stats["xyz_gradient_accum"] / stats["denom"]).nan_to_num(0.0).squeeze(-1)
+    s = torch.exp(t["scaling"])
+    sel = (grads >= args["max_grad"]) & (s.max(1).values > args["percent_dense"] * args["extent"])
+    op = torch.sigmoid(t["opacity"]).squeeze(-1)[sel]
+    child_scale = torch.maximum(s[sel][:, 0], s[sel][:, 1]) / 1.6
+    alive = ~(op < args["min_opacity"])
+    if args["max_screen_size"]:
+        alive &= ~(child_scale > 0.1 * args["extent"])
+    return torch.cat([z[:n_split][alive], z[n_split:][alive]], 0)
+
+
+def test_densification_stats_kernel():
+    from svgir_b200 import optim
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    P = 4097
+    st = optim.DensificationState(P, dev)
+    ref = {k: torch.zeros(P, 1) for k in ("weights_accum", "xyz_gradient_accum", "denom")}
+    from oracle import optim_oracle as OO
+    for it in range(3):
+        vg = torch.randn(P, 3, generator=g) * 1e-4
+        radii = torch.randint(-1, 6, (P,), generator=g).clamp_min(0).int()
+        w = torch.rand(P, 1, generator=g)
+        st.add(vg.to(dev), radii.to(dev), w.to(dev))
+        OO.add_densification_stats(ref, vg, radii > 0, w)
+    for k in ref:
+        torch.testing.assert_close(getattr(st, k).cpu(), ref[k], rtol=1e-6, atol=1e-9)
