@@ -535,7 +535,7 @@ typedef struct svgir_adam_group {
     float nan_value;
     int32_t reserved_;
 } svgir_adam_group;
-int svgir_adam_step(const svgir_adam_group* groups /* host */, int n_groups, float beta1, float beta2, float eps, int step,
+int svgir_adam_step(const svgir_adam_group* groups /* host */, int n_groups, double beta1, double beta2, double eps, int step,
                     void* stream);
 
 /* add_densification_stats (gaussian_model.py:1270-1276): weights_accum += weights; for radii > 0:
@@ -565,6 +565,87 @@ int svgir_gather_rows(long long n_rows, int K, const float* src_rows, const int3
 int svgir_densify_split(long long n_new, long long first_split, const int32_t* src, const uint8_t* kind, const float* xyz_old,
                         const float* scaling_old, const float* rotation_old, const float* normal_samples, float* xyz_new,
                         float* scaling_new, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Radiance cache and radiance-consistency loss.  Replaces, for stage 2:
+ *   GaussianModel.update_radiace (scene/gaussian_model.py:469-522) -> Renderer.render_radiance_with_sampling_SH
+ *     (pbgi/renderer.py:596-615) -> the Slang kernels render_radiance_with_sampling_SH / gs_bvh_hit / ellipse_hit
+ *     (pbgi/bvhworkers/intersect_test.slang:1879-1991, :251-443, :94-149), and
+ *   GaussianModel.get_radiance_loss (scene/gaussian_model.py:544-575) -> Renderer.render_irradiance_sample
+ *     (pbgi/renderer.py:181-227, :748-751) -> render_irradiance_sample (intersect_test.slang:1143-1378) with
+ *     shading_brdf_simple (pbgi/bvhworkers/pbr.slang:283-330) and DirectLightMap.direct_light.
+ * The reference builds a second LBVH for this (pbgi/renderer.py:586-590, cube leaf boxes of 3*max|scale|,
+ * get_elements.slang:58-82); here the closest-hit query walks the SAME tree svgir_bvh_build made for the visibility
+ * trace (its leaf boxes contain every point with disM <= 9, the only points a hit can lie on).
+ * Where the reference's kernels are racy or depend on the traversal order the intended value is computed; every such
+ * place is listed in DESIGN.md Appendix C (R1-R5). */
+#define SVGIR_RADIANCE_RECORD_FLOATS 32
+#define SVGIR_RADIANCE_SCRATCH_FLOATS 2048
+
+/* One 128-byte record per surfel for the closest-hit query: centre, opacity, the rotation columns
+ * (matrixFromRotationQuaternions, intersect_test.slang:224-249; rotations [P,4] raw (r,x,y,z)), the first two scales
+ * (scales [P,scale_stride], scale_stride >= 2), the normal the facing test uses (normals [P,3] = proxy_normals) and
+ * Sigma^-1 (symm_inv [P,6], upper triangle as strip_symmetric orders it). records [P,32], 16-B aligned. */
+int svgir_radiance_pack_surfels(int P, const float* means3D, const float* scales, int scale_stride, const float* rotations,
+                                const float* normals, const float* opacity, const float* symm_inv, float* records,
+                                void* stream);
+
+/* render_radiance_with_sampling_SH: ray (n,s) starts at origins[n] along normalize(dirs[n,s]) and is advanced from hit
+ * to hit (closest facing surfel with alpha >= 1/255 in [t_min, 0.2), t_min 0.042 then 0.01) while T > 0.001, summing
+ * eval_sh(shs[hit], centre - origin) * alpha * T. radiance [N,S,3] (clamped to [0,10]), visibility [N,S] (T, or 0 once
+ * T < 0.2), hit_index [N,S] (first hit or -1), uv [N,S,2] (of the first hit). shs [P,16,3].
+ * self_mod: a hit on surfel (first_index + n) % self_mod ... is ignored -- see below:
+ *   self_mod == 0  the ray ignores its own surfel, index first_index + n (what the kernel means to do);
+ *   self_mod  > 0  the reference's behaviour when update_radiace feeds it chunks of self_mod surfels: the kernel
+ *                  compares the hit with the CHUNK-LOCAL index (intersect_test.slang:1931), i.e. ignores surfel
+ *                  (first_index + n) % self_mod. */
+int svgir_radiance_cache_build(const svgir_bvh* bvh, int N, int S, int first_index, int self_mod, const float* origins,
+                               const float* dirs, const float* records, const float* shs, float* radiance,
+                               float* visibility, int32_t* hit_index, float* uv, void* stream);
+
+#define SVGIR_RADIANCE_ENV_READY 1      /* env_act_scratch already holds the activated env map */
+#define SVGIR_RADIANCE_BWD_REFERENCE_GRID 2 /* backward: only secondary sample 0 carries gradient, S times over -- what
+                                               the reference's backward launch computes (grid (N/256,1,S) with the
+                                               sample index read from y, pbgi/renderer.py:224) */
+typedef struct svgir_radiance_loss_cfg {
+    int32_t P, S, env_h, env_w;
+    int32_t env_mode;       /* as svgir_shade_cfg: 0 = learnable map (softplus, x2), 1 = fixed map */
+    int32_t flags;
+    int32_t rough_stride;   /* floats per row of roughness / d_roughness (column 0 is used, intersect_test.slang:1281) */
+    int32_t reserved_;
+} svgir_radiance_loss_cfg;
+
+typedef struct svgir_radiance_loss_in {
+    const float* means3D;        /* [P,3] */
+    const float* campos;         /* [3] device */
+    const float* geo_normal;     /* [P,3] */
+    const float* incident_dirs;  /* [P,S,3]  _incident_dirs */
+    const float* incident_areas; /* [P,S]    _incident_areas */
+    const float* visibility;     /* [P,S]    _visibility_tracing */
+    const int32_t* hit_index;    /* [P,S]    hemi_index_buffers */
+    const float* uv;             /* [P,S,2]  uv_buffers */
+    const float* radiances;      /* [P,S,3]  _radiances */
+    const float* radiance_ratio; /* device scalar or NULL (= 1) */
+    const float* normals;        /* [P,12] shading normals, element 4*c + v */
+    const float* albedo;         /* [P,12] element 4*c + v */
+    const float* roughness;      /* [P,rough_stride] */
+    const float* env;            /* [env_h,env_w,3] raw parameter */
+    float* env_act_scratch;      /* [env_h*env_w*3] */
+} svgir_radiance_loss_in;
+
+/* loss [1] = mean |irradiance - nan_to_num(radiances[n, sel[n]] * ratio)| over [P,3]; irradiance [P,3] and
+ * sample_index [P] (= max_idx, gaussian_model.py:565) are written for the backward; scratch
+ * [SVGIR_RADIANCE_SCRATCH_FLOATS]. The sum over secondary samples is complete and deterministic in order (the
+ * reference adds with a non-atomic read-modify-write from S threads, intersect_test.slang:1371-1373). */
+int svgir_radiance_loss_forward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in, float* loss,
+                                float* irradiance, int32_t* sample_index, float* scratch, void* stream);
+
+/* Adds grad_loss * dloss/d{albedo, roughness[:,0], env} into d_albedo [P,12], d_roughness [P,rough_stride] (atomic;
+ * zero them first) and d_env [env_h,env_w,3] (+=, through d_env_scratch [env_h*env_w*4]). grad_loss: device scalar or
+ * NULL (= 1). Any of the three destinations may be NULL. */
+int svgir_radiance_loss_backward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in,
+                                 const float* grad_loss, const float* irradiance, const int32_t* sample_index,
+                                 float* d_albedo, float* d_roughness, float* d_env, float* d_env_scratch, void* stream);
 
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
  * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps

@@ -1,0 +1,222 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, float32) of the reference's radiance cache and radiance-consistency
+loss, which csrc/radiance.cu implements:
+
+  render_radiance_with_sampling_SH   /root/reference/pbgi/bvhworkers/intersect_test.slang:1879-1991
+    gs_bvh_hit                       :251-443   (brute force over all surfels instead of the LBVH walk)
+    ellipse_hit                      :94-149
+    gaussian_fn                      :189-196
+    matrixFromRotationQuaternions    :224-249
+    eval_sh                          /root/reference/pbgi/bvhworkers/sh_utils.slang
+  get_radiance_loss                  /root/reference/scene/gaussian_model.py:544-575
+    render_irradiance_sample         intersect_test.slang:1143-1378
+    shading_brdf_simple              /root/reference/pbgi/bvhworkers/pbr.slang:283-330
+    DirectLightMap.direct_light      /root/reference/scene/direct_light_map.py:70-83
+
+PARITY UNPINNED: the reference runs these kernels through slangtorch (a third-party Slang JIT that is neither in
+/root/reference nor in this image), and it ships no test, fixture or golden vector for them, so this restatement could
+not be checked against the reference's own output. Where the reference's kernels are racy or depend on the LBVH
+traversal order, the INTENDED value is restated (same choices as the CUDA path):
+  R1 the alpha a query returns is that of the closest hit (the reference returns the alpha of the last leaf visited
+     whose test passed, :409-415);
+  R2 a surfel whose plane hit lies beyond the current closest distance is not a hit (the reference reports "hit" on
+     surfel 0 at t_max when only such surfels exist, :404-413);
+  R3 irradiance is the complete sum over the secondary samples (the reference adds with a non-atomic
+     read-modify-write from S threads, :1371-1373) and is 0 when the primary sample hit nothing (the reference
+     writes through a 3-index view of a [N,3] tensor there, :1203-1206);
+  R4 the gradient is that of the complete sum (the reference's backward grid differentiates sample 0 S times,
+     pbgi/renderer.py:224); `reference_grid=True` restates that instead;
+  R5 self_mod restates the chunk-local self test (:1931 with update_radiace's chunking, gaussian_model.py:491-503).
+Only tests/ may import this module."""
+import numpy as np
+
+F = np.float32
+
+
+def rotation_matrices(rot):
+    """matrixFromRotationQuaternions (intersect_test.slang:224-249). rot [P,4] raw (r,x,y,z) -> [P,3,3]."""
+    rot = np.asarray(rot, F)
+    norm = np.sqrt((rot * rot).sum(-1) + F(0.00000001)).astype(F)
+    r, x, y, z = (rot / norm[:, None]).T
+    m = np.empty((rot.shape[0], 3, 3), F)
+    m[:, 0, 0] = 1 - 2 * (y * y + z * z); m[:, 0, 1] = 2 * (x * y - r * z); m[:, 0, 2] = 2 * (x * z + r * y)
+    m[:, 1, 0] = 2 * (x * y + r * z); m[:, 1, 1] = 1 - 2 * (x * x + z * z); m[:, 1, 2] = 2 * (y * z - r * x)
+    m[:, 2, 0] = 2 * (x * z - r * y); m[:, 2, 1] = 2 * (y * z + r * x); m[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return m
+
+
+def eval_sh(sh, d):
+    """sh [16,3], d [3] -> [3] (sh_utils.slang: degree 3, +0.5)."""
+    d = np.asarray(d, F)
+    x, y, z = (d / np.sqrt((d * d).sum())).astype(F)
+    C0, C1 = F(0.28209479177387814), F(0.4886025119029199)
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    w = np.array([C0, -C1 * y, C1 * z, -C1 * x,
+                  C2[0] * x * y, C2[1] * y * z, C2[2] * (2.0 * z * z - x * x - y * y), C2[3] * x * z, C2[4] * (x * x - y * y),
+                  C3[0] * y * (3.0 * x * x - y * y), C3[1] * x * y * z, C3[2] * y * (4.0 * z * z - x * x - y * y),
+                  C3[3] * z * (2.0 * z * z - 3.0 * x * x - 3.0 * y * y), C3[4] * x * (4.0 * z * z - x * x - y * y),
+                  C3[5] * z * (x * x - y * y), C3[6] * x * (x * x - 3.0 * y * y)], F)
+    return (w[:, None] * np.asarray(sh, F)).sum(0).astype(F) + F(0.5)
+
+
+class Surfels:
+    """The per-surfel tensors gs_bvh_hit reads (:303-330)."""
+
+    def __init__(self, centers, scales, rotations, normals, opacity, cov_inv):
+        self.c = np.asarray(centers, F)
+        self.s = np.asarray(scales, F)
+        self.R = rotation_matrices(rotations)
+        n = np.asarray(normals, F)
+        self.n = (n / np.sqrt((n * n).sum(-1, keepdims=True))).astype(F)
+        self.o = np.asarray(opacity, F).reshape(-1)
+        self.ci = np.asarray(cov_inv, F)
+
+
+def closest_hit(sf, o, d, t_min, t_max):
+    """gs_bvh_hit for one ray over all surfels -> (index or -1, t, alpha, uv)."""
+    o = np.asarray(o, F); d = np.asarray(d, F)
+    nW = sf.R[:, :, 2]                                            # L (0,0,1) = third column (:101-102)
+    denom = (nW * d).sum(-1).astype(F)
+    ok = np.abs(denom) >= F(1e-6)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (((sf.c - o) * nW).sum(-1) / denom).astype(F)
+    ok &= t >= F(t_min)
+    ok &= t < F(t_max)
+    pos = (o[None] + t[:, None] * d[None]).astype(F)
+    e = (pos - sf.c).astype(F)
+    a = (sf.R[:, :, 0] * e).sum(-1).astype(F)                     # posM = R^-1 (pos - centre) (:122)
+    b = (sf.R[:, :, 1] * e).sum(-1).astype(F)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        disM = (a * a) / (sf.s[:, 0] * sf.s[:, 0]) + (b * b) / (sf.s[:, 1] * sf.s[:, 1])
+        ok &= disM <= F(9.0)
+        ci = sf.ci
+        dd = -e                                                   # gaussian_fn: d = mean - pos
+        power = F(-0.5) * (dd[:, 0] * dd[:, 0] * ci[:, 0] + dd[:, 1] * dd[:, 1] * ci[:, 3] + dd[:, 2] * dd[:, 2] * ci[:, 5] +
+                           2 * dd[:, 0] * dd[:, 1] * ci[:, 1] + 2 * dd[:, 0] * dd[:, 2] * ci[:, 2] + 2 * dd[:, 1] * dd[:, 2] * ci[:, 4])
+        ok &= ~(power > 0)
+        alpha = np.minimum(F(0.99), sf.o * np.exp(power.astype(F))).astype(F)
+    ok &= ~(alpha < F(1.0 / 255.0))
+    ok &= (sf.n * d).sum(-1) < 0
+    if not ok.any():
+        return -1, F(0), F(0), (F(0), F(0))
+    tt = np.where(ok, t, np.inf)
+    i = int(np.argmin(tt))
+    u, v = a[i] / sf.s[i, 0], b[i] / sf.s[i, 1]
+    if u < v:
+        u, v = v, u
+    u = min(max(F(u) * F(0.5) + F(0.5), F(0.001)), F(0.999))
+    v = min(max(F(v) * F(0.5) + F(0.5), F(0.001)), F(0.999))
+    return i, t[i], alpha[i], (u, v)
+
+
+def render_radiance_with_sampling_SH(sf, shs, origins, dirs, first_index=0, self_mod=0):
+    """origins [N,3], dirs [N,S,3] -> radiance [N,S,3], visibility [N,S], hit_index [N,S], uv [N,S,2]."""
+    origins = np.asarray(origins, F); dirs = np.asarray(dirs, F); shs = np.asarray(shs, F)
+    N, S = dirs.shape[:2]
+    rad = np.zeros((N, S, 3), F); vis = np.ones((N, S), F)
+    hit = np.zeros((N, S), np.int32); uv = np.zeros((N, S, 2), F)
+    for n in range(N):
+        self_i = (first_index + n) % self_mod if self_mod > 0 else first_index + n
+        for s in range(S):
+            d = dirs[n, s]
+            d = (d / np.sqrt((d * d).sum())).astype(F)
+            o = origins[n].copy()
+            T, t_min, t_max = F(1.0), 0.042, 0.2
+            acc = np.zeros(3, F)
+            visible, first, fuv = True, -1, (F(0), F(0))
+            while T > F(0.001):
+                i, t, alpha, huv = closest_hit(sf, o, d, t_min, t_max)
+                if i < 0 or i == self_i:
+                    break
+                if first == -1:
+                    first, fuv, t_min = i, huv, 0.01
+                col = eval_sh(shs[i], sf.c[i] - o)
+                o = (o + d * t).astype(F)
+                acc = (acc + col * (alpha * T)).astype(F)
+                T = F(T * (F(1) - alpha))
+                if T < F(0.2):
+                    visible = False
+            vis[n, s] = T if visible else 0.0
+            rad[n, s] = np.clip(acc, 0.0, 10.0)
+            hit[n, s] = first
+            uv[n, s] = fuv
+    return rad, vis, hit, uv
+
+
+def direct_light(env_act, dirs, scale):
+    """grid_sample(bilinear, zeros padding, align_corners=True) on the lat-long map (direct_light_map.py:70-83).
+    env_act [He,We,3] activated; dirs [...,3]."""
+    env_act = np.asarray(env_act, np.float64)
+    He, We = env_act.shape[:2]
+    d = np.asarray(dirs, np.float64).reshape(-1, 3)
+    phi = np.arccos(d[:, 2]) - 1e-6
+    theta = np.arctan2(d[:, 1], d[:, 0])
+    ix = ((-theta / np.pi) + 1) / 2 * (We - 1)
+    iy = ((phi / np.pi * 2 - 1) + 1) / 2 * (He - 1)
+    x0, y0 = np.floor(ix).astype(int), np.floor(iy).astype(int)
+    wx, wy = ix - x0, iy - y0
+    out = np.zeros((d.shape[0], 3))
+    for k in range(4):
+        x, y = x0 + (k & 1), y0 + (k >> 1)
+        w = (wx if k & 1 else 1 - wx) * (wy if k >> 1 else 1 - wy)
+        ok = (x >= 0) & (x <= We - 1) & (y >= 0) & (y <= He - 1)
+        out[ok] += env_act[y[ok], x[ok]] * w[ok, None]
+    return (out * scale).reshape(np.asarray(dirs).shape)
+
+
+def brdf_simple(V, L, normal, albedo, rough):
+    """shading_brdf_simple (pbr.slang:283-330); V = view_dir, L = light_dir (normalised inside)."""
+    V = V / np.linalg.norm(V); L = L / np.linalg.norm(L)
+    N = normal / np.linalg.norm(normal)
+    H = (V + L) / np.linalg.norm(V + L)
+    cl = lambda x: min(max(x, 1e-6), 1.0)
+    NoL, NoV, NoH, VoH = cl(N @ L), cl(N @ V), cl(N @ H), cl(V @ H)
+    alpha = rough * rough; alpha2 = alpha * alpha
+    k = (alpha + 2.0 * rough + 1.0) / 8.0
+    FMi = (-5.55473 * VoH - 6.98316) * VoH
+    frac = (0.04 + (1 - 0.04) * 2.0 ** FMi) * alpha2
+    nom0 = NoH * NoH * (alpha2 - 1.0) + 1.0
+    nom = min(max(4 * np.pi * nom0 * nom0 * (NoV * (1 - k) + k) * (NoL * (1 - k) + k), 1e-6), 4 * np.pi)
+    return frac / nom + np.asarray(albedo, np.float64) / np.pi
+
+
+def select_samples(xyz, campos, geo_normal, dirs, vis):
+    """gaussian_model.py:556-565 -> max_idx [N]."""
+    xyz = np.asarray(xyz, F); gn = np.asarray(geo_normal, F)
+    vd = xyz - np.asarray(campos, F)[None]
+    vd = (vd / np.maximum(np.sqrt((vd * vd).sum(-1, keepdims=True)), F(1e-12))).astype(F)
+    refl = (2 * (gn * vd).sum(-1, keepdims=True) * gn + vd).astype(F)
+    ndi = (np.asarray(dirs, F) * refl[:, None]).sum(-1).astype(F) * (F(1) - np.asarray(vis, F))
+    return np.argmax(ndi, axis=-1).astype(np.int32), ndi
+
+
+def irradiance_sample(sel, dirs, envmap, hit, uv, normals, albedo, roughness):
+    """render_irradiance_sample forward (float64). normals / albedo [P,12] (4*c + v), envmap [P,S,3] -> [P,3]."""
+    P, S = hit.shape
+    dirs = np.asarray(dirs, np.float64); envmap = np.asarray(envmap, np.float64); uv = np.asarray(uv, np.float64)
+    nr = np.asarray(normals, np.float64).reshape(P, 3, 4); al = np.asarray(albedo, np.float64).reshape(P, 3, 4)
+    out = np.zeros((P, 3))
+    for n in range(P):
+        h = int(hit[n, sel[n]])
+        if h == -1:
+            continue
+        V = -dirs[n, sel[n]]
+        for s2 in range(S):
+            if hit[h, s2] != -1:
+                continue
+            u, v = uv[h, s2]
+            w = [(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v]
+            irr = sum(w[k] * brdf_simple(V, dirs[h, s2], nr[h, :, k], al[h, :, k], float(roughness[h, 0])) for k in range(4))
+            out[n] += irr * envmap[h, s2] / S
+    return out
+
+
+def radiance_loss(xyz, campos, geo_normal, dirs, areas, vis, hit, uv, radiances, ratio, normals, albedo, roughness, env_act,
+                  env_scale):
+    """get_radiance_loss (gaussian_model.py:544-575) -> (loss, irradiance [P,3], max_idx [P])."""
+    sel, _ = select_samples(xyz, campos, geo_normal, dirs, vis)
+    envmap = direct_light(env_act, dirs, env_scale) * np.asarray(areas, np.float64).reshape(*hit.shape, 1)
+    irr = irradiance_sample(sel, dirs, envmap, hit, uv, normals, albedo, roughness)
+    tgt = np.nan_to_num(np.asarray(radiances, np.float64)[np.arange(hit.shape[0]), sel] * ratio, nan=0.0)
+    return np.abs(irr - tgt).mean(), irr, sel

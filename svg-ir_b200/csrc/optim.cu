@@ -19,7 +19,7 @@ struct AdamArgs {
     svgir_adam_group g[SVGIR_ADAM_MAX_GROUPS];
     int first_block[SVGIR_ADAM_MAX_GROUPS + 1];   // first CTA of each group (prefix sums of ceil(numel / 1024))
     int n;
-    float beta1, beta2, eps, bc1, bc2_sqrt;
+    float beta1, beta2, omb1, omb2, eps, bc1, bc2_sqrt;   // omb = 1 - beta, rounded from the double difference as torch does
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
         if (i >= n) break;
         float gr = g[i];
         if (G.nan_fix && gr != gr) gr = G.nan_value;              // replace_nangrad_to_zero
-        m[i] = m[i] + (gr - m[i]) * (1.f - a.beta1);               // lerp_
-        v[i] = v[i] * a.beta2 + (1.f - a.beta2) * gr * gr;         // mul_ / addcmul_
+        m[i] = m[i] + (gr - m[i]) * a.omb1;               // lerp_
+        v[i] = v[i] * a.beta2 + a.omb2 * gr * gr;         // mul_ / addcmul_
         const float denom = sqrtf(v[i]) / a.bc2_sqrt + a.eps;
         p[i] = p[i] - step_size * (m[i] / denom);                  // addcdiv_
     }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) densify_split_kernel(long long n_new, lon
 
 using namespace svgir;
 
-extern "C" int svgir_adam_step(const svgir_adam_group* groups, int n_groups, float beta1, float beta2, float eps, int step,
+extern "C" int svgir_adam_step(const svgir_adam_group* groups, int n_groups, double beta1, double beta2, double eps, int step,
                                void* stream) {
     if (!groups || n_groups <= 0 || n_groups > SVGIR_ADAM_MAX_GROUPS || step < 1) { set_error("adam_step: 1..%d groups, step >= 1", SVGIR_ADAM_MAX_GROUPS); return SVGIR_ERR_INVALID; }
     AdamArgs a;
@@ -195,9 +195,10 @@ extern "C" int svgir_adam_step(const svgir_adam_group* groups, int n_groups, flo
         blocks += (int)((g.numel + 1023) / 1024);
     }
     a.first_block[n_groups] = blocks;
-    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+    a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+    a.bc1 = (float)(1.0 - pow(beta1, (double)step));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
     if (blocks == 0) return SVGIR_OK;
     cudaStream_t s = (cudaStream_t)stream;
     { TimedScope ts_("adam", s); adam_kernel<<<blocks, 256, 0, s>>>(a); }

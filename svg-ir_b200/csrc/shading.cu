@@ -24,6 +24,7 @@
 //
 // Roofline: HBM-bound, algorithmic bytes N*(Ns*32 + 124) + N*4*(60+S).
 #include "common.cuh"
+#include "env.cuh"
 
 namespace svgir {
 
@@ -34,7 +35,6 @@ namespace svgir {
 #endif
 #define VUF_FLOATS 12    // forward per-vertex uniform block in shared memory
 #define VU_FLOATS 24     // backward per-vertex uniform block (see shade_bwd_kernel)
-#define PI_F 3.14159265358979323846f
 
 struct SampleShared {  // vertex-independent per-sample quantities, produced by one lane of the quad
     float wx, wy, wz;      // raw incident direction
@@ -45,41 +45,6 @@ struct SampleShared {  // vertex-independent per-sample quantities, produced by 
     float gr, gg, gb;      // area * clamp(env)*vis
     float lr, lg, lb;      // area * radiance
 };
-
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
-
-// lat-long bilinear lookup (grid_sample, align_corners=True, zero padding). env [He][We][3].
-// Returns texel corner (x0,y0) and weights so the backward can scatter.
-struct EnvTap { int x0, y0; float wx1, wy1; };
-
-__device__ __forceinline__ EnvTap env_coords(float dx, float dy, float dz, int He, int We) {
-    const float phi = acosf(dz) - 1e-6f;
-    const float theta = atan2f(dy, dx);
-    const float qy = (phi * (1.f / PI_F)) * 2.f - 1.f;   // one rounding away from phi / pi: < 1e-7 of a texel
-    const float qx = -theta * (1.f / PI_F);
-    const float ix = (qx + 1.f) / 2.f * (float)(We - 1);
-    const float iy = (qy + 1.f) / 2.f * (float)(He - 1);
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    EnvTap t;
-    t.x0 = (int)fx0; t.y0 = (int)fy0;
-    t.wx1 = ix - fx0; t.wy1 = iy - fy0;
-    return t;
-}
-
-__device__ __forceinline__ void env_fetch(const float* env, int He, int We, const EnvTap& t, float out[3]) {
-    const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
-    out[0] = out[1] = out[2] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = t.x0 + (k & 1), y = t.y0 + (k >> 1);
-        if (x < 0 || x > We - 1 || y < 0 || y > He - 1) continue;
-        const float w = ((k & 1) ? t.wx1 : wx0) * ((k >> 1) ? t.wy1 : wy0);
-        const float* e = env + ((size_t)y * We + x) * 3;
-        out[0] = fmaf(e[0], w, out[0]);
-        out[1] = fmaf(e[1], w, out[1]);
-        out[2] = fmaf(e[2], w, out[2]);
-    }
-}
 
 __global__ void env_activate_kernel(int n, const float* __restrict__ param, float* __restrict__ act, int mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,14 +433,6 @@ struct ShadeGradsK {
     int accumulate;                              // += into d_base_color / d_roughness / d_metallic / d_normals
 };
 
-// Env-map gradient scatter. sm_100 has no native shared-memory float atomic (atomicAdd on shared
-// compiles to a compare-and-swap loop that costs ~2 ms at the training shape), so the four bilinear
-// taps of a sample go straight to L2 as four fire-and-forget vector reductions
-// (REDG.E.ADD.F32x4) into a [He,We,4] accumulator; a tiny kernel folds it into d_env afterwards.
-__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
-}
-
 __global__ void env_grad_finalize_kernel(int ntex, int env_mode, const float* __restrict__ acc,
                                          const float* __restrict__ env_param, float* __restrict__ d_env) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -863,6 +820,13 @@ __global__ void __launch_bounds__(256) direct_light_bwd_kernel(int n, int He, in
             if (val != 0.f) atomicAdd(&d_env[b + ch], val);
         }
     }
+}
+
+void launch_env_activate(int nenv, const float* param, float* act, int env_mode, cudaStream_t s) {
+    env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, param, act, env_mode);
+}
+void launch_env_grad_finalize(int ntex, int env_mode, const float* acc, const float* env_param, float* d_env, cudaStream_t s) {
+    env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, env_mode, acc, env_param, d_env);
 }
 
 }  // namespace svgir

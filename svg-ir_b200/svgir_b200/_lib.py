@@ -170,4 +170,5 @@ EXPORTED_SYMBOLS = [
     "svgir_edge_aware_blocks", "svgir_edge_aware_forward", "svgir_edge_aware_backward", "svgir_tv_loss",
     "svgir_adam_step", "svgir_densify_stats", "svgir_densify_decide", "svgir_densify_index", "svgir_gather_rows",
     "svgir_densify_split",
+    "svgir_radiance_pack_surfels", "svgir_radiance_cache_build", "svgir_radiance_loss_forward", "svgir_radiance_loss_backward",
 ]

@@ -42,7 +42,7 @@ def _L():
     L = _lib.lib()
     if not _bound:
         vp, ll = C.c_void_p, C.c_longlong
-        L.svgir_adam_step.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp]
+        L.svgir_adam_step.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, vp]
         L.svgir_adam_step.restype = C.c_int
         L.svgir_densify_stats.argtypes = [C.c_int] + [vp] * 8
         L.svgir_densify_stats.restype = C.c_int

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     """sizeof of every ctypes mirror == sizeof of the C struct, measured by compiling include/svgir_b200.h."""
     import ctypes as C
     import subprocess
-    from svgir_b200 import _lib, losses, optim, shading
+    from svgir_b200 import _lib, bvh, losses, optim, radiance, shading
     pairs = [("svgir_raster_cfg", _lib.RasterCfg), ("svgir_raster_in", _lib.RasterIn),
              ("svgir_raster_state", _lib.RasterState), ("svgir_raster_out", _lib.RasterOut),
              ("svgir_raster_grads", _lib.RasterGrads), ("svgir_shade_cfg", shading.ShadeCfg),
@@ -38,7 +38,9 @@ def test_struct_layouts_match_header_sizes(tmp_path):
              ("svgir_shade_grads", shading.ShadeGrads), ("svgir_peer_comm", _lib.PeerComm),
              ("svgir_param_grads", _lib.ParamGrads), ("svgir_train_loss_cfg", losses.TrainLossCfg),
              ("svgir_train_loss_in", losses.TrainLossIn), ("svgir_train_loss_grads", losses.TrainLossGrads),
-             ("svgir_adam_group", optim.AdamGroup), ("svgir_densify_cfg", optim.DensifyCfg)]
+             ("svgir_adam_group", optim.AdamGroup), ("svgir_densify_cfg", optim.DensifyCfg),
+             ("svgir_bvh", bvh.BvhStruct), ("svgir_radiance_loss_cfg", radiance.RadianceLossCfg),
+             ("svgir_radiance_loss_in", radiance.RadianceLossIn)]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "svgir_b200.h"\nint main(void){' +
                    "".join('printf("%%zu\\n", sizeof(%s));' % n for n, _ in pairs) + "return 0;}\n")

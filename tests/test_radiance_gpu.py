@@ -1,0 +1,196 @@
+"""Radiance cache + radiance-consistency loss (csrc/radiance.cu through svgir_b200.radiance) against the numpy
+restatement oracle/radiance_oracle.py (parity unpinned, see its header) and, for the gradients, a float64 torch graph of
+the same formulas (intersect_test.slang:1143-1378, pbr.slang:283-330, direct_light_map.py:70-83)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(P, seed, dev, box=0.25, smin=0.02, smax=0.06):
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(P, 3, generator=g) - 0.5) * 2 * box
+    scaling = torch.cat([smin + (smax - smin) * torch.rand(P, 2, generator=g), torch.full((P, 1), 0.01)], 1)
+    rot = torch.randn(P, 4, generator=g)
+    q = rot / rot.norm(dim=1, keepdim=True)
+    r, x, y, z = q.unbind(1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(P, 3, 3)
+    Sinv = R @ torch.diag_embed(1.0 / scaling ** 2) @ R.transpose(1, 2)
+    ci = torch.stack([Sinv[:, 0, 0], Sinv[:, 0, 1], Sinv[:, 0, 2], Sinv[:, 1, 1], Sinv[:, 1, 2], Sinv[:, 2, 2]], 1)
+    opacity = 0.3 + 0.7 * torch.rand(P, 1, generator=g)
+    shs = torch.cat([torch.rand(P, 1, 3, generator=g), 0.1 * torch.randn(P, 15, 3, generator=g)], 1)
+    t = dict(xyz=xyz, scaling=scaling, rotation=rot, geo_normal=R[:, :, 2].contiguous(), opacity=opacity, cov_inv=ci, shs=shs)
+    return {k: v.float().to(dev) for k, v in t.items()}
+
+
+def _build(sc, S, seed):
+    from svgir_b200 import bvh, radiance, sampling
+    dev = sc["xyz"].device
+    tracer = bvh.RayTracer(sc["xyz"], sc["scaling"], sc["rotation"])
+    rec = radiance.pack_surfels(sc["xyz"], sc["scaling"], sc["rotation"], sc["geo_normal"], sc["opacity"], sc["cov_inv"])
+    u = torch.rand(sc["xyz"].shape[0], 1, generator=torch.Generator().manual_seed(seed)).to(dev)
+    dirs, areas = sampling.fibonacci_sphere_sampling(sc["geo_normal"], S, random_rotate=True, rand_u=u)
+    return tracer, rec, dirs, areas
+
+
+def test_cache_matches_oracle_on_a_small_scene():
+    from oracle import radiance_oracle as ro
+    from svgir_b200 import radiance
+    dev = torch.device("cuda:0")
+    P, S = 300, 8
+    sc = _scene(P, 3, dev)
+    tracer, rec, dirs, _ = _build(sc, S, 4)
+    for self_mod in (0, 100):
+        rad, vis, hit, uv = radiance.render_radiance_with_sampling_SH(tracer.bvh, rec, sc["shs"], sc["xyz"], dirs, S,
+                                                                      self_mod=self_mod)
+        c = {k: v.cpu().numpy() for k, v in sc.items()}
+        sf = ro.Surfels(c["xyz"], c["scaling"], c["rotation"], c["geo_normal"], c["opacity"], c["cov_inv"])
+        o_rad, o_vis, o_hit, o_uv = ro.render_radiance_with_sampling_SH(sf, c["shs"], c["xyz"], dirs.cpu().numpy(),
+                                                                        self_mod=self_mod)
+        hit_n = hit[..., 0].cpu().numpy()
+        assert (hit_n >= 0).mean() > 0.2, "scene too sparse to test anything"
+        same = hit_n == o_hit
+        # float32 arithmetic differs in contraction only; a ray grazing a 3-sigma rim may flip
+        assert same.mean() >= 0.995, same.mean()
+        ok = same & (np.abs(vis[..., 0].cpu().numpy() - o_vis) < 1e-5)
+        assert ok.mean() >= 0.99, ok.mean()
+        np.testing.assert_allclose(rad.cpu().numpy()[ok], o_rad[ok], atol=2e-5, rtol=1e-5)     # fp32, tolerance written here
+        np.testing.assert_allclose(uv.cpu().numpy()[ok], o_uv[ok], atol=2e-5)
+
+
+def test_cache_properties_at_scale_and_determinism():
+    from svgir_b200 import radiance
+    dev = torch.device("cuda:0")
+    P, S = 100_000, 64
+    sc = _scene(P, 5, dev, box=1.0, smin=0.01, smax=0.03)
+    tracer, rec, dirs, _ = _build(sc, S, 6)
+    a = radiance.render_radiance_with_sampling_SH(tracer.bvh, rec, sc["shs"], sc["xyz"], dirs, S)
+    b = radiance.render_radiance_with_sampling_SH(tracer.bvh, rec, sc["shs"], sc["xyz"], dirs, S)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    rad, vis, hit, uv = a
+    assert int(hit.min()) >= -1 and int(hit.max()) < P
+    own = torch.arange(P, device=dev, dtype=torch.int32)[:, None, None]
+    assert not bool((hit == own).any())                                   # a ray never reports its own surfel
+    assert float(rad.min()) >= 0.0 and float(rad.max()) <= 10.0
+    v = vis[..., 0]
+    assert bool(((v == 0) | ((v >= 0.2) & (v <= 1.0))).all())
+    nohit = hit[..., 0] == -1
+    assert bool((v[nohit] == 1.0).all()) and not bool(rad[nohit].any()) and not bool(uv[nohit].any())
+    assert bool(((uv[~nohit] >= 0.001) & (uv[~nohit] <= 0.999)).all())
+    assert bool((uv[..., 0] >= uv[..., 1]).all())                          # ellipse_hit orders (u, v)
+    assert 0.02 < float((~nohit).float().mean()) < 0.98
+
+
+def _materials(P, S, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    n12 = torch.randn(P, 3, 4, generator=g)
+    alb = 0.05 + 0.9 * torch.rand(P, 12, generator=g)
+    rough = 0.1 + 0.85 * torch.rand(P, 4, generator=g)
+    env = torch.randn(16, 32, 3, generator=g)
+    radiances = torch.rand(P, S, 3, generator=g)
+    return [x.float().to(dev) for x in (n12.reshape(P, 12), alb, rough, env, radiances)]
+
+
+def _torch_loss(cam, env, sc, dirs, areas, vis, hit, uv, radiances, ratio, n12, alb, rough, sel, only_first=False):
+    """float64 graph of get_radiance_loss given the selected samples."""
+    P, S = hit.shape
+    dd = dirs.double()
+    act = F.softplus(env.double())
+    d = dd.reshape(-1, 3)
+    phi = torch.arccos(d[:, 2]) - 1e-6
+    theta = torch.atan2(d[:, 1], d[:, 0])
+    grid = torch.stack((-theta / math.pi, phi / math.pi * 2 - 1), 1)[None, None]
+    light = F.grid_sample(act.permute(2, 0, 1)[None], grid, align_corners=True)[0, :, 0].t().reshape(P, S, 3) * 2.0
+    envmap = light * areas.double().reshape(P, S, 1)
+    idx = torch.arange(P, device=hit.device)
+    h = hit[idx, sel.long()].long()
+    valid = h >= 0
+    hs = h.clamp_min(0)
+    V = -dd[idx, sel.long()]
+    V = V / V.norm(dim=-1, keepdim=True)                                  # [P,3]
+    L = dd[hs]
+    L = L / L.norm(dim=-1, keepdim=True)                                  # [P,S,3]
+    H = V[:, None] + L
+    H = H / H.norm(dim=-1, keepdim=True)
+    nrm = n12.double().reshape(-1, 3, 4)[hs]                              # [P,3,4]
+    nrm = nrm / nrm.norm(dim=1, keepdim=True)
+    albv = alb.double().reshape(-1, 3, 4)[hs]
+    r = rough.double()[hs, 0][:, None, None]                              # [P,1,1]
+    cl = lambda x: x.clamp(1e-6, 1.0)
+    NoL = cl(torch.einsum("psc,pcv->psv", L, nrm))
+    NoV = cl(torch.einsum("pc,pcv->pv", V, nrm))[:, None]
+    NoH = cl(torch.einsum("psc,pcv->psv", H, nrm))
+    VoH = cl((V[:, None] * H).sum(-1))[..., None]
+    a2 = r ** 4
+    k = (r * r + 2 * r + 1) / 8
+    Fr = 0.04 + 0.96 * torch.pow(2.0, (-5.55473 * VoH - 6.98316) * VoH)
+    nom0 = NoH * NoH * (a2 - 1) + 1
+    nom = (4 * math.pi * nom0 * nom0 * (NoV * (1 - k) + k) * (NoL * (1 - k) + k)).clamp(1e-6, 4 * math.pi)
+    spec = Fr * a2 / nom                                                  # [P,S,4]
+    uvh = uv.double().reshape(P, S, 2)[hs]
+    u, v = uvh[..., 0], uvh[..., 1]
+    w = torch.stack([(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v], -1)     # [P,S,4]
+    brdf = (w * spec).sum(-1, keepdim=True) + torch.einsum("psv,pcv->psc", w, albv) / math.pi
+    term = brdf * envmap[hs] / S
+    open_ = (hit[hs] == -1) & valid[:, None]
+    if only_first:
+        open_ = open_ & (torch.arange(S, device=hit.device)[None] == 0)
+    irr = (term * open_[..., None]).sum(1)
+    if only_first:
+        irr = irr * S
+    tgt = torch.nan_to_num(radiances.double()[idx, sel.long()] * ratio, nan=0.0)
+    return (irr - tgt).abs().mean(), irr
+
+
+@pytest.mark.parametrize("ref_grid", [False, True])
+def test_loss_and_gradients(ref_grid):
+    from oracle import radiance_oracle as ro
+    from svgir_b200 import radiance
+    dev = torch.device("cuda:0")
+    P, S = 400, 16
+    sc = _scene(P, 7, dev)
+    tracer, rec, dirs, areas = _build(sc, S, 8)
+    _, vis, hit, uv = radiance.render_radiance_with_sampling_SH(tracer.bvh, rec, sc["shs"], sc["xyz"], dirs, S)
+    n12, alb, rough, env, radiances = _materials(P, S, dev, 9)
+    ratio = torch.tensor(0.8, device=dev)
+    cam = torch.tensor([0.3, -0.2, 1.5], device=dev)
+    alb.requires_grad_(True); rough.requires_grad_(True); env.requires_grad_(True)
+    loss, irr, sel = radiance.radiance_loss(cam, (env, 0), sc["xyz"], sc["geo_normal"], dirs, areas, vis, hit, uv, radiances,
+                                            ratio, n12, alb, rough, reference_backward_grid=ref_grid, return_aux=True)
+    (3.0 * loss).backward()
+    hit2 = hit[..., 0]
+    # forward against the numpy restatement
+    c = lambda x: x.detach().cpu().numpy()
+    o_loss, o_irr, o_sel = ro.radiance_loss(c(sc["xyz"]), c(cam), c(sc["geo_normal"]), c(dirs), c(areas)[..., 0], c(vis)[..., 0],
+                                            c(hit2), c(uv), c(radiances), 0.8, c(n12), c(alb), c(rough),
+                                            c(F.softplus(env)), 2.0)
+    same_sel = c(sel) == o_sel
+    assert same_sel.mean() >= 0.99                                        # near-tied scores may pick another sample
+    assert (c(hit2)[np.arange(P), c(sel)] >= 0).mean() > 0.05, "no occluded samples selected: nothing tested"
+    np.testing.assert_allclose(c(irr)[same_sel], o_irr[same_sel], rtol=2e-4, atol=1e-6)     # fp32 vs float64
+    if same_sel.all():
+        assert abs(float(loss) - o_loss) < 1e-5 * max(1.0, o_loss)
+    # gradients against the float64 torch graph with the kernel's own selection
+    a2, r2, e2 = (x.detach().double().requires_grad_(True) for x in (alb, rough, env))
+    t_loss, t_irr = _torch_loss(cam, e2, sc, dirs, areas, vis, hit2, uv, radiances, 0.8, n12, a2, r2, sel, only_first=False)
+    assert abs(float(loss) - float(t_loss)) < 1e-5 * max(1.0, float(t_loss))
+    if ref_grid:
+        # reference backward grid: gradient of S x (secondary sample 0) with the forward's sign
+        sign = torch.sign(t_irr.detach() - torch.nan_to_num(radiances.double()[torch.arange(P, device=dev), sel.long()] * 0.8))
+        _, f_irr = _torch_loss(cam, e2, sc, dirs, areas, vis, hit2, uv, radiances, 0.8, n12, a2, r2, sel, only_first=True)
+        (3.0 * (f_irr * sign).sum() / (3 * P)).backward()
+    else:
+        (3.0 * t_loss).backward()
+    for got, want, name in ((alb.grad, a2.grad, "albedo"), (rough.grad, r2.grad, "roughness"), (env.grad, e2.grad, "env")):
+        err = float((got.double() - want).abs().max())
+        scale = float(want.abs().max())
+        assert scale > 0, name
+        assert err < 2e-4 * scale, (name, err, scale)
+    assert not bool(rough.grad[:, 1:].any())                              # only column 0 is read (:1281)
