@@ -211,6 +211,7 @@ int svgir_mark_visible(int variant, int P, const float* means3D, const float* vi
  * scene/envmap.py:54-72); the optional per-vertex metallic follows the legacy CUDA
  * render_equation (rgss-rasterization/render_equation.cu:55-190: f_d=(1-m)base/pi,
  * F0=0.04(1-m)+base*m).  All [N,12] tensors are channel-major (R v0..v3, G v0..v3, B v0..v3). */
+#define SVGIR_SHADE_ENV_COPIES 16   /* replicas of the env-gradient accumulator (same-address reductions serialise) */
 typedef struct svgir_shade_cfg {
     int32_t N, Ns;            /* surfels, light samples per surfel */
     int32_t env_h, env_w;     /* lat-long env map size */
@@ -297,7 +298,7 @@ typedef struct svgir_shade_grads {
     const float* g_pack;
     const float* sum_direct;    /* [N,12] written by svgir_shade_forward (required) */
     const float* sum_indirect;  /* [N,12] or NULL; required when g_direct / g_indirect are given */
-    float* d_env_scratch;       /* [env_h,env_w,4] scratch (library zeroes it); required with d_env */
+    float* d_env_scratch;       /* [SVGIR_SHADE_ENV_COPIES,env_h,env_w,4] scratch (library zeroes it); required with d_env */
     int32_t g_row_stride, g_mean_vis_stride, g_mean_stride, reserved_;
     float* d_means3D;           /* [N,3] += (atomic) -d/d(campos - means3D); required when in->viewdirs is NULL */
 } svgir_shade_grads;
@@ -581,6 +582,7 @@ int svgir_densify_split(long long n_new, long long first_split, const int32_t* s
  * place is listed in DESIGN.md Appendix C (R1-R5). */
 #define SVGIR_RADIANCE_RECORD_FLOATS 32
 #define SVGIR_RADIANCE_SCRATCH_FLOATS 2048
+#define SVGIR_RADIANCE_ENV_COPIES 32
 
 /* One 128-byte record per surfel for the closest-hit query: centre, opacity, the rotation columns
  * (matrixFromRotationQuaternions, intersect_test.slang:224-249; rotations [P,4] raw (r,x,y,z)), the first two scales
@@ -594,7 +596,7 @@ int svgir_radiance_pack_surfels(int P, const float* means3D, const float* scales
  * to hit (closest facing surfel with alpha >= 1/255 in [t_min, 0.2), t_min 0.042 then 0.01) while T > 0.001, summing
  * eval_sh(shs[hit], centre - origin) * alpha * T. radiance [N,S,3] (clamped to [0,10]), visibility [N,S] (T, or 0 once
  * T < 0.2), hit_index [N,S] (first hit or -1), uv [N,S,2] (of the first hit). shs [P,16,3].
- * self_mod: a hit on surfel (first_index + n) % self_mod ... is ignored -- see below:
+ * Which surfel a ray ignores:
  *   self_mod == 0  the ray ignores its own surfel, index first_index + n (what the kernel means to do);
  *   self_mod  > 0  the reference's behaviour when update_radiace feeds it chunks of self_mod surfels: the kernel
  *                  compares the hit with the CHUNK-LOCAL index (intersect_test.slang:1931), i.e. ignores surfel
@@ -633,18 +635,19 @@ typedef struct svgir_radiance_loss_in {
     float* env_act_scratch;      /* [env_h*env_w*3] */
 } svgir_radiance_loss_in;
 
-/* loss [1] = mean |irradiance - nan_to_num(radiances[n, sel[n]] * ratio)| over [P,3]; irradiance [P,3] and
- * sample_index [P] (= max_idx, gaussian_model.py:565) are written for the backward; scratch
- * [SVGIR_RADIANCE_SCRATCH_FLOATS]. The sum over secondary samples is complete and deterministic in order (the
- * reference adds with a non-atomic read-modify-write from S threads, intersect_test.slang:1371-1373). */
+/* loss [1] = mean |irradiance - nan_to_num(radiances[n, sel[n]] * ratio)| over [P,3]. Written: irradiance [P,3];
+ * sample_index [P] (= max_idx, gaussian_model.py:565; may be NULL); saved [P,8] (16-B aligned: per surfel the view
+ * vector of the selected sample, the surfel it hit, the target colour -- what the backward needs). scratch
+ * [SVGIR_RADIANCE_SCRATCH_FLOATS]. The sum over secondary samples is complete and fixed in order (the reference adds
+ * with a non-atomic read-modify-write from S threads, intersect_test.slang:1371-1373). */
 int svgir_radiance_loss_forward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in, float* loss,
-                                float* irradiance, int32_t* sample_index, float* scratch, void* stream);
+                                float* irradiance, int32_t* sample_index, float* saved, float* scratch, void* stream);
 
 /* Adds grad_loss * dloss/d{albedo, roughness[:,0], env} into d_albedo [P,12], d_roughness [P,rough_stride] (atomic;
- * zero them first) and d_env [env_h,env_w,3] (+=, through d_env_scratch [env_h*env_w*4]). grad_loss: device scalar or
- * NULL (= 1). Any of the three destinations may be NULL. */
+ * zero them first) and d_env [env_h,env_w,3] (+=, through d_env_scratch [SVGIR_RADIANCE_ENV_COPIES*env_h*env_w*4]). grad_loss: device scalar or
+ * NULL (= 1). irradiance / saved: as the forward wrote them. Any of the three destinations may be NULL. */
 int svgir_radiance_loss_backward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in,
-                                 const float* grad_loss, const float* irradiance, const int32_t* sample_index,
+                                 const float* grad_loss, const float* irradiance, const float* saved,
                                  float* d_albedo, float* d_roughness, float* d_env, float* d_env_scratch, void* stream);
 
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------

@@ -48,13 +48,15 @@ __device__ __forceinline__ void env_fetch(const float* env, int He, int We, cons
 // Env-map gradient scatter. sm_100 has no native shared-memory float atomic (atomicAdd on shared
 // compiles to a compare-and-swap loop that costs ~2 ms at the training shape), so the four bilinear
 // taps of a sample go straight to L2 as four fire-and-forget vector reductions
-// (REDG.E.ADD.F32x4) into a [He,We,4] accumulator; a tiny kernel folds it into d_env afterwards.
+// (REDG.E.ADD.F32x4) into a [He,We,4] accumulator; a tiny kernel folds it into d_env afterwards. Reductions on one
+// address serialise in L2 and 10^7 samples land on a few hundred texels, so the accumulator is replicated and every
+// CTA scatters into replica blockIdx % copies (measured on the radiance-consistency backward: 3.4 ms -> 0.8 ms).
 __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
 }
 
 // defined in shading.cu
 void launch_env_activate(int nenv, const float* param, float* act, int env_mode, cudaStream_t s);
-void launch_env_grad_finalize(int ntex, int env_mode, const float* acc, const float* env_param, float* d_env, cudaStream_t s);
+void launch_env_grad_finalize(int ntex, int copies, int env_mode, const float* acc, const float* env_param, float* d_env, cudaStream_t s);
 
 }  // namespace svgir

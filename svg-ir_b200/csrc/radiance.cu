@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(RC_THREADS) radiance_cache_kernel(
 // ---- radiance-consistency loss ---------------------------------------------------------------------------------
 static constexpr int RL_THREADS = 256;
 static constexpr int RL_WPC = RL_THREADS / 32;
+// The env-map gradient of ~10^7 samples lands on a few hundred texels: same-address reductions serialise in L2, so the
+// accumulator is replicated and each CTA scatters into copy blockIdx % ENV_COPIES; the finalize kernel folds the copies.
+static constexpr int ENV_COPIES = SVGIR_RADIANCE_ENV_COPIES;
 
 struct RLArgs {
     int P, S, He, We, env_mode, rough_stride, ref_grid;
@@ -247,9 +250,22 @@ __device__ __forceinline__ float brdf_specular(float Vx, float Vy, float Vz, flo
     return frac / nom;
 }
 
-// Per-warp selection of the primary sample (gaussian_model.py:556-565): first index of the maximum of
-// dot(dirs[n,s], view_reflect) * (1 - visibility[n,s]).
-__device__ __forceinline__ int select_sample(const RLArgs& a, int n, int lane) {
+__device__ __forceinline__ float nan_to_num_f(float x) {
+    if (x != x) return 0.f;
+    if (x == INFINITY) return FLT_MAX;
+    if (x == -INFINITY) return -FLT_MAX;
+    return x;
+}
+
+// Selection of the primary sample (gaussian_model.py:549-565), a warp per surfel: first index of the maximum of
+// dot(dirs[n,s], view_reflect) * (1 - visibility[n,s]). Everything the irradiance kernels need about surfel n goes into
+// two float4: saved[2n] = { V = normalize(-dirs[n,sel]), bits(hit[n,sel]) }, saved[2n+1] = { target rgb, bits(sel) },
+// target = nan_to_num(radiances[n,sel] * ratio) (:323-324, :573).
+__global__ void __launch_bounds__(RL_THREADS) radiance_select_kernel(const RLArgs a, int32_t* __restrict__ sample_index,
+                                                                     float4* __restrict__ saved) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * RL_WPC + (threadIdx.x >> 5);
+    if (n >= a.P) return;
     const float cx = __ldg(a.campos), cy = __ldg(a.campos + 1), cz = __ldg(a.campos + 2);
     float vx = __ldg(a.means3D + 3 * (size_t)n) - cx, vy = __ldg(a.means3D + 3 * (size_t)n + 1) - cy,
           vz = __ldg(a.means3D + 3 * (size_t)n + 2) - cz;
@@ -272,14 +288,19 @@ __device__ __forceinline__ int select_sample(const RLArgs& a, int n, int lane) {
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
     }
-    return bi;
-}
-
-__device__ __forceinline__ float nan_to_num_f(float x) {
-    if (x != x) return 0.f;
-    if (x == INFINITY) return FLT_MAX;
-    if (x == -INFINITY) return -FLT_MAX;
-    return x;
+    if (lane == 0) {
+        const int sel = bi;
+        const int h = __ldg(a.hit + (size_t)n * a.S + sel);
+        const float* pd = a.dirs + ((size_t)n * a.S + sel) * 3;
+        float Vx = -__ldg(pd), Vy = -__ldg(pd + 1), Vz = -__ldg(pd + 2);
+        const float il = 1.f / sqrtf(Vx * Vx + Vy * Vy + Vz * Vz);
+        const float ratio = a.ratio ? __ldg(a.ratio) : 1.f;
+        const float* rp = a.radiances + ((size_t)n * a.S + sel) * 3;
+        saved[2 * (size_t)n] = make_float4(Vx * il, Vy * il, Vz * il, __int_as_float(h));
+        saved[2 * (size_t)n + 1] = make_float4(nan_to_num_f(__ldg(rp) * ratio), nan_to_num_f(__ldg(rp + 1) * ratio),
+                                               nan_to_num_f(__ldg(rp + 2) * ratio), __int_as_float(sel));
+        if (sample_index) sample_index[n] = sel;
+    }
 }
 
 struct HitSurfel { float nrm[12], alb[12], rough; };
@@ -300,50 +321,64 @@ __device__ __forceinline__ void load_hit_surfel(const RLArgs& a, int h, HitSurfe
     }
 }
 
-// One secondary sample of render_irradiance_sample (:1210-1311). Returns false when the term is zero.
+// Raw inputs of one secondary sample of render_irradiance_sample (:1210-1311): loaded unconditionally so that all the
+// gathers of a surfel are in flight together.
+struct SecRaw { int hit2; float rx, ry, rz, u, v, area; };
+__device__ __forceinline__ void load_secondary_raw(const RLArgs& a, int h, int s2, SecRaw& r) {
+    const size_t i = (size_t)h * a.S + (s2 < a.S ? s2 : 0);
+    r.hit2 = s2 < a.S ? __ldg(a.hit + i) : 0;           // anything but -1 closes the sample
+    const float* d = a.dirs + i * 3;
+    r.rx = __ldg(d); r.ry = __ldg(d + 1); r.rz = __ldg(d + 2);
+    const float2 uv = __ldg(reinterpret_cast<const float2*>(a.uv) + i);
+    r.u = uv.x; r.v = uv.y;
+    r.area = __ldg(a.areas + i);
+}
+
 struct SecSample { float Lx, Ly, Lz, Hx, Hy, Hz, VoH, w[4], E[3]; EnvTap tap; float escale; };
-__device__ __forceinline__ bool load_secondary(const RLArgs& a, int h, int s2, float Vx, float Vy, float Vz, SecSample& q) {
-    if (__ldg(a.hit + (size_t)h * a.S + s2) != -1) return false;
-    const float* d = a.dirs + ((size_t)h * a.S + s2) * 3;
-    const float rx = __ldg(d), ry = __ldg(d + 1), rz = __ldg(d + 2);
-    const float il = rsqrtf(rx * rx + ry * ry + rz * rz);
-    q.Lx = rx * il; q.Ly = ry * il; q.Lz = rz * il;
+__device__ __forceinline__ void make_secondary(const RLArgs& a, const SecRaw& r, float Vx, float Vy, float Vz, SecSample& q) {
+    const float il = rsqrtf(r.rx * r.rx + r.ry * r.ry + r.rz * r.rz);
+    q.Lx = r.rx * il; q.Ly = r.ry * il; q.Lz = r.rz * il;
     float hx = Vx + q.Lx, hy = Vy + q.Ly, hz = Vz + q.Lz;
     const float hl = rsqrtf(hx * hx + hy * hy + hz * hz);
     q.Hx = hx * hl; q.Hy = hy * hl; q.Hz = hz * hl;
     q.VoH = fminf(fmaxf(Vx * q.Hx + Vy * q.Hy + Vz * q.Hz, 1e-6f), 1.f);
-    const float u = __ldg(a.uv + ((size_t)h * a.S + s2) * 2), v = __ldg(a.uv + ((size_t)h * a.S + s2) * 2 + 1);
-    q.w[0] = (1 - u) * (1 - v); q.w[1] = u * (1 - v); q.w[2] = (1 - u) * v; q.w[3] = u * v;
+    q.w[0] = (1 - r.u) * (1 - r.v); q.w[1] = r.u * (1 - r.v); q.w[2] = (1 - r.u) * r.v; q.w[3] = r.u * r.v;
     // envmap[h,s2] = direct_light(dirs[h,s2]) * areas[h,s2] (gaussian_model.py:547), on the raw direction
-    q.tap = env_coords(rx, ry, rz, a.He, a.We);
-    q.escale = a.env_scale * __ldg(a.areas + (size_t)h * a.S + s2);
+    q.tap = env_coords(r.rx, r.ry, r.rz, a.He, a.We);
+    q.escale = a.env_scale * r.area;
     float e[3];
     env_fetch(a.env_act, a.He, a.We, q.tap, e);
     q.E[0] = e[0] * q.escale; q.E[1] = e[1] * q.escale; q.E[2] = e[2] * q.escale;
-    return true;
 }
 
-__global__ void __launch_bounds__(RL_THREADS) radiance_loss_fwd_kernel(const RLArgs a, float* __restrict__ irradiance,
-                                                                       int32_t* __restrict__ sample_index,
-                                                                       float* __restrict__ partials) {
+__global__ void __launch_bounds__(RL_THREADS, 3) radiance_loss_fwd_kernel(const RLArgs a, const float4* __restrict__ saved,
+                                                                          float* __restrict__ irradiance,
+                                                                          float* __restrict__ partials) {
     __shared__ float wsum[RL_WPC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_S = 1.f / (float)a.S;
-    const float ratio = a.ratio ? __ldg(a.ratio) : 1.f;
+    const int stride = gridDim.x * RL_WPC;
     float loss_acc = 0.f;
-    for (int n = blockIdx.x * RL_WPC + warp; n < a.P; n += gridDim.x * RL_WPC) {
-        const int sel = select_sample(a, n, lane);
-        const int h = __ldg(a.hit + (size_t)n * a.S + sel);
+    int n = blockIdx.x * RL_WPC + warp;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    if (n < a.P) { A = __ldg(saved + 2 * (size_t)n); B = __ldg(saved + 2 * (size_t)n + 1); }
+    while (n < a.P) {
+        const int n_next = n + stride;
+        float4 An = A, Bn = B;
+        if (n_next < a.P) { An = __ldg(saved + 2 * (size_t)n_next); Bn = __ldg(saved + 2 * (size_t)n_next + 1); }
+        const int h = __float_as_int(A.w);
         float irr[3] = {0.f, 0.f, 0.f};
         if (h != -1) {
-            const float* pd = a.dirs + ((size_t)n * a.S + sel) * 3;
-            float Vx = -__ldg(pd), Vy = -__ldg(pd + 1), Vz = -__ldg(pd + 2);
-            { const float il = 1.f / sqrtf(Vx * Vx + Vy * Vy + Vz * Vz); Vx *= il; Vy *= il; Vz *= il; }
+            const float Vx = A.x, Vy = A.y, Vz = A.z;
             HitSurfel hs;
             load_hit_surfel(a, h, hs);
+#pragma unroll 2
             for (int s2 = lane; s2 < a.S; s2 += 32) {
+                SecRaw raw;
+                load_secondary_raw(a, h, s2, raw);
+                if (raw.hit2 != -1) continue;
                 SecSample q;
-                if (!load_secondary(a, h, s2, Vx, Vy, Vz, q)) continue;
+                make_secondary(a, raw, Vx, Vy, Vz, q);
                 float spec = 0.f, mix[3] = {0.f, 0.f, 0.f}, dummy;
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
@@ -363,14 +398,10 @@ __global__ void __launch_bounds__(RL_THREADS) radiance_loss_fwd_kernel(const RLA
             }
         }
         if (lane == 0) {
-            sample_index[n] = sel;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                irradiance[3 * (size_t)n + c] = irr[c];
-                const float tgt = nan_to_num_f(__ldg(a.radiances + ((size_t)n * a.S + sel) * 3 + c) * ratio);
-                loss_acc += fabsf(irr[c] - tgt);
-            }
+            irradiance[3 * (size_t)n] = irr[0]; irradiance[3 * (size_t)n + 1] = irr[1]; irradiance[3 * (size_t)n + 2] = irr[2];
+            loss_acc += fabsf(irr[0] - B.x) + fabsf(irr[1] - B.y) + fabsf(irr[2] - B.z);
         }
+        n = n_next; A = An; B = Bn;
     }
     if (lane == 0) wsum[warp] = loss_acc;
     __syncthreads();
@@ -396,88 +427,103 @@ __global__ void __launch_bounds__(256) radiance_loss_reduce_kernel(int nblocks, 
     if (threadIdx.x == 0) loss[0] = sh[0] * scale;
 }
 
-__global__ void __launch_bounds__(RL_THREADS) radiance_loss_bwd_kernel(const RLArgs a, const float* __restrict__ grad_loss,
-                                                                       const float* __restrict__ irradiance,
-                                                                       const int32_t* __restrict__ sample_index,
-                                                                       float* __restrict__ d_albedo,
-                                                                       float* __restrict__ d_roughness,
-                                                                       float* __restrict__ d_env_acc) {
+__global__ void __launch_bounds__(RL_THREADS, 2) radiance_loss_bwd_kernel(const RLArgs a, const float* __restrict__ grad_loss,
+                                                                          const float4* __restrict__ saved,
+                                                                          const float* __restrict__ irradiance,
+                                                                          float* __restrict__ d_albedo,
+                                                                          float* __restrict__ d_roughness,
+                                                                          float* __restrict__ d_env_acc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_S = 1.f / (float)a.S;
-    const float ratio = a.ratio ? __ldg(a.ratio) : 1.f;
     const float gscale = (grad_loss ? __ldg(grad_loss) : 1.f) / (3.f * (float)a.P);
-    for (int n = blockIdx.x * RL_WPC + warp; n < a.P; n += gridDim.x * RL_WPC) {
-        const int sel = __ldg(sample_index + n);
-        const int h = __ldg(a.hit + (size_t)n * a.S + sel);
-        if (h == -1) continue;
-        float G[3];
-        bool any = false;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float d = __ldg(irradiance + 3 * (size_t)n + c) -
-                            nan_to_num_f(__ldg(a.radiances + ((size_t)n * a.S + sel) * 3 + c) * ratio);
-            G[c] = (d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f)) * inv_S;    // sign(x - y) / numel, and the 1/S of :1299
-            any |= G[c] != 0.f;
+    const int stride = gridDim.x * RL_WPC;
+    float* env_copy = d_env_acc ? d_env_acc + (size_t)(blockIdx.x % ENV_COPIES) * a.He * a.We * 4 : nullptr;
+    int n = blockIdx.x * RL_WPC + warp;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    float I0 = 0.f, I1 = 0.f, I2 = 0.f;
+    if (n < a.P) {
+        A = __ldg(saved + 2 * (size_t)n); B = __ldg(saved + 2 * (size_t)n + 1);
+        I0 = __ldg(irradiance + 3 * (size_t)n); I1 = __ldg(irradiance + 3 * (size_t)n + 1); I2 = __ldg(irradiance + 3 * (size_t)n + 2);
+    }
+    while (n < a.P) {
+        const int n_next = n + stride;
+        float4 An = A, Bn = B;
+        float J0 = 0.f, J1 = 0.f, J2 = 0.f;
+        if (n_next < a.P) {
+            An = __ldg(saved + 2 * (size_t)n_next); Bn = __ldg(saved + 2 * (size_t)n_next + 1);
+            J0 = __ldg(irradiance + 3 * (size_t)n_next); J1 = __ldg(irradiance + 3 * (size_t)n_next + 1);
+            J2 = __ldg(irradiance + 3 * (size_t)n_next + 2);
         }
-        if (!any) continue;
-        const float* pd = a.dirs + ((size_t)n * a.S + sel) * 3;
-        float Vx = -__ldg(pd), Vy = -__ldg(pd + 1), Vz = -__ldg(pd + 2);
-        { const float il = 1.f / sqrtf(Vx * Vx + Vy * Vy + Vz * Vz); Vx *= il; Vy *= il; Vz *= il; }
-        HitSurfel hs;
-        load_hit_surfel(a, h, hs);
-        float acc[13];                                   // 12 albedo entries (4*c + v) + roughness
+        const int h = __float_as_int(A.w);
+        float G[3];
+        {   // sign(x - y) / numel, and the 1/S of :1299
+            const float d0 = I0 - B.x, d1 = I1 - B.y, d2 = I2 - B.z;
+            G[0] = (d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f)) * inv_S;
+            G[1] = (d1 > 0.f ? gscale : (d1 < 0.f ? -gscale : 0.f)) * inv_S;
+            G[2] = (d2 > 0.f ? gscale : (d2 < 0.f ? -gscale : 0.f)) * inv_S;
+        }
+        if (h != -1 && (G[0] != 0.f || G[1] != 0.f || G[2] != 0.f)) {
+            const float Vx = A.x, Vy = A.y, Vz = A.z;
+            HitSurfel hs;
+            load_hit_surfel(a, h, hs);
+            float acc[13];                                   // 12 albedo entries (4*c + v) + roughness
 #pragma unroll
-        for (int k = 0; k < 13; k++) acc[k] = 0.f;
-        // reference-grid mode: every one of the S backward threads differentiates secondary sample 0
-        const int s_end = a.ref_grid ? 1 : a.S;
-        const float rep = a.ref_grid ? (float)a.S : 1.f;
-        for (int s2 = lane; s2 < s_end; s2 += 32) {
-            SecSample q;
-            if (!load_secondary(a, h, s2, Vx, Vy, Vz, q)) continue;
-            float spec = 0.f, dspec = 0.f, mix[3] = {0.f, 0.f, 0.f};
+            for (int k = 0; k < 13; k++) acc[k] = 0.f;
+            // reference-grid mode: every one of the S backward threads differentiates secondary sample 0
+            const int s_end = a.ref_grid ? 1 : a.S;
+            const float rep = a.ref_grid ? (float)a.S : 1.f;
+#pragma unroll 2
+            for (int s2 = lane; s2 < s_end; s2 += 32) {
+                SecRaw raw;
+                load_secondary_raw(a, h, s2, raw);
+                if (raw.hit2 != -1) continue;
+                SecSample q;
+                make_secondary(a, raw, Vx, Vy, Vz, q);
+                float spec = 0.f, dspec = 0.f, mix[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                float ds;
-                const float sp = brdf_specular<true>(Vx, Vy, Vz, q.Lx, q.Ly, q.Lz, q.Hx, q.Hy, q.Hz, q.VoH, hs.nrm[v],
-                                                     hs.nrm[4 + v], hs.nrm[8 + v], hs.rough, ds);
-                spec += q.w[v] * sp;
-                dspec += q.w[v] * ds;
+                for (int v = 0; v < 4; v++) {
+                    float ds;
+                    const float sp = brdf_specular<true>(Vx, Vy, Vz, q.Lx, q.Ly, q.Lz, q.Hx, q.Hy, q.Hz, q.VoH, hs.nrm[v],
+                                                         hs.nrm[4 + v], hs.nrm[8 + v], hs.rough, ds);
+                    spec += q.w[v] * sp;
+                    dspec += q.w[v] * ds;
 #pragma unroll
-                for (int c = 0; c < 3; c++) mix[c] += q.w[v] * (hs.alb[4 * c + v] * (1.f / PI_F));
-            }
-            float ge[3], gsum = 0.f;
+                    for (int c = 0; c < 3; c++) mix[c] += q.w[v] * (hs.alb[4 * c + v] * (1.f / PI_F));
+                }
+                float ge[3], gsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float g = G[c] * rep;
-                const float gE = g * q.E[c];
+                for (int c = 0; c < 3; c++) {
+                    const float g = G[c] * rep;
+                    const float gE = g * q.E[c];
 #pragma unroll
-                for (int v = 0; v < 4; v++) acc[4 * c + v] += gE * q.w[v] * (1.f / PI_F);
-                gsum += gE;
-                ge[c] = g * (spec + mix[c]) * q.escale;    // d loss / d (bilinear env value)
-            }
-            acc[12] += gsum * dspec;
-            if (d_env_acc) {
-                const float wx0 = 1.f - q.tap.wx1, wy0 = 1.f - q.tap.wy1;
+                    for (int v = 0; v < 4; v++) acc[4 * c + v] += gE * q.w[v] * (1.f / PI_F);
+                    gsum += gE;
+                    ge[c] = g * (spec + mix[c]) * q.escale;    // d loss / d (bilinear env value)
+                }
+                acc[12] += gsum * dspec;
+                if (d_env_acc) {
+                    const float wx0 = 1.f - q.tap.wx1, wy0 = 1.f - q.tap.wy1;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x = q.tap.x0 + (k & 1), y = q.tap.y0 + (k >> 1);
-                    if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
-                    const float w = ((k & 1) ? q.tap.wx1 : wx0) * ((k >> 1) ? q.tap.wy1 : wy0);
-                    red_add_v4(d_env_acc + ((size_t)y * a.We + x) * 4, ge[0] * w, ge[1] * w, ge[2] * w);
+                    for (int k = 0; k < 4; k++) {
+                        const int x = q.tap.x0 + (k & 1), y = q.tap.y0 + (k >> 1);
+                        if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
+                        const float w = ((k & 1) ? q.tap.wx1 : wx0) * ((k >> 1) ? q.tap.wy1 : wy0);
+                        red_add_v4(env_copy + ((size_t)y * a.We + x) * 4, ge[0] * w, ge[1] * w, ge[2] * w);
+                    }
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 13; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+            float mine = 0.f;   // lane k adds entry k
+#pragma unroll
+            for (int k = 0; k < 13; k++) if (lane == k) mine = acc[k];
+            if (lane < 12) { if (d_albedo && mine != 0.f) atomicAdd(d_albedo + (size_t)h * 12 + lane, mine); }
+            else if (lane == 12) { if (d_roughness && mine != 0.f) atomicAdd(d_roughness + (size_t)h * a.rough_stride, mine); }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 13; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        }
-        // lane k adds entry k
-        float mine = 0.f;
-#pragma unroll
-        for (int k = 0; k < 13; k++) if (lane == k) mine = acc[k];
-        if (lane < 12) { if (d_albedo && mine != 0.f) atomicAdd(d_albedo + (size_t)h * 12 + lane, mine); }
-        else if (lane == 12) { if (d_roughness && mine != 0.f) atomicAdd(d_roughness + (size_t)h * a.rough_stride, mine); }
+        n = n_next; A = An; B = Bn; I0 = J0; I1 = J1; I2 = J2;
     }
 }
 
@@ -544,37 +590,39 @@ int svgir_radiance_cache_build(const svgir_bvh* b, int N, int S, int first_index
 }
 
 int svgir_radiance_loss_forward(const svgir_radiance_loss_cfg* c, const svgir_radiance_loss_in* in, float* loss,
-                                float* irradiance, int32_t* sample_index, float* scratch, void* stream) {
+                                float* irradiance, int32_t* sample_index, float* saved, float* scratch, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     RLArgs a;
     int rc = rl_prepare(c, in, a, s);
     if (rc) return rc;
-    if (!loss || !irradiance || !sample_index || !scratch) { set_error("radiance_loss_forward: missing output"); return SVGIR_ERR_INVALID; }
+    if (!loss || !irradiance || !saved || !scratch) { set_error("radiance_loss_forward: missing output"); return SVGIR_ERR_INVALID; }
+    if ((uintptr_t)saved & 15) { set_error("radiance_loss_forward: saved must be 16-byte aligned"); return SVGIR_ERR_INVALID; }
     if (c->P == 0) { cudaMemsetAsync(loss, 0, sizeof(float), s); return SVGIR_OK; }
     const int grid = rl_grid(c->P);
     static_assert(148 * 8 <= SVGIR_RADIANCE_SCRATCH_FLOATS, "scratch");
     { TimedScope t_("radiance_loss_fwd", s);
-      radiance_loss_fwd_kernel<<<grid, RL_THREADS, 0, s>>>(a, irradiance, sample_index, scratch);
+      radiance_select_kernel<<<(c->P + RL_WPC - 1) / RL_WPC, RL_THREADS, 0, s>>>(a, sample_index, (float4*)saved);
+      radiance_loss_fwd_kernel<<<grid, RL_THREADS, 0, s>>>(a, (const float4*)saved, irradiance, scratch);
       radiance_loss_reduce_kernel<<<1, 256, 0, s>>>(grid, 1.f / (3.f * (float)c->P), scratch, loss); }
     return check_launch("radiance_loss_forward", false, s);
 }
 
 int svgir_radiance_loss_backward(const svgir_radiance_loss_cfg* c, const svgir_radiance_loss_in* in, const float* grad_loss,
-                                 const float* irradiance, const int32_t* sample_index, float* d_albedo, float* d_roughness,
+                                 const float* irradiance, const float* saved, float* d_albedo, float* d_roughness,
                                  float* d_env, float* d_env_scratch, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     RLArgs a;
     int rc = rl_prepare(c, in, a, s);
     if (rc) return rc;
-    if (!irradiance || !sample_index) { set_error("radiance_loss_backward: irradiance / sample_index of the forward are required"); return SVGIR_ERR_INVALID; }
-    if (d_env && !d_env_scratch) { set_error("radiance_loss_backward: d_env needs d_env_scratch [env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
+    if (!irradiance || !saved || ((uintptr_t)saved & 15)) { set_error("radiance_loss_backward: irradiance / saved of the forward are required"); return SVGIR_ERR_INVALID; }
+    if (d_env && !d_env_scratch) { set_error("radiance_loss_backward: d_env needs d_env_scratch [SVGIR_RADIANCE_ENV_COPIES*env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
     if (c->P == 0) return SVGIR_OK;
     const int ntex = a.He * a.We;
-    if (d_env && cudaMemsetAsync(d_env_scratch, 0, (size_t)ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+    if (d_env && cudaMemsetAsync(d_env_scratch, 0, (size_t)ENV_COPIES * ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
     { TimedScope t_("radiance_loss_bwd", s);
-      radiance_loss_bwd_kernel<<<rl_grid(c->P), RL_THREADS, 0, s>>>(a, grad_loss, irradiance, sample_index, d_albedo, d_roughness,
+      radiance_loss_bwd_kernel<<<rl_grid(c->P), RL_THREADS, 0, s>>>(a, grad_loss, (const float4*)saved, irradiance, d_albedo, d_roughness,
                                                                    d_env ? d_env_scratch : nullptr); }
-    if (d_env) launch_env_grad_finalize(ntex, c->env_mode, d_env_scratch, in->env, d_env, s);
+    if (d_env) launch_env_grad_finalize(ntex, ENV_COPIES, c->env_mode, d_env_scratch, in->env, d_env, s);
     return check_launch("radiance_loss_backward", false, s);
 }
 

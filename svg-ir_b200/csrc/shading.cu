@@ -428,16 +428,17 @@ struct ShadeGradsK {
     float* d_base_color; float* d_roughness; float* d_metallic; float* d_normals; float* d_viewdirs;
     float* d_radiance;                           // [N,Ns,3] or null
     float* d_visibility;                         // [N,Ns] or null
-    float* d_env_acc;                            // [He,We,4] zeroed accumulator of the env gradient, or null
+    float* d_env_acc;                            // [SVGIR_SHADE_ENV_COPIES][He,We,4] zeroed accumulators of the env gradient, or null
     float* d_means3D;                            // fused view directions: [N,3] += -(gradient of the raw view vector)
     int accumulate;                              // += into d_base_color / d_roughness / d_metallic / d_normals
 };
 
-__global__ void env_grad_finalize_kernel(int ntex, int env_mode, const float* __restrict__ acc,
+__global__ void env_grad_finalize_kernel(int ntex, int copies, int env_mode, const float* __restrict__ acc,
                                          const float* __restrict__ env_param, float* __restrict__ d_env) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntex * 3) return;
-    float val = acc[(i / 3) * 4 + (i % 3)];
+    float val = 0.f;
+    for (int c = 0; c < copies; c++) val += acc[((size_t)c * ntex + i / 3) * 4 + (i % 3)];
     if (env_mode == 0) val = val / (1.f + expf(-env_param[i]));  // softplus'
     d_env[i] += val;
 }
@@ -474,6 +475,8 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
     constexpr int NACC = MET ? 10 : 7;   // per-vertex partial sums kept by every lane
     if (a.skip_flag && __ldg(a.skip_flag) != 0) return;   // the step's binning overflowed: contribute nothing
     const int nenv = a.He * a.We * 3;
+    // same-address reductions serialise in L2: each CTA scatters into one of SVGIR_SHADE_ENV_COPIES replicas of the accumulator
+    float* env_copy = g.d_env_acc ? g.d_env_acc + (size_t)(blockIdx.x % SVGIR_SHADE_ENV_COPIES) * a.He * a.We * 4 : nullptr;
     float* vu_all = smem_b;                                         // [WPC][4][VU_FLOATS]
     float* env_s = smem_b + WPC * 4 * VU_FLOATS;                    // activated env (if it fits)
     const float* env = a.env_act;
@@ -667,7 +670,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
                     const int x = sm.tap.x0 + (kk & 1), y = sm.tap.y0 + (kk >> 1);
                     if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
                     const float w = ((kk & 1) ? sm.tap.wx1 : wx0) * ((kk >> 1) ? sm.tap.wy1 : wy0);
-                    red_add_v4(g.d_env_acc + (size_t)(y * a.We + x) * 4, draw[0] * w, draw[1] * w, draw[2] * w);
+                    red_add_v4(env_copy + (size_t)(y * a.We + x) * 4, draw[0] * w, draw[1] * w, draw[2] * w);
                 }
             }
         }
@@ -825,8 +828,8 @@ __global__ void __launch_bounds__(256) direct_light_bwd_kernel(int n, int He, in
 void launch_env_activate(int nenv, const float* param, float* act, int env_mode, cudaStream_t s) {
     env_activate_kernel<<<(nenv + 255) / 256, 256, 0, s>>>(nenv, param, act, env_mode);
 }
-void launch_env_grad_finalize(int ntex, int env_mode, const float* acc, const float* env_param, float* d_env, cudaStream_t s) {
-    env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, env_mode, acc, env_param, d_env);
+void launch_env_grad_finalize(int ntex, int copies, int env_mode, const float* acc, const float* env_param, float* d_env, cudaStream_t s) {
+    env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, copies, env_mode, acc, env_param, d_env);
 }
 
 }  // namespace svgir
@@ -943,8 +946,8 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
                   gr->d_means3D, (c->flags & SVGIR_SHADE_ACCUMULATE) ? 1 : 0};
     const int ntex = a.He * a.We;
     if (gr->d_env) {
-        if (!gr->d_env_scratch) { set_error("shade_backward: d_env needs d_env_scratch [env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
-        if (cudaMemsetAsync(gr->d_env_scratch, 0, (size_t)ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+        if (!gr->d_env_scratch) { set_error("shade_backward: d_env needs d_env_scratch [SVGIR_SHADE_ENV_COPIES*env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
+        if (cudaMemsetAsync(gr->d_env_scratch, 0, (size_t)SVGIR_SHADE_ENV_COPIES * ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
     }
     {
         TimedScope ts_("shade_bwd", s);
@@ -952,7 +955,7 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
     }
     if (gr->d_env) {
         TimedScope ts_("env_grad_finalize", s);
-        env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, c->env_mode, gr->d_env_scratch, in->env, gr->d_env);
+        env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, SVGIR_SHADE_ENV_COPIES, c->env_mode, gr->d_env_scratch, in->env, gr->d_env);
     }
     return check_launch("shade_backward", c->debug, s);
 }

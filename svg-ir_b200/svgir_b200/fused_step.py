@@ -151,7 +151,7 @@ class FusedTrainStep:
         He, We = int(env_param.shape[-3]), int(env_param.shape[-2])
         self.env_hw = (He, We)
         self.env_act = torch.empty((He, We, 3), **f32)
-        self.env_scratch = torch.empty((He, We, 4), **f32)
+        self.env_scratch = torch.empty((shading.ENV_COPIES, He, We, 4), **f32)
         self.sums = torch.empty((P, 12), **f32)
         self.loss_out = torch.zeros(8, **f32)
         nblk = int(self.L.svgir_train_loss_blocks(W, H))

@@ -26,6 +26,7 @@ RADIANCE_ENV_READY = 1
 RADIANCE_BWD_REFERENCE_GRID = 2
 RECORD_FLOATS = 32
 SCRATCH_FLOATS = 2048
+ENV_COPIES = 32
 
 
 class RadianceLossCfg(C.Structure):
@@ -52,7 +53,7 @@ def _L():
         L.svgir_radiance_cache_build.argtypes = [C.POINTER(_bvh.BvhStruct), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
                                                  vp, vp, vp, vp, vp]
         L.svgir_radiance_cache_build.restype = C.c_int
-        L.svgir_radiance_loss_forward.argtypes = [C.POINTER(RadianceLossCfg), C.POINTER(RadianceLossIn), vp, vp, vp, vp, vp]
+        L.svgir_radiance_loss_forward.argtypes = [C.POINTER(RadianceLossCfg), C.POINTER(RadianceLossIn), vp, vp, vp, vp, vp, vp]
         L.svgir_radiance_loss_forward.restype = C.c_int
         L.svgir_radiance_loss_backward.argtypes = [C.POINTER(RadianceLossCfg), C.POINTER(RadianceLossIn), vp, vp, vp, vp, vp,
                                                    vp, vp, vp]
@@ -153,18 +154,19 @@ class _RadianceLossFn(torch.autograd.Function):
         irr = torch.empty((P, 3), dtype=torch.float32, device=dev)
         sel = torch.empty((P,), dtype=torch.int32, device=dev)
         scratch = torch.empty((SCRATCH_FLOATS,), dtype=torch.float32, device=dev)
+        saved = torch.empty((P, 8), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.svgir_radiance_loss_forward(C.byref(cfg), C.byref(cin), loss.data_ptr(), irr.data_ptr(), sel.data_ptr(),
-                                                     scratch.data_ptr(), _stream(dev)), "radiance_loss_forward")
+                                                     saved.data_ptr(), scratch.data_ptr(), _stream(dev)), "radiance_loss_forward")
         ctx.cfg, ctx.cin, ctx.keep = cfg, cin, (t, hit_c, scratch_env)
-        ctx.save_for_backward(irr, sel)
+        ctx.save_for_backward(irr, saved)
         ctx.mark_non_differentiable(irr, sel)
         return loss[0], irr, sel
 
     @staticmethod
     def backward(ctx, g_loss, g_irr, _g_sel):
         L = _L()
-        irr, sel = ctx.saved_tensors
+        irr, saved = ctx.saved_tensors
         t, _hit, _scr = ctx.keep
         cfg = ctx.cfg
         dev = irr.device
@@ -172,12 +174,12 @@ class _RadianceLossFn(torch.autograd.Function):
         d_alb = torch.zeros_like(t["albedo"]) if need_a else None
         d_rough = torch.zeros_like(t["roughness"]) if need_r else None
         d_env = torch.zeros_like(t["env"]) if need_e else None
-        d_env_scr = torch.empty((cfg.env_h * cfg.env_w * 4,), dtype=torch.float32, device=dev) if need_e else None
+        d_env_scr = torch.empty((ENV_COPIES * cfg.env_h * cfg.env_w * 4,), dtype=torch.float32, device=dev) if need_e else None
         g = g_loss.detach().reshape(1).float().contiguous()
         p = lambda x: None if x is None else x.data_ptr()
         with torch.cuda.device(dev):
             _lib.check(L.svgir_radiance_loss_backward(C.byref(cfg), C.byref(ctx.cin), g.data_ptr(), irr.data_ptr(),
-                                                      sel.data_ptr(), p(d_alb), p(d_rough), p(d_env), p(d_env_scr),
+                                                      saved.data_ptr(), p(d_alb), p(d_rough), p(d_env), p(d_env_scr),
                                                       _stream(dev)), "radiance_loss_backward")
         return (d_alb, d_rough, d_env) + (None,) * 13
 

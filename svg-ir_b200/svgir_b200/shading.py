@@ -93,6 +93,7 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+ENV_COPIES = 16       # SVGIR_SHADE_ENV_COPIES
 MODE_LEARNABLE = 0  # softplus(param), x2   (DirectLightMap)
 MODE_FIXED = 1      # linear map as given, x1 (EnvLight after its 32x64 resize)
 
@@ -177,7 +178,7 @@ class _ShadeFn(torch.autograd.Function):
                       _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), None)
         cg = ShadeGrads(*[_p(x) for x in gs], _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad),
                         _p(d_vis), _p(d_env), None, _p(sums[0]), _p(sums[1]),
-                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, 0, 0, 0, 0)
+                        _p(torch.empty((ENV_COPIES, He, We, 4), **f32)) if d_env is not None else None, 0, 0, 0, 0)
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
@@ -306,7 +307,7 @@ class _ShadePackedFn(torch.autograd.Function):
             gin = (vp, None, None, vp + 4 * 40, vp + 4 * 52, fp + 4 * 6, fp + 4 * 3, fp, None)
         cg = ShadeGrads(*gin, _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad), _p(d_vis),
                         _p(d_env), vp + 4 * 12, _p(sums[0]), _p(sums[1]) if sums.shape[0] > 1 else None,
-                        _p(torch.empty((He, We, 4), **f32)) if d_env is not None else None, VS, S, S, 0, _p(d_xyz))
+                        _p(torch.empty((ENV_COPIES, He, We, 4), **f32)) if d_env is not None else None, VS, S, S, 0, _p(d_xyz))
         if N > 0:
             with torch.cuda.device(dev):
                 _lib.check(L.svgir_shade_backward(C.byref(cfg), C.byref(cin), C.byref(cg), _stream(dev)), "shade_backward")
