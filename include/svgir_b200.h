@@ -609,6 +609,8 @@ int svgir_radiance_cache_build(const svgir_bvh* bvh, int N, int S, int first_ind
 #define SVGIR_RADIANCE_BWD_REFERENCE_GRID 2 /* backward: only secondary sample 0 carries gradient, S times over -- what
                                                the reference's backward launch computes (grid (N/256,1,S) with the
                                                sample index read from y, pbgi/renderer.py:224) */
+#define SVGIR_RADIANCE_NORMALS_VERTEX_MAJOR 4 /* normals is [P,4,3] (get_shading_normal as it is, element 3*v + c) instead of
+                                                the transposed [P,12] the reference hands to its kernel (:551) */
 typedef struct svgir_radiance_loss_cfg {
     int32_t P, S, env_h, env_w;
     int32_t env_mode;       /* as svgir_shade_cfg: 0 = learnable map (softplus, x2), 1 = fixed map */
@@ -633,6 +635,8 @@ typedef struct svgir_radiance_loss_in {
     const float* roughness;      /* [P,rough_stride] */
     const float* env;            /* [env_h,env_w,3] raw parameter */
     float* env_act_scratch;      /* [env_h*env_w*3] */
+    const int32_t* skip_flag;    /* optional device flag: nonzero = the backward adds nothing (the fused training step
+                                    passes its binning-overflow flag: an overflowed step contributes no gradient) */
 } svgir_radiance_loss_in;
 
 /* loss [1] = mean |irradiance - nan_to_num(radiances[n, sel[n]] * ratio)| over [P,3]. Written: irradiance [P,3];

@@ -211,11 +211,12 @@ static constexpr int RL_WPC = RL_THREADS / 32;
 static constexpr int ENV_COPIES = SVGIR_RADIANCE_ENV_COPIES;
 
 struct RLArgs {
-    int P, S, He, We, env_mode, rough_stride, ref_grid;
+    int P, S, He, We, env_mode, rough_stride, ref_grid, nrm_vmajor;
     float env_scale;
     const float *means3D, *campos, *geo_normal, *dirs, *areas, *vis, *uv, *radiances, *ratio, *normals, *albedo,
         *roughness, *env_act, *env_param;
     const int32_t* hit;
+    const int32_t* skip_flag;
 };
 
 // shading_brdf_simple (pbr.slang:283-330): specular part and, optionally, its derivative w.r.t. roughness.
@@ -310,7 +311,13 @@ __device__ __forceinline__ void load_hit_surfel(const RLArgs& a, int h, HitSurfe
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float4 nv = __ldg(np + k), av = __ldg(ap + k);
-        hs.nrm[4 * k] = nv.x; hs.nrm[4 * k + 1] = nv.y; hs.nrm[4 * k + 2] = nv.z; hs.nrm[4 * k + 3] = nv.w;
+        if (a.nrm_vmajor) {   // flat element e = 4k..4k+3 of [v][c] goes to slot 4*(e % 3) + e / 3
+            const float e4[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) hs.nrm[4 * ((4 * k + j) % 3) + (4 * k + j) / 3] = e4[j];
+        } else {
+            hs.nrm[4 * k] = nv.x; hs.nrm[4 * k + 1] = nv.y; hs.nrm[4 * k + 2] = nv.z; hs.nrm[4 * k + 3] = nv.w;
+        }
         hs.alb[4 * k] = av.x; hs.alb[4 * k + 1] = av.y; hs.alb[4 * k + 2] = av.z; hs.alb[4 * k + 3] = av.w;
     }
     hs.rough = __ldg(a.roughness + (size_t)h * a.rough_stride);
@@ -433,6 +440,7 @@ __global__ void __launch_bounds__(RL_THREADS, 2) radiance_loss_bwd_kernel(const 
                                                                           float* __restrict__ d_albedo,
                                                                           float* __restrict__ d_roughness,
                                                                           float* __restrict__ d_env_acc) {
+    if (a.skip_flag && __ldg(a.skip_flag) != 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_S = 1.f / (float)a.S;
     const float gscale = (grad_loss ? __ldg(grad_loss) : 1.f) / (3.f * (float)a.P);
@@ -537,11 +545,12 @@ static int rl_prepare(const svgir_radiance_loss_cfg* c, const svgir_radiance_los
     if (!(c->flags & SVGIR_RADIANCE_ENV_READY)) launch_env_activate(nenv, in->env, in->env_act_scratch, c->env_mode, s);
     a.P = c->P; a.S = c->S; a.He = c->env_h; a.We = c->env_w; a.env_mode = c->env_mode; a.rough_stride = c->rough_stride;
     a.ref_grid = (c->flags & SVGIR_RADIANCE_BWD_REFERENCE_GRID) ? 1 : 0;
+    a.nrm_vmajor = (c->flags & SVGIR_RADIANCE_NORMALS_VERTEX_MAJOR) ? 1 : 0;
     a.env_scale = c->env_mode == 0 ? 2.0f : 1.0f;
     a.means3D = in->means3D; a.campos = in->campos; a.geo_normal = in->geo_normal; a.dirs = in->incident_dirs;
     a.areas = in->incident_areas; a.vis = in->visibility; a.uv = in->uv; a.radiances = in->radiances;
     a.ratio = in->radiance_ratio; a.normals = in->normals; a.albedo = in->albedo; a.roughness = in->roughness;
-    a.env_act = in->env_act_scratch; a.env_param = in->env; a.hit = in->hit_index;
+    a.env_act = in->env_act_scratch; a.env_param = in->env; a.hit = in->hit_index; a.skip_flag = in->skip_flag;
     return SVGIR_OK;
 }
 

@@ -64,13 +64,16 @@ class FusedTrainStep:
     def __init__(self, pc, env_param: torch.Tensor, bg: torch.Tensor, cam, gt_image: torch.Tensor, bucket=None,
                  lambda_pbr: float = 1.0, lambda_normal: float = 0.02, zero_grads: bool = True,
                  reduce_in_step: bool = False, capacity: Optional[int] = None, surface_term: str = "depth2normal",
-                 image_mask: Optional[torch.Tensor] = None):
+                 image_mask: Optional[torch.Tensor] = None, radiance_cache=None, lambda_radiance: float = 0.05):
         """pc: pipeline.SurfelModel; cam: pipeline.ViewCamera whose tensors are the step's STATIC camera inputs (copy a
         new view into cam.block before each step); gt_image: the static ground-truth buffer [3,H,W].
         bucket: dist.FlatGradBucket over pc.trainable() + [env_param] (default: a private one, so that all parameter
         gradients are one memset); zero_grads=False leaves clearing it to the caller (multi-view accumulation).
         reduce_in_step (needs a bucket built on dist.PeerAllReduce): the gradient all-reduce over NVLink peer memory
-        is part of the step -- segment 0 on the side stream under the shading backward, the rest after it."""
+        is part of the step -- segment 0 on the side stream under the shading backward, the rest after it.
+        radiance_cache (radiance.RadianceCache after update()): adds lambda_radiance * get_radiance_loss
+        (gaussian_renderer/svgss.py:319-320, arguments/__init__.py:130) to the step: its kernels run on the side stream
+        under the rasteriser and add their albedo / roughness / env gradients before the shading backward adds its own."""
         self.L = _lib.lib()
         shading._L()
         losses._bind()
@@ -227,6 +230,32 @@ class FusedTrainStep:
         self.lgr = losses.TrainLossGrads(self.gimg["color"].data_ptr(), self.gimg["normal"].data_ptr(),
                                          self.gimg["depth"].data_ptr() if mode == losses.NORMAL_D2N else None,
                                          self.gimg["opacity"].data_ptr(), None, self.gimg["vfeature"].data_ptr())
+        # radiance-consistency term (optional)
+        self.rc = radiance_cache
+        self.lambda_radiance = float(lambda_radiance)
+        if self.rc is not None:
+            from . import radiance as _rad
+            _rad._L()
+            rc = self.rc
+            S2 = int(rc.incident_dirs.shape[1])
+            hit = rc.hemi_index_buffers.reshape(P, S2)
+            if hit.dtype != torch.int32 or not hit.is_contiguous():
+                raise RuntimeError("FusedTrainStep: radiance_cache.hemi_index_buffers must be contiguous int32")
+            for tns in (rc.incident_dirs, rc.incident_areas, rc.visibility_tracing, rc.uv_buffers, rc.radiances, rc.geo_normal):
+                if tns.dtype != torch.float32 or not tns.is_contiguous() or tns.shape[0] != P:
+                    raise RuntimeError("FusedTrainStep: radiance_cache tensors must be contiguous fp32 over the same surfels")
+            self.rad = {"irr": torch.empty((P, 3), **f32), "saved": torch.empty((P, 8), **f32),
+                        "scratch": torch.empty((_rad.SCRATCH_FLOATS,), **f32), "env_act": torch.empty((He, We, 3), **f32),
+                        "env_scratch": torch.empty((_rad.ENV_COPIES, He, We, 4), **f32), "loss": torch.zeros(1, **f32),
+                        "grad": torch.full((1,), self.lambda_radiance, **f32),
+                        "ratio": rc.radiance_ratio.detach().reshape(1).to(**f32).contiguous(), "hit": hit}
+            self.rcfg = _rad.RadianceLossCfg(P, S2, He, We, shading.MODE_LEARNABLE, _rad.RADIANCE_NORMALS_VERTEX_MAJOR,
+                                             int(pc.roughness.shape[1]), 0)   # pc.shading_normal is [P,4,3]
+            self.rin = _rad.RadianceLossIn(
+                pc.xyz.data_ptr(), cam.camera_center.data_ptr(), rc.geo_normal.data_ptr(), rc.incident_dirs.data_ptr(),
+                rc.incident_areas.data_ptr(), rc.visibility_tracing.data_ptr(), hit.data_ptr(), rc.uv_buffers.data_ptr(),
+                rc.radiances.data_ptr(), self.rad["ratio"].data_ptr(), pc.shading_normal.data_ptr(), pc.base_color.data_ptr(),
+                pc.roughness.data_ptr(), env3.data_ptr(), self.rad["env_act"].data_ptr(), t["num_rendered"][1:].data_ptr())
         self.cap = 0
         self._alloc_bins(capacity if capacity else raster._CAP_HINT.get((dev.index, P, W, H), 0))
         self.launches = 0
@@ -234,7 +263,8 @@ class FusedTrainStep:
             "render": self.img["color"], "depth": self.img["depth"], "geo_normal": self.img["normal"],
             "opacity": self.img["opacity"], "raw_feature": self.img["feature"], "raw_vfeature": self.img["vfeature"],
             "radii": self.radii, "weights": self.weights, "viewspace_grad": self.dmeans2D,
-            "diffuse_light": self.vfeats[:, 40:52], "loss_terms": self.loss_out})
+            "diffuse_light": self.vfeats[:, 40:52], "loss_terms": self.loss_out,
+            "loss_radiance": self.rad["loss"] if self.rc is not None else None})
 
     # ---------------------------------------------------------------------------------------------------------------
     def _bind_grads(self):
@@ -307,6 +337,19 @@ class FusedTrainStep:
             chk(L.svgir_raster_bin(cfg, cin, cst, cout, ss), "raster_bin")
             binned = torch.cuda.Event()
             binned.record(side)
+            if self.rc is not None:
+                # radiance-consistency term: needs the camera centre only. Its backward adds (atomically) into the same
+                # albedo / roughness / env gradients the shading backward accumulates into, so it is ordered before it;
+                # the overflow flag it tests is final once binning is (same stream).
+                r = self.rad
+                gv = self.gviews
+                chk(L.svgir_radiance_loss_forward(C.byref(self.rcfg), C.byref(self.rin), r["loss"].data_ptr(), r["irr"].data_ptr(),
+                                                  None, r["saved"].data_ptr(), r["scratch"].data_ptr(), ss), "radiance_loss_forward")
+                chk(L.svgir_radiance_loss_backward(C.byref(self.rcfg), C.byref(self.rin), r["grad"].data_ptr(), r["irr"].data_ptr(),
+                                                   r["saved"].data_ptr(), gv[5].data_ptr(), gv[6].data_ptr(), gv[8].data_ptr(),
+                                                   r["env_scratch"].data_ptr(), ss), "radiance_loss_backward")
+                rad_done = torch.cuda.Event()
+                rad_done.record(side)
             chk(L.svgir_shade_forward(C.byref(self.scfg_f), C.byref(self.sin), C.byref(self.sout), cs), "shade_forward")
             cur.wait_event(binned)
             chk(L.svgir_raster_composite(cfg, cin, cst, cout, cs), "raster_composite")
@@ -333,6 +376,8 @@ class FusedTrainStep:
                     L.svgir_shade_reserve_sms(self.peer.BG_GRID)
             done = torch.cuda.Event()
             done.record(side)
+            if self.rc is not None:
+                cur.wait_event(rad_done)
             chk(L.svgir_shade_backward(C.byref(self.scfg_b), C.byref(self.sin), C.byref(self.sgr), cs), "shade_backward")
             L.svgir_shade_reserve_sms(0)
             cur.wait_event(done)

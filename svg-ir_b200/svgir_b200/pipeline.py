@@ -344,8 +344,11 @@ class GraphedTrainingStep:
 
     def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
                  gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False,
-                 zero_in_graph: bool = True, fused: Optional[bool] = None):
+                 zero_in_graph: bool = True, fused: Optional[bool] = None, radiance_cache=None,
+                 lambda_radiance: float = 0.05):
         self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
+        # radiance_cache (fused path only): the step also carries lambda_radiance * get_radiance_loss (svgss.py:319-320)
+        self.radiance_cache, self.lambda_radiance = radiance_cache, lambda_radiance
         # zero_in_graph=False (needs `bucket`): the graph ACCUMULATES into the bucket instead of zeroing it first, so a
         # rank that renders several views per step replays it once per view and reduces once (C4: 8 views / step);
         # the caller zeroes the bucket at the start of the step. A (re-)capture leaves the bucket's content untouched,
@@ -362,6 +365,8 @@ class GraphedTrainingStep:
         self.fused = FUSED_STEP if fused is None else bool(fused)
         if self.fused and self.reduce_in_graph and getattr(bucket, "segment_peer", None) is None:
             self.fused = False   # NCCL collectives inside the step are issued through the autograd hooks
+        if radiance_cache is not None and not self.fused:
+            raise ValueError("radiance_cache is carried by the fused step only")
         self.flag_host = raster.pinned_forever((1,), torch.float32) if self.reduce_in_graph else None
         dev = pc.xyz.device
         self.dev = dev
@@ -396,7 +401,8 @@ class GraphedTrainingStep:
         keep = None if self.zero_in_graph else self.bucket.flat.clone()   # accumulated gradients survive the capture
         if self.fs is None:
             self.fs = fused_step.FusedTrainStep(self.pc, self.env, self.bg, self.cam, self.gt, bucket=self.bucket,
-                                                zero_grads=self.zero_in_graph, reduce_in_step=self.reduce_in_graph)
+                                                zero_grads=self.zero_in_graph, reduce_in_step=self.reduce_in_graph,
+                                                radiance_cache=self.radiance_cache, lambda_radiance=self.lambda_radiance)
             if self.bucket is None:
                 self.bucket_private = self.fs.bucket
         fs = self.fs

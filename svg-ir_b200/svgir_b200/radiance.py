@@ -24,6 +24,7 @@ from .shading import env_of
 
 RADIANCE_ENV_READY = 1
 RADIANCE_BWD_REFERENCE_GRID = 2
+RADIANCE_NORMALS_VERTEX_MAJOR = 4
 RECORD_FLOATS = 32
 SCRATCH_FLOATS = 2048
 ENV_COPIES = 32
@@ -37,7 +38,7 @@ class RadianceLossCfg(C.Structure):
 class RadianceLossIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "means3D", "campos", "geo_normal", "incident_dirs", "incident_areas", "visibility", "hit_index", "uv", "radiances",
-        "radiance_ratio", "normals", "albedo", "roughness", "env", "env_act_scratch")]
+        "radiance_ratio", "normals", "albedo", "roughness", "env", "env_act_scratch", "skip_flag")]
 
 
 _BOUND = False
@@ -138,6 +139,9 @@ class _RadianceLossFn(torch.autograd.Function):
         hit_c = hit.detach().contiguous()
         if hit_c.dtype != torch.int32:
             hit_c = hit_c.int()
+        if t["normals"].dim() == 3 and t["normals"].shape == (P, 4, 3):
+            flags = int(flags) | RADIANCE_NORMALS_VERTEX_MAJOR          # get_shading_normal as it is
+            t["normals"] = t["normals"].reshape(P, 12)
         if t["albedo"].shape != (P, 12) or t["normals"].shape != (P, 12) or t["roughness"].dim() != 2 or \
                 t["roughness"].shape[0] != P or t["dirs"].shape != (P, S, 3) or t["radiances"].shape != (P, S, 3) or \
                 t["uv"].numel() != P * S * 2 or t["vis"].numel() != P * S or t["areas"].numel() != P * S:
@@ -149,7 +153,7 @@ class _RadianceLossFn(torch.autograd.Function):
                              t["areas"].data_ptr(), t["vis"].data_ptr(), hit_c.data_ptr(), t["uv"].data_ptr(),
                              t["radiances"].data_ptr(), None if t["ratio"] is None else t["ratio"].data_ptr(),
                              t["normals"].data_ptr(), t["albedo"].data_ptr(), t["roughness"].data_ptr(), t["env"].data_ptr(),
-                             scratch_env.data_ptr())
+                             scratch_env.data_ptr(), None)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         irr = torch.empty((P, 3), dtype=torch.float32, device=dev)
         sel = torch.empty((P,), dtype=torch.int32, device=dev)
@@ -187,8 +191,9 @@ class _RadianceLossFn(torch.autograd.Function):
 def radiance_loss(cam_center, direct_light, xyz, geo_normal, incident_dirs, incident_areas, visibility, hit_indices, uvs,
                   radiances, radiance_ratio, normals, albedo, roughness, reference_backward_grid: bool = False,
                   return_aux: bool = False):
-    """get_radiance_loss (scene/gaussian_model.py:544-575) on explicit tensors. `normals` / `albedo` [P,12] with element
-    4*c + v (get_shading_normal.transpose(1,2).reshape(P,-1), get_albedo), roughness [P,V]; `radiances` already detached
+    """get_radiance_loss (scene/gaussian_model.py:544-575) on explicit tensors. `normals` [P,12] with element 4*c + v
+    (get_shading_normal.transpose(1,2).reshape(P,-1), as the reference passes it) or [P,4,3] (get_shading_normal itself,
+    read in place); `albedo` [P,12] element 4*c + v (get_albedo); roughness [P,V]; `radiances` already detached
     like GaussianModel.get_radiances does (:323-324); radiance_ratio a scalar tensor or None."""
     env, mode, tr = env_of(direct_light)
     if tr is not None:
@@ -210,6 +215,7 @@ class RadianceCache:
         self.radiances = self.init_radiances = self.radiance_mean = None
         self.hemi_index_buffers = self.uv_buffers = None
         self.radiance_ratio: Optional[torch.Tensor] = None
+        self.geo_normal = None
 
     @torch.no_grad()
     def update(self, xyz, scaling, rotation, opacity, geo_normal, inverse_covariance, features, sample_num: int = 64,
@@ -221,6 +227,7 @@ class RadianceCache:
         P = xyz.shape[0]
         dev = xyz.device
         self.tracer = _bvh.RayTracer(xyz, scaling, rotation)
+        self.geo_normal = geo_normal.detach()
         records = pack_surfels(xyz, scaling, rotation, geo_normal, opacity, inverse_covariance)
         chunk = P // ((sample_num - 1) // 24 + 1)
         if reference_chunking and 0 < chunk < P:
@@ -249,7 +256,7 @@ class RadianceCache:
 
     def loss(self, cam_center, direct_light, xyz, geo_normal, shading_normal, albedo, roughness, **kw):
         """get_radiance_loss. shading_normal [P,V,3] (get_shading_normal) or already [P,12]."""
-        n12 = shading_normal if shading_normal.dim() == 2 else shading_normal.transpose(1, 2).reshape(shading_normal.shape[0], -1)
+        n12 = shading_normal
         return radiance_loss(cam_center, direct_light, xyz, geo_normal, self.incident_dirs, self.incident_areas,
                              self.visibility_tracing, self.hemi_index_buffers, self.uv_buffers, self.radiances.detach(),
                              self.radiance_ratio.detach(), n12, albedo, roughness, **kw)

@@ -166,3 +166,53 @@ def test_prefetched_inputs_match_inline():
         rb.finish()
         assert float(rb.loss) == float(la)
         assert torch.equal(rb.res["render"], ra.res["render"])
+
+
+def _quat_R(q):
+    q = q / q.norm(dim=1, keepdim=True)
+    r, x, y, z = q.unbind(1)
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+
+
+def test_fused_step_carries_the_radiance_consistency_term():
+    """FusedTrainStep(radiance_cache=...) = training_step + lambda_radiance * get_radiance_loss (svgss.py:319-320): the
+    term's kernels run on the side stream and add into the same gradient buffers."""
+    from svgir_b200 import fused_step, radiance
+    pipeline, cloud, mats, cams, gts, dev = _setup(P=6000, Ns=16)
+    bg = torch.zeros(3, device=dev)
+    pc_e, env_e = _model(pipeline, cloud, mats, dev)
+    pc_f, env_f = _model(pipeline, cloud, mats, dev)
+    with torch.no_grad():
+        R = _quat_R(pc_f.rotation)
+        sc = pc_f.scaling.clone()
+        sc[:, 2] = 1e-3
+        Sinv = R @ torch.diag_embed(1.0 / sc ** 2) @ R.transpose(1, 2)
+        ci = torch.stack([Sinv[:, 0, 0], Sinv[:, 0, 1], Sinv[:, 0, 2], Sinv[:, 1, 1], Sinv[:, 1, 2], Sinv[:, 2, 2]], 1).contiguous()
+        gn = R[:, :, 2].contiguous()
+        torch.manual_seed(5)
+        rc = radiance.RadianceCache().update(pc_f.xyz, sc, pc_f.rotation, pc_f.opacity, gn, ci, pc_f.shs, sample_num=16)
+        rc.radiances = torch.rand_like(rc.radiances)              # a target the irradiance cannot already match
+    assert float((rc.hemi_index_buffers >= 0).float().mean()) > 0.01
+    lam = 0.05
+    cam = pipeline.blocked_camera(cams[0].image_height, cams[0].image_width, cams[0].tanfovx, cams[0].tanfovy,
+                                  cams[0].world_view_transform, cams[0].full_proj_transform, cams[0].camera_center,
+                                  cams[0].patch_bbox, cams[0].prcppoint, device=dev)
+    gt = gts[0].clone()
+    fs = fused_step.FusedTrainStep(pc_f, env_f, bg, cam, gt, radiance_cache=rc, lambda_radiance=lam)
+    fs.calibrate()
+    for i in (1, 3):
+        cam.block.copy_(cams[i].block)
+        loss_f = fs.enqueue()
+        torch.cuda.synchronize()
+        assert not fs.read_count()[1]
+        loss_e, _ = pipeline.training_step(cams[i], pc_e, env_e, bg, gts[0])
+        lr = rc.loss(cams[i].camera_center, (env_e, 0), pc_e.xyz, gn, pc_e.shading_normal, pc_e.base_color, pc_e.roughness)
+        (lam * lr).backward()
+        assert abs(float(loss_f) - float(loss_e)) <= 2e-6 * abs(float(loss_e))
+        assert abs(float(fs.result["loss_radiance"]) - float(lr)) <= 1e-6 * abs(float(lr))
+        _check_grads(_grads(pc_f, env_f), _grads(pc_e, env_e))
+        # the term reaches surfels this view culls
+        culled = ~fs.result["visibility_filter"]
+        assert float(pc_f.base_color.grad[culled].abs().sum()) > 0.0
