@@ -857,6 +857,75 @@ def measure_visibility(args, ctx: Ctx, reps: int = 5) -> dict:
 _REF_CACHE = {}
 
 
+def measure_radiance(args, ctx: Ctx, steps: int = 10, warmup: int = 3) -> dict:
+    """the radiance cache (update_radiace: tree + 64 hit-to-hit rays per surfel) and the training step with
+    the radiance-consistency term in it (svgss.py:319-320, lambda_radiance = 0.05), on the headline scene."""
+    from svgir_b200 import _lib, pipeline, radiance
+    dev = ctx.dev
+    cloud, mats, cams, gts = build_host_workload()
+    pc = pipeline.model_from_scene(cloud, mats, dev)
+    env = torch.from_numpy(mats["env_param"]).to(dev).requires_grad_(True)
+    bg = torch.zeros(3, device=dev)
+    cam_dev = [pipeline.camera_from_scene(c, dev) for c in cams]
+    gt_dev = [torch.from_numpy(g).to(dev) for g in gts]
+    with torch.no_grad():
+        q = pc.rotation / pc.rotation.norm(dim=1, keepdim=True)
+        r, x, y, z = q.unbind(1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+        sc = pc.scaling.detach().clone()
+        sc[:, 2] = 1e-3     # the synthetic surfels are 1e-6 thin: Sigma^-1 = R diag(1/s^2) R^T would not survive fp32
+        Sinv = R @ torch.diag_embed(1.0 / sc ** 2) @ R.transpose(1, 2)
+        ci = torch.stack([Sinv[:, 0, 0], Sinv[:, 0, 1], Sinv[:, 0, 2], Sinv[:, 1, 1], Sinv[:, 1, 2], Sinv[:, 2, 2]], 1).contiguous()
+        gn = R[:, :, 2].contiguous()
+    rc = radiance.RadianceCache()
+    torch.manual_seed(11)
+    rc.update(pc.xyz, sc, pc.rotation, pc.opacity, gn, ci, pc.shs, sample_num=NS)   # warm-up (allocations)
+    torch.cuda.synchronize()
+    _lib.timing_collect(reset=True)
+    _lib.timing_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc.update(pc.xyz, sc, pc.rotation, pc.opacity, gn, ci, pc.shs, sample_num=NS)
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    trace_ms = _lib.timing_collect("radiance_cache")[0]
+    out = {"cache": {"update_ms": round(e0.elapsed_time(e1), 2), "trace_kernel_ms": round(trace_ms, 2),
+                     "rays": P_SURFELS * NS, "rays_per_s": round(P_SURFELS * NS / (trace_ms * 1e-3)) if trace_ms else None,
+                     "first_hit_fraction": round(float((rc.hemi_index_buffers >= 0).float().mean()), 4),
+                     "occluded_fraction": round(float((rc.visibility_tracing == 0).float().mean()), 4)}}
+    runner = pipeline.GraphedTrainingStep(pc, env, bg, cam_dev[0], gt_dev[0], radiance_cache=rc, lambda_radiance=0.05)
+    for i in range(warmup):
+        runner(cam_dev[i % N_VIEWS], gt_dev[i % len(gt_dev)])
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        runner(cam_dev[(warmup + i) % N_VIEWS], gt_dev[i % len(gt_dev)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    _lib.timing_collect(reset=True)
+    _lib.timing_enable(True)
+    for i in range(3):
+        runner.fs.enqueue()
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    k = {}
+    for name in ("radiance_loss_fused",):
+        t, n = _lib.timing_collect(name)
+        k[name] = round(t / n, 4) if n else None
+    out["step_with_term"] = {"value": round(1000.0 / ms, 2), "unit": "it/s", "ms_per_step": round(ms, 4), "steps": steps,
+                             "warmup": warmup, "lambda_radiance": 0.05, "kernels_ms": k,
+                             "loss_radiance": float(runner.fs.result["loss_radiance"]),
+                             "note": "the headline step plus get_radiance_loss; select+forward and backward kernels run on "
+                                     "the side stream under the rasteriser"}
+    out["config"] = {"workload": "C3-train + radiance term: 300k surfels x 64 samples, env 16x32", "parity": "unpinned (Slang "
+                     "kernels cannot run here; numpy restatement oracle/radiance_oracle.py)"}
+    return out
+
+
 def _ref_inputs():
     if "w" not in _REF_CACHE:
         _REF_CACHE["w"] = build_host_workload()
@@ -1045,6 +1114,7 @@ def run_ours(args):
                                       if k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "workload_stats", "e2e",
                                                "roofline", "kernels_ms", "launch_mode")})
             extra("visibility", lambda: measure_visibility(args, ctx))
+            extra("radiance", lambda: measure_radiance(args, ctx))
 
             def refcuda():
                 r = measure_reference_cuda(steps=5, warmup=2)
@@ -1072,6 +1142,9 @@ def run_workload(args):
         clocks.mark(True)
         out = measure_c4(args, ctx, args.steps, args.warmup)
         clocks.mark(False)
+    elif args.workload == "radiance":
+        out = {"metric": "radiance cache + training step with the radiance-consistency term", "n_gpus": 1,
+               "radiance": measure_radiance(args, ctx, args.steps, args.warmup)}
     else:
         out = {"metric": "visibility precompute (LBVH build + opacity trace)", "n_gpus": 1, "visibility": measure_visibility(args, ctx)}
     if ctx.rank == 0:
@@ -1101,7 +1174,7 @@ def main():
     ap.add_argument("--bg-ctas", type=int, default=4, help="--reduce overlap: CTA limit of the communicator that carries the "
                     "segment overlapped with the shading backward (0 = default communicator for both segments)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4", "visibility"],
+    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4", "visibility", "radiance"],
                     help="train = C3-train fwd+bwd it/s (headline, plus the extra keys); relight = C3-eval forward ms/frame (Ns=384, "
                          "S=7, VS=64); c4 = 1M surfels, 8 views per step sharded over the ranks (strong scaling); visibility = LBVH "
                          "build + opacity trace vs the reference kernels")

@@ -654,6 +654,14 @@ int svgir_radiance_loss_backward(const svgir_radiance_loss_cfg* cfg, const svgir
                                  const float* grad_loss, const float* irradiance, const float* saved,
                                  float* d_albedo, float* d_roughness, float* d_env, float* d_env_scratch, void* stream);
 
+/* Both in one pass, for a caller that knows the upstream gradient beforehand (the training step: grad_loss =
+ * lambda_radiance): the gradients of a surfel are accumulated right after its irradiance, while its rows are in cache.
+ * With in->skip_flag set (nonzero on the device) the loss is still evaluated and the gradients are left untouched. */
+int svgir_radiance_loss_forward_backward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in,
+                                         const float* grad_loss, float* loss, float* irradiance, int32_t* sample_index,
+                                         float* saved, float* scratch, float* d_albedo, float* d_roughness, float* d_env,
+                                         float* d_env_scratch, void* stream);
+
 /* ---- per-surfel gradient all-reduce over NVLink peer memory (view-sharded data parallelism) ------
  * New: the reference is single-process / single-GPU (train.py:108-143). Every rank keeps
  * its flat gradient buffer in a symmetric allocation that is peer-mapped into all ranks of the box; the

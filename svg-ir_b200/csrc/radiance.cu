@@ -358,10 +358,88 @@ __device__ __forceinline__ void make_secondary(const RLArgs& a, const SecRaw& r,
     q.E[0] = e[0] * q.escale; q.E[1] = e[1] * q.escale; q.E[2] = e[2] * q.escale;
 }
 
-__global__ void __launch_bounds__(RL_THREADS, 3) radiance_loss_fwd_kernel(const RLArgs a, const float4* __restrict__ saved,
-                                                                          float* __restrict__ irradiance,
-                                                                          float* __restrict__ partials) {
+// Gradient of one surfel's irradiance (G = d loss / d irradiance[n] / S) w.r.t. the hit surfel's albedo and roughness
+// and the env map: the secondary samples are evaluated again (their rows are in L1/L2 from the forward pass).
+__device__ __forceinline__ void radiance_surfel_grads(const RLArgs& a, int h, float Vx, float Vy, float Vz, const float (&G)[3],
+                                                      const HitSurfel& hs, int lane, float* __restrict__ d_albedo,
+                                                      float* __restrict__ d_roughness, float* __restrict__ env_copy) {
+    float acc[13];                                   // 12 albedo entries (4*c + v) + roughness
+#pragma unroll
+    for (int k = 0; k < 13; k++) acc[k] = 0.f;
+    // reference-grid mode: every one of the S backward threads differentiates secondary sample 0
+    const int s_end = a.ref_grid ? 1 : a.S;
+    const float rep = a.ref_grid ? (float)a.S : 1.f;
+#pragma unroll 2
+    for (int s2 = lane; s2 < s_end; s2 += 32) {
+        SecRaw raw;
+        load_secondary_raw(a, h, s2, raw);
+        if (raw.hit2 != -1) continue;
+        SecSample q;
+        make_secondary(a, raw, Vx, Vy, Vz, q);
+        float spec = 0.f, dspec = 0.f, mix[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            float ds;
+            const float sp = brdf_specular<true>(Vx, Vy, Vz, q.Lx, q.Ly, q.Lz, q.Hx, q.Hy, q.Hz, q.VoH, hs.nrm[v],
+                                                 hs.nrm[4 + v], hs.nrm[8 + v], hs.rough, ds);
+            spec += q.w[v] * sp;
+            dspec += q.w[v] * ds;
+#pragma unroll
+            for (int c = 0; c < 3; c++) mix[c] += q.w[v] * (hs.alb[4 * c + v] * (1.f / PI_F));
+        }
+        float ge[3], gsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float g = G[c] * rep;
+            const float gE = g * q.E[c];
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[4 * c + v] += gE * q.w[v] * (1.f / PI_F);
+            gsum += gE;
+            ge[c] = g * (spec + mix[c]) * q.escale;    // d loss / d (bilinear env value)
+        }
+        acc[12] += gsum * dspec;
+        if (env_copy) {
+            const float wx0 = 1.f - q.tap.wx1, wy0 = 1.f - q.tap.wy1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int x = q.tap.x0 + (k & 1), y = q.tap.y0 + (k >> 1);
+                if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
+                const float w = ((k & 1) ? q.tap.wx1 : wx0) * ((k >> 1) ? q.tap.wy1 : wy0);
+                red_add_v4(env_copy + ((size_t)y * a.We + x) * 4, ge[0] * w, ge[1] * w, ge[2] * w);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    float mine = 0.f;   // lane k adds entry k
+#pragma unroll
+    for (int k = 0; k < 13; k++) if (lane == k) mine = acc[k];
+    if (lane < 12) { if (d_albedo && mine != 0.f) atomicAdd(d_albedo + (size_t)h * 12 + lane, mine); }
+    else if (lane == 12) { if (d_roughness && mine != 0.f) atomicAdd(d_roughness + (size_t)h * a.rough_stride, mine); }
+}
+
+// sign(irradiance - target) * grad / numel, and the 1/S of :1299
+__device__ __forceinline__ bool radiance_upstream(const float (&irr)[3], const float4& B, float gscale, float inv_S, float (&G)[3]) {
+    const float d0 = irr[0] - B.x, d1 = irr[1] - B.y, d2 = irr[2] - B.z;
+    G[0] = (d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f)) * inv_S;
+    G[1] = (d1 > 0.f ? gscale : (d1 < 0.f ? -gscale : 0.f)) * inv_S;
+    G[2] = (d2 > 0.f ? gscale : (d2 < 0.f ? -gscale : 0.f)) * inv_S;
+    return G[0] != 0.f || G[1] != 0.f || G[2] != 0.f;
+}
+
+// WITH_GRAD: forward and backward in one pass (the step knows the upstream gradient beforehand: lambda_radiance).
+template <bool WITH_GRAD>
+__global__ void __launch_bounds__(RL_THREADS, WITH_GRAD ? 2 : 3) radiance_loss_fwd_kernel(
+    const RLArgs a, const float4* __restrict__ saved, float* __restrict__ irradiance, float* __restrict__ partials,
+    const float* __restrict__ grad_loss, float* __restrict__ d_albedo, float* __restrict__ d_roughness,
+    float* __restrict__ d_env_acc) {
     __shared__ float wsum[RL_WPC];
+    const bool want_grad = WITH_GRAD && !(a.skip_flag && __ldg(a.skip_flag) != 0);
+    const float gscale = WITH_GRAD ? (grad_loss ? __ldg(grad_loss) : 1.f) / (3.f * (float)a.P) : 0.f;
+    float* env_copy = (WITH_GRAD && d_env_acc) ? d_env_acc + (size_t)(blockIdx.x % ENV_COPIES) * a.He * a.We * 4 : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_S = 1.f / (float)a.S;
     const int stride = gridDim.x * RL_WPC;
@@ -402,6 +480,11 @@ __global__ void __launch_bounds__(RL_THREADS, 3) radiance_loss_fwd_kernel(const 
             for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) irr[c] += __shfl_xor_sync(0xffffffffu, irr[c], o);
+            }
+            if (WITH_GRAD) {
+                float G[3];
+                if (radiance_upstream(irr, B, gscale, inv_S, G) && want_grad)
+                    radiance_surfel_grads(a, h, Vx, Vy, Vz, G, hs, lane, d_albedo, d_roughness, env_copy);
             }
         }
         if (lane == 0) {
@@ -448,10 +531,10 @@ __global__ void __launch_bounds__(RL_THREADS, 2) radiance_loss_bwd_kernel(const 
     float* env_copy = d_env_acc ? d_env_acc + (size_t)(blockIdx.x % ENV_COPIES) * a.He * a.We * 4 : nullptr;
     int n = blockIdx.x * RL_WPC + warp;
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-    float I0 = 0.f, I1 = 0.f, I2 = 0.f;
+    float I[3] = {0.f, 0.f, 0.f};
     if (n < a.P) {
         A = __ldg(saved + 2 * (size_t)n); B = __ldg(saved + 2 * (size_t)n + 1);
-        I0 = __ldg(irradiance + 3 * (size_t)n); I1 = __ldg(irradiance + 3 * (size_t)n + 1); I2 = __ldg(irradiance + 3 * (size_t)n + 2);
+        I[0] = __ldg(irradiance + 3 * (size_t)n); I[1] = __ldg(irradiance + 3 * (size_t)n + 1); I[2] = __ldg(irradiance + 3 * (size_t)n + 2);
     }
     while (n < a.P) {
         const int n_next = n + stride;
@@ -464,74 +547,12 @@ __global__ void __launch_bounds__(RL_THREADS, 2) radiance_loss_bwd_kernel(const 
         }
         const int h = __float_as_int(A.w);
         float G[3];
-        {   // sign(x - y) / numel, and the 1/S of :1299
-            const float d0 = I0 - B.x, d1 = I1 - B.y, d2 = I2 - B.z;
-            G[0] = (d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f)) * inv_S;
-            G[1] = (d1 > 0.f ? gscale : (d1 < 0.f ? -gscale : 0.f)) * inv_S;
-            G[2] = (d2 > 0.f ? gscale : (d2 < 0.f ? -gscale : 0.f)) * inv_S;
-        }
-        if (h != -1 && (G[0] != 0.f || G[1] != 0.f || G[2] != 0.f)) {
-            const float Vx = A.x, Vy = A.y, Vz = A.z;
+        if (radiance_upstream(I, B, gscale, inv_S, G) && h != -1) {
             HitSurfel hs;
             load_hit_surfel(a, h, hs);
-            float acc[13];                                   // 12 albedo entries (4*c + v) + roughness
-#pragma unroll
-            for (int k = 0; k < 13; k++) acc[k] = 0.f;
-            // reference-grid mode: every one of the S backward threads differentiates secondary sample 0
-            const int s_end = a.ref_grid ? 1 : a.S;
-            const float rep = a.ref_grid ? (float)a.S : 1.f;
-#pragma unroll 2
-            for (int s2 = lane; s2 < s_end; s2 += 32) {
-                SecRaw raw;
-                load_secondary_raw(a, h, s2, raw);
-                if (raw.hit2 != -1) continue;
-                SecSample q;
-                make_secondary(a, raw, Vx, Vy, Vz, q);
-                float spec = 0.f, dspec = 0.f, mix[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    float ds;
-                    const float sp = brdf_specular<true>(Vx, Vy, Vz, q.Lx, q.Ly, q.Lz, q.Hx, q.Hy, q.Hz, q.VoH, hs.nrm[v],
-                                                         hs.nrm[4 + v], hs.nrm[8 + v], hs.rough, ds);
-                    spec += q.w[v] * sp;
-                    dspec += q.w[v] * ds;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) mix[c] += q.w[v] * (hs.alb[4 * c + v] * (1.f / PI_F));
-                }
-                float ge[3], gsum = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float g = G[c] * rep;
-                    const float gE = g * q.E[c];
-#pragma unroll
-                    for (int v = 0; v < 4; v++) acc[4 * c + v] += gE * q.w[v] * (1.f / PI_F);
-                    gsum += gE;
-                    ge[c] = g * (spec + mix[c]) * q.escale;    // d loss / d (bilinear env value)
-                }
-                acc[12] += gsum * dspec;
-                if (d_env_acc) {
-                    const float wx0 = 1.f - q.tap.wx1, wy0 = 1.f - q.tap.wy1;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int x = q.tap.x0 + (k & 1), y = q.tap.y0 + (k >> 1);
-                        if (x < 0 || x > a.We - 1 || y < 0 || y > a.He - 1) continue;
-                        const float w = ((k & 1) ? q.tap.wx1 : wx0) * ((k >> 1) ? q.tap.wy1 : wy0);
-                        red_add_v4(env_copy + ((size_t)y * a.We + x) * 4, ge[0] * w, ge[1] * w, ge[2] * w);
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int k = 0; k < 13; k++) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-            }
-            float mine = 0.f;   // lane k adds entry k
-#pragma unroll
-            for (int k = 0; k < 13; k++) if (lane == k) mine = acc[k];
-            if (lane < 12) { if (d_albedo && mine != 0.f) atomicAdd(d_albedo + (size_t)h * 12 + lane, mine); }
-            else if (lane == 12) { if (d_roughness && mine != 0.f) atomicAdd(d_roughness + (size_t)h * a.rough_stride, mine); }
+            radiance_surfel_grads(a, h, A.x, A.y, A.z, G, hs, lane, d_albedo, d_roughness, env_copy);
         }
-        n = n_next; A = An; B = Bn; I0 = J0; I1 = J1; I2 = J2;
+        n = n_next; A = An; B = Bn; I[0] = J0; I[1] = J1; I[2] = J2;
     }
 }
 
@@ -611,7 +632,8 @@ int svgir_radiance_loss_forward(const svgir_radiance_loss_cfg* c, const svgir_ra
     static_assert(148 * 8 <= SVGIR_RADIANCE_SCRATCH_FLOATS, "scratch");
     { TimedScope t_("radiance_loss_fwd", s);
       radiance_select_kernel<<<(c->P + RL_WPC - 1) / RL_WPC, RL_THREADS, 0, s>>>(a, sample_index, (float4*)saved);
-      radiance_loss_fwd_kernel<<<grid, RL_THREADS, 0, s>>>(a, (const float4*)saved, irradiance, scratch);
+      radiance_loss_fwd_kernel<false><<<grid, RL_THREADS, 0, s>>>(a, (const float4*)saved, irradiance, scratch, nullptr, nullptr,
+                                                                  nullptr, nullptr);
       radiance_loss_reduce_kernel<<<1, 256, 0, s>>>(grid, 1.f / (3.f * (float)c->P), scratch, loss); }
     return check_launch("radiance_loss_forward", false, s);
 }
@@ -633,6 +655,30 @@ int svgir_radiance_loss_backward(const svgir_radiance_loss_cfg* c, const svgir_r
                                                                    d_env ? d_env_scratch : nullptr); }
     if (d_env) launch_env_grad_finalize(ntex, ENV_COPIES, c->env_mode, d_env_scratch, in->env, d_env, s);
     return check_launch("radiance_loss_backward", false, s);
+}
+
+int svgir_radiance_loss_forward_backward(const svgir_radiance_loss_cfg* c, const svgir_radiance_loss_in* in,
+                                         const float* grad_loss, float* loss, float* irradiance, int32_t* sample_index,
+                                         float* saved, float* scratch, float* d_albedo, float* d_roughness, float* d_env,
+                                         float* d_env_scratch, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RLArgs a;
+    int rc = rl_prepare(c, in, a, s);
+    if (rc) return rc;
+    if (!loss || !irradiance || !saved || !scratch) { set_error("radiance_loss_forward_backward: missing output"); return SVGIR_ERR_INVALID; }
+    if ((uintptr_t)saved & 15) { set_error("radiance_loss_forward_backward: saved must be 16-byte aligned"); return SVGIR_ERR_INVALID; }
+    if (d_env && !d_env_scratch) { set_error("radiance_loss_forward_backward: d_env needs d_env_scratch [SVGIR_RADIANCE_ENV_COPIES*env_h*env_w*4]"); return SVGIR_ERR_INVALID; }
+    if (c->P == 0) { cudaMemsetAsync(loss, 0, sizeof(float), s); return SVGIR_OK; }
+    const int ntex = a.He * a.We;
+    if (d_env && cudaMemsetAsync(d_env_scratch, 0, (size_t)ENV_COPIES * ntex * 4 * sizeof(float), s) != cudaSuccess) { set_error("memset failed"); return SVGIR_ERR_CUDA; }
+    const int grid = rl_grid(c->P);
+    { TimedScope t_("radiance_loss_fused", s);
+      radiance_select_kernel<<<(c->P + RL_WPC - 1) / RL_WPC, RL_THREADS, 0, s>>>(a, sample_index, (float4*)saved);
+      radiance_loss_fwd_kernel<true><<<grid, RL_THREADS, 0, s>>>(a, (const float4*)saved, irradiance, scratch, grad_loss, d_albedo,
+                                                                 d_roughness, d_env ? d_env_scratch : nullptr);
+      radiance_loss_reduce_kernel<<<1, 256, 0, s>>>(grid, 1.f / (3.f * (float)c->P), scratch, loss); }
+    if (d_env) launch_env_grad_finalize(ntex, ENV_COPIES, c->env_mode, d_env_scratch, in->env, d_env, s);
+    return check_launch("radiance_loss_forward_backward", false, s);
 }
 
 }  // extern "C"

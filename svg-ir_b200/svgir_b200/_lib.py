@@ -171,4 +171,5 @@ EXPORTED_SYMBOLS = [
     "svgir_adam_step", "svgir_densify_stats", "svgir_densify_decide", "svgir_densify_index", "svgir_gather_rows",
     "svgir_densify_split",
     "svgir_radiance_pack_surfels", "svgir_radiance_cache_build", "svgir_radiance_loss_forward", "svgir_radiance_loss_backward",
+    "svgir_radiance_loss_forward_backward",
 ]

@@ -343,11 +343,10 @@ class FusedTrainStep:
                 # the overflow flag it tests is final once binning is (same stream).
                 r = self.rad
                 gv = self.gviews
-                chk(L.svgir_radiance_loss_forward(C.byref(self.rcfg), C.byref(self.rin), r["loss"].data_ptr(), r["irr"].data_ptr(),
-                                                  None, r["saved"].data_ptr(), r["scratch"].data_ptr(), ss), "radiance_loss_forward")
-                chk(L.svgir_radiance_loss_backward(C.byref(self.rcfg), C.byref(self.rin), r["grad"].data_ptr(), r["irr"].data_ptr(),
-                                                   r["saved"].data_ptr(), gv[5].data_ptr(), gv[6].data_ptr(), gv[8].data_ptr(),
-                                                   r["env_scratch"].data_ptr(), ss), "radiance_loss_backward")
+                chk(L.svgir_radiance_loss_forward_backward(
+                    C.byref(self.rcfg), C.byref(self.rin), r["grad"].data_ptr(), r["loss"].data_ptr(), r["irr"].data_ptr(), None,
+                    r["saved"].data_ptr(), r["scratch"].data_ptr(), gv[5].data_ptr(), gv[6].data_ptr(), gv[8].data_ptr(),
+                    r["env_scratch"].data_ptr(), ss), "radiance_loss_forward_backward")
                 rad_done = torch.cuda.Event()
                 rad_done.record(side)
             chk(L.svgir_shade_forward(C.byref(self.scfg_f), C.byref(self.sin), C.byref(self.sout), cs), "shade_forward")

@@ -59,6 +59,8 @@ def _L():
         L.svgir_radiance_loss_backward.argtypes = [C.POINTER(RadianceLossCfg), C.POINTER(RadianceLossIn), vp, vp, vp, vp, vp,
                                                    vp, vp, vp]
         L.svgir_radiance_loss_backward.restype = C.c_int
+        L.svgir_radiance_loss_forward_backward.argtypes = [C.POINTER(RadianceLossCfg), C.POINTER(RadianceLossIn)] + [vp] * 11
+        L.svgir_radiance_loss_forward_backward.restype = C.c_int
         _BOUND = True
     return L
 

@@ -77,6 +77,10 @@ def main():
 
     ms_fb, _ = timed(fb, 10)
     res["loss_forward_backward_ms"] = ms_fb
+    env.requires_grad_(False)
+    ms_fb2, _ = timed(fb, 10)
+    res["loss_forward_backward_no_env_grad_ms"] = ms_fb2
+    env.requires_grad_(True)
     res["loss"] = float(loss)
     res["selected_hit_fraction"] = float((hit[torch.arange(P, device=dev), sel.long(), 0] >= 0).float().mean())
     # algorithmic bytes of the loss forward: per surfel dirs+vis of its own row (S*16 B) and, when the selected sample hit,
