@@ -572,23 +572,44 @@ def measure_c4(args, ctx: Ctx, steps: int, warmup: int) -> dict:
     params = pc.trainable() + [env]
     mine = svdist.views_for_rank(V, rank, world)
 
+    # Exchange (N > 1). p2p-overlap (default): the LAST local view's graph carries the all-reduce -- the rasteriser-side
+    # gradient segment on a side stream under that view's shading backward, the shading-side segment after it (the same
+    # in-step exchange as the headline); the views before it replay an accumulate-only graph. p2p: one peer-memory
+    # kernel after the local views; post: one NCCL all-reduce after them.
     peer, bucket, note = None, None, None
+    in_step = world > 1 and args.reduce == "p2p-overlap" and len(mine) > 0
     if world > 1 and args.reduce != "post":
-        peer, bucket, note = make_peer_bucket(
-            ctx, lambda pr: svdist.FlatGradBucket(params, alloc=pr.allocate, reducer=pr.all_reduce))
+        if in_step:
+            mk = lambda pr: svdist.FlatGradBucket(params, segments=pipeline.reduce_segments(pc), extra_floats=1,
+                                                  alloc=pr.allocate, segment_peer=pr)
+        else:
+            mk = lambda pr: svdist.FlatGradBucket(params, alloc=pr.allocate, reducer=pr.all_reduce)
+        peer, bucket, note = make_peer_bucket(ctx, mk)
+    in_step = in_step and peer is not None
     if bucket is None:
         bucket = svdist.FlatGradBucket(params)
     runner = pipeline.GraphedTrainingStep(pc, env, bg, cams[0], gts[0], bucket=bucket, zero_in_graph=False)
+    runner_last = pipeline.GraphedTrainingStep(pc, env, bg, cams[0], gts[0], bucket=bucket, zero_in_graph=False,
+                                               reduce_in_graph=True, on_overflow="raise") if in_step else None
+    redone = [0]
 
     def step(i):
-        bucket.zero()
-        R = 0
-        loss = None
-        for v in mine:
-            loss, res = runner(cams[v], gts[(i + v) % 2])
-            R += int(res["num_rendered"])
-        bucket.all_reduce()   # one exchange per step (no-op at N=1)
-        return loss, R
+        for _ in range(4):
+            bucket.zero()
+            R = 0
+            loss = None
+            try:
+                for k, v in enumerate(mine):
+                    r = runner_last if (in_step and k == len(mine) - 1) else runner
+                    loss, res = r(cams[v], gts[(i + v) % 2])
+                    R += int(res["num_rendered"])
+            except pipeline.BinOverflow:   # raised on every rank together (the flag travels with the gradients)
+                redone[0] += 1
+                continue
+            if not in_step:
+                bucket.all_reduce()   # one exchange per step (no-op at N=1)
+            return loss, R
+        raise RuntimeError("C4: binning capacity did not converge")
 
     for i in range(warmup):
         loss, R = step(i)
@@ -632,12 +653,17 @@ def measure_c4(args, ctx: Ctx, steps: int, warmup: int) -> dict:
                    "views_per_step": V, "views_per_rank": len(mine), "parallelism": f"view-dp{world}",
                    "l2": "working set > L2 (per-sample light buffers 2 GB/view)"},
         "R_last_step_local": R,
-        "gpu_launches": int(runner.launches_per_step * len(mine) * steps + (steps if peer is not None else 0)),
+        "gpu_launches": int((runner.launches_per_step * (len(mine) - 1) + runner_last.launches_per_step) * steps) if in_step
+        else int(runner.launches_per_step * len(mine) * steps + (steps if peer is not None else 0)),
+        "steps_redone_after_overflow": redone[0],
         "grad_allreduce": None if world == 1 else {"bytes": bucket.nbytes, "ms": None if ar_ms is None else round(ar_ms, 4),
-                                                   "mode": "svgir_peer_allreduce after the local views"
-                                                   if peer is not None else "one NCCL all-reduce after the local views", "note": note},
+                                                   "mode": ("svgir_peer_allreduce inside the last local view's graph: rasteriser-side "
+                                                            "segment under its shading backward, shading-side segment after it"
+                                                            if in_step else "svgir_peer_allreduce after the local views")
+                                                   if peer is not None else "one NCCL all-reduce after the local views", "note": note,
+                                                   "ms_note": "ms = the whole bucket exchanged alone, all ranks entering together"},
         "kernels_ms": kt}
-    runner = None
+    runner = runner_last = None
     del pc, env, params, bucket, peer, mats
     gc.collect()
     torch.cuda.empty_cache()

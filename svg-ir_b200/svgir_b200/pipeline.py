@@ -324,6 +324,11 @@ def reduce_segments(pc: SurfelModel) -> list:
 FUSED_STEP = True
 
 
+class BinOverflow(RuntimeError):
+    """Raised by GraphedTrainingStep(on_overflow="raise") after a replay whose binning buffers were too small on some
+    rank: the buffers have been grown and the graph re-captured; the caller re-runs its whole step."""
+
+
 class GraphedTrainingStep:
     """One training iteration captured ONCE into a CUDA graph and replayed: one cudaGraphLaunch per iteration
     instead of ~150 host-side launches and tensor allocations, and no mid-step device->host read
@@ -345,7 +350,7 @@ class GraphedTrainingStep:
     def __init__(self, pc: SurfelModel, env_param: torch.Tensor, bg: torch.Tensor, cam: ViewCamera,
                  gt_image: torch.Tensor, bucket=None, warmup: int = 2, reduce_in_graph: bool = False,
                  zero_in_graph: bool = True, fused: Optional[bool] = None, radiance_cache=None,
-                 lambda_radiance: float = 0.05):
+                 lambda_radiance: float = 0.05, on_overflow: str = "rerun"):
         self.pc, self.env, self.bg, self.bucket = pc, env_param, bg, bucket
         # radiance_cache (fused path only): the step also carries lambda_radiance * get_radiance_loss (svgss.py:319-320)
         self.radiance_cache, self.lambda_radiance = radiance_cache, lambda_radiance
@@ -354,9 +359,17 @@ class GraphedTrainingStep:
         # the caller zeroes the bucket at the start of the step. A (re-)capture leaves the bucket's content untouched,
         # and a replay whose binning overflowed adds exactly zero (every backward kernel returns at once when the
         # overflow flag is set), so re-running the step after the re-capture gives the complete sum.
+        # on_overflow="raise": after an overflowed replay the step is NOT re-run here; BinOverflow is raised (on every rank
+        # when the reduction is in the graph: the flag is summed with the gradients) once the bins are grown and the graph
+        # re-captured. That is what makes accumulate + reduce_in_graph usable: the LAST local view of a multi-view step
+        # carries the exchange under its shading backward; after the in-place all-reduce the bucket holds all ranks' sums,
+        # so a re-run of that one view would count them twice -- the caller zeroes the bucket and redoes the step instead.
         self.zero_in_graph = bool(zero_in_graph)
-        if not self.zero_in_graph and (bucket is None or reduce_in_graph):
-            raise ValueError("zero_in_graph=False needs a bucket and a reduction outside the graph")
+        if on_overflow not in ("rerun", "raise"):
+            raise ValueError("on_overflow: 'rerun' or 'raise'")
+        self.on_overflow = on_overflow
+        if not self.zero_in_graph and (bucket is None or (reduce_in_graph and on_overflow != "raise")):
+            raise ValueError("zero_in_graph=False needs a bucket and a reduction outside the graph (or on_overflow='raise')")
         # reduce_in_graph: the segment-wise all-reduce of `bucket` is captured INSIDE the graph, overlapped
         # with the shading backward; the caller must not all-reduce again.
         self.reduce_in_graph = bool(reduce_in_graph and bucket is not None)
@@ -438,6 +451,8 @@ class GraphedTrainingStep:
                 fs.grow(R)
             self.graph = None
             self._capture_fused()
+            if self.on_overflow == "raise":
+                raise BinOverflow("binning buffers overflowed; re-captured with larger ones -- redo the step")
             self.graph.replay()
         raise RuntimeError("GraphedTrainingStep: binning capacity did not converge")
 

@@ -231,6 +231,58 @@ def _peer_worker(rank, world, port, q):
             pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v], zero_grad=False)
         for a, b in zip(params_s, pc_e.trainable() + [env_e]):
             step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+        # several views per rank (C4): the views before the last replay an accumulate-only graph, the LAST one carries the
+        # exchange in its graph (on_overflow="raise": after the in-place all-reduce a re-run of one view would count the
+        # other ranks' sums twice, so the step is redone). Rank 1 captures with no slack, then the surfels grow: its last
+        # view overflows, BOTH ranks raise BinOverflow and redo the step.
+        pc_m, env_m = model()
+        with torch.no_grad():
+            pc_m.scaling.mul_(1.2)
+        params_m = pc_m.trainable() + [env_m]
+        peer_m = D.PeerAllReduce(dev)
+        bucket_m = D.FlatGradBucket(params_m, segments=pipeline.reduce_segments(pc_m), extra_floats=1,
+                                    alloc=peer_m.allocate, segment_peer=peer_m)
+        run_acc = pipeline.GraphedTrainingStep(pc_m, env_m, bg, cams[0], gts[0], bucket=bucket_m, zero_in_graph=False)
+        if rank == 1:
+            raster._CAP_HINT.clear()
+            raster.ASYNC_SLACK, raster.ASYNC_MARGIN = 1.0, 16
+        run_last = pipeline.GraphedTrainingStep(pc_m, env_m, bg, cams[0], gts[0], bucket=bucket_m, zero_in_graph=False,
+                                                reduce_in_graph=True, on_overflow="raise")
+        mine = [rank, rank + 2]
+        redone = 0
+
+        def multi_step():
+            nonlocal redone
+            for _ in range(4):
+                bucket_m.zero()
+                try:
+                    run_acc(cams[mine[0]], gts[mine[0] % 2])
+                    run_last(cams[mine[1]], gts[mine[1] % 2])
+                    return
+                except pipeline.BinOverflow:
+                    redone += 1
+            raise RuntimeError("did not converge")
+
+        def check_multi():
+            nonlocal step_worst
+            torch.cuda.synchronize()
+            for t in pc_e.trainable() + [env_e]:
+                t.grad = None
+            for v in range(4):
+                pipeline.training_step(cams[v], pc_e, env_e, bg, gts[v % 2], zero_grad=False)
+            for a, b in zip(params_m, pc_e.trainable() + [env_e]):
+                step_worst = max(step_worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20)))
+
+        multi_step()
+        raster.ASYNC_SLACK, raster.ASYNC_MARGIN = old
+        check_multi()
+        assert redone == 0, redone
+        with torch.no_grad():
+            pc_m.scaling.mul_(1.15)
+            pc_e.scaling.mul_(1.15)
+        multi_step()
+        check_multi()
+        assert redone == 1, (rank, redone)   # rank 1's bins overflowed; rank 0 saw the summed flag
         q.put((rank, out, step_worst, None))
         torch.cuda.synchronize()
         dist.barrier()
