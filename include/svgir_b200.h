@@ -599,7 +599,7 @@ int svgir_radiance_pack_surfels(int P, const float* means3D, const float* scales
  * Which surfel a ray ignores:
  *   self_mod == 0  the ray ignores its own surfel, index first_index + n (what the kernel means to do);
  *   self_mod  > 0  the reference's behaviour when update_radiace feeds it chunks of self_mod surfels: the kernel
- *                  compares the hit with the CHUNK-LOCAL index (intersect_test.slang:1931), i.e. ignores surfel
+ *                  compares the hit with the CHUNK-LOCAL index (intersect_test.slang:1932), i.e. ignores surfel
  *                  (first_index + n) % self_mod. */
 int svgir_radiance_cache_build(const svgir_bvh* bvh, int N, int S, int first_index, int self_mod, const float* origins,
                                const float* dirs, const float* records, const float* shs, float* radiance,
@@ -608,14 +608,14 @@ int svgir_radiance_cache_build(const svgir_bvh* bvh, int N, int S, int first_ind
 #define SVGIR_RADIANCE_ENV_READY 1      /* env_act_scratch already holds the activated env map */
 #define SVGIR_RADIANCE_BWD_REFERENCE_GRID 2 /* backward: only secondary sample 0 carries gradient, S times over -- what
                                                the reference's backward launch computes (grid (N/256,1,S) with the
-                                               sample index read from y, pbgi/renderer.py:224) */
+                                               sample index read from y, pbgi/renderer.py:223) */
 #define SVGIR_RADIANCE_NORMALS_VERTEX_MAJOR 4 /* normals is [P,4,3] (get_shading_normal as it is, element 3*v + c) instead of
                                                 the transposed [P,12] the reference hands to its kernel (:551) */
 typedef struct svgir_radiance_loss_cfg {
     int32_t P, S, env_h, env_w;
     int32_t env_mode;       /* as svgir_shade_cfg: 0 = learnable map (softplus, x2), 1 = fixed map */
     int32_t flags;
-    int32_t rough_stride;   /* floats per row of roughness / d_roughness (column 0 is used, intersect_test.slang:1281) */
+    int32_t rough_stride;   /* floats per row of roughness / d_roughness (column 0 is used, intersect_test.slang:1277) */
     int32_t reserved_;
 } svgir_radiance_loss_cfg;
 
@@ -643,7 +643,7 @@ typedef struct svgir_radiance_loss_in {
  * sample_index [P] (= max_idx, gaussian_model.py:565; may be NULL); saved [P,8] (16-B aligned: per surfel the view
  * vector of the selected sample, the surfel it hit, the target colour -- what the backward needs). scratch
  * [SVGIR_RADIANCE_SCRATCH_FLOATS]. The sum over secondary samples is complete and fixed in order (the reference adds
- * with a non-atomic read-modify-write from S threads, intersect_test.slang:1371-1373). */
+ * with a non-atomic read-modify-write from S threads, intersect_test.slang:1354-1356). */
 int svgir_radiance_loss_forward(const svgir_radiance_loss_cfg* cfg, const svgir_radiance_loss_in* in, float* loss,
                                 float* irradiance, int32_t* sample_index, float* saved, float* scratch, void* stream);
 

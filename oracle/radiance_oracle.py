@@ -17,15 +17,15 @@ PARITY UNPINNED: the reference runs these kernels through slangtorch (a third-pa
 not be checked against the reference's own output. Where the reference's kernels are racy or depend on the LBVH
 traversal order, the INTENDED value is restated (same choices as the CUDA path):
   R1 the alpha a query returns is that of the closest hit (the reference returns the alpha of the last leaf visited
-     whose test passed, :409-415);
+     whose test passed, :409-422);
   R2 a surfel whose plane hit lies beyond the current closest distance is not a hit (the reference reports "hit" on
-     surfel 0 at t_max when only such surfels exist, :404-413);
+     surfel 0 at t_max when only such surfels exist, :409-429);
   R3 irradiance is the complete sum over the secondary samples (the reference adds with a non-atomic
-     read-modify-write from S threads, :1371-1373) and is 0 when the primary sample hit nothing (the reference
-     writes through a 3-index view of a [N,3] tensor there, :1203-1206);
+     read-modify-write from S threads, :1354-1356) and is 0 when the primary sample hit nothing (the reference
+     writes through a 3-index view of a [N,3] tensor there, :1208-1210);
   R4 the gradient is that of the complete sum (the reference's backward grid differentiates sample 0 S times,
-     pbgi/renderer.py:224); `reference_grid=True` restates that instead;
-  R5 self_mod restates the chunk-local self test (:1931 with update_radiace's chunking, gaussian_model.py:491-503).
+     pbgi/renderer.py:223); `reference_grid=True` restates that instead;
+  R5 self_mod restates the chunk-local self test (:1932 with update_radiace's chunking, gaussian_model.py:487-497).
 Only tests/ may import this module."""
 import numpy as np
 

@@ -77,8 +77,8 @@ __device__ __forceinline__ float slab_entry(float lx, float ly, float lz, float 
     return t_min;
 }
 
-// The leaf test of gs_bvh_hit (intersect_test.slang:303-413) = ellipse_hit (:94-149) followed by the power, alpha and
-// facing rejections, in the reference's order. A hit replaces the current one only when it is strictly closer (:404).
+// The leaf test of gs_bvh_hit (intersect_test.slang:307-424) = ellipse_hit (:94-149) followed by the power, alpha and
+// facing rejections, in the reference's order. A hit replaces the current one only when it is strictly closer (:409).
 __device__ __forceinline__ void surfel_test(const float4* __restrict__ rec, int obj, float ox, float oy, float oz, float dx,
                                             float dy, float dz, float t_min, Hit& h) {
     const float4* r = rec + (size_t)obj * 8;
@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(RC_THREADS) radiance_cache_kernel(
         }
         // an internal node popped later is re-tested against the current closest hit by the slab test of its
         // children only; that is conservative (never drops a closer hit)
-        if (h.index < 0 || h.index == self) break;          // :1931, :1970-1973
-        if (first_hit == -1) { first_hit = h.index; fu = h.u; fv = h.v; t_min = 0.01f; }   // :1942-1947
+        if (h.index < 0 || h.index == self) break;          // :1932, :1970-1973
+        if (first_hit == -1) { first_hit = h.index; fu = h.u; fv = h.v; t_min = 0.01f; }   // :1944-1949
         const float4 hc = __ldg(rec + (size_t)h.index * 8);
         float col[3];
         eval_sh3(shs + (size_t)h.index * 48, hc.x - ox, hc.y - oy, hc.z - oz, col);
         ox += dx * h.t; oy += dy * h.t; oz += dz * h.t;
-        const float w = h.alpha * T;                        // (1 - debug_res.x) * test_T, :1957
+        const float w = h.alpha * T;                        // (1 - debug_res.x) * test_T, :1961
         sr += col[0] * w; sg += col[1] * w; sb += col[2] * w;
         T *= 1.f - h.alpha;
         if (T < 0.2f) visible = false;
@@ -328,7 +328,7 @@ __device__ __forceinline__ void load_hit_surfel(const RLArgs& a, int h, HitSurfe
     }
 }
 
-// Raw inputs of one secondary sample of render_irradiance_sample (:1210-1311): loaded unconditionally so that all the
+// Raw inputs of one secondary sample of render_irradiance_sample (:1212-1303): loaded unconditionally so that all the
 // gathers of a surfel are in flight together.
 struct SecRaw { int hit2; float rx, ry, rz, u, v, area; };
 __device__ __forceinline__ void load_secondary_raw(const RLArgs& a, int h, int s2, SecRaw& r) {
@@ -421,7 +421,7 @@ __device__ __forceinline__ void radiance_surfel_grads(const RLArgs& a, int h, fl
     else if (lane == 12) { if (d_roughness && mine != 0.f) atomicAdd(d_roughness + (size_t)h * a.rough_stride, mine); }
 }
 
-// sign(irradiance - target) * grad / numel, and the 1/S of :1299
+// sign(irradiance - target) * grad / numel, and the 1/S of :1301
 __device__ __forceinline__ bool radiance_upstream(const float (&irr)[3], const float4& B, float gscale, float inv_S, float (&G)[3]) {
     const float d0 = irr[0] - B.x, d1 = irr[1] - B.y, d2 = irr[2] - B.z;
     G[0] = (d0 > 0.f ? gscale : (d0 < 0.f ? -gscale : 0.f)) * inv_S;

@@ -224,7 +224,7 @@ class RadianceCache:
                reference_chunking: bool = True):
         """update_radiace: rebuild the tree, draw sample_num fibonacci directions per surfel with a random azimuth offset,
         trace. reference_chunking=True draws the offsets chunk by chunk as the reference does (chunk =
-        P // ((sample_num-1)//24+1), :491; same torch.rand calls, so a seeded run draws the same numbers) and reproduces
+        P // ((sample_num-1)//24+1), :487; same torch.rand calls, so a seeded run draws the same numbers) and reproduces
         its chunk-local self test; everything still runs as one launch."""
         P = xyz.shape[0]
         dev = xyz.device

@@ -193,4 +193,4 @@ def test_loss_and_gradients(ref_grid):
         scale = float(want.abs().max())
         assert scale > 0, name
         assert err < 2e-4 * scale, (name, err, scale)
-    assert not bool(rough.grad[:, 1:].any())                              # only column 0 is read (:1281)
+    assert not bool(rough.grad[:, 1:].any())                              # only column 0 is read (:1277)

@@ -27,5 +27,9 @@ if [ "$3" != "skip-ncu" ]; then
       --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $out/ncu_launch.log 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'composite|shade_' -c 8 \
       -o $out/step_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $out/ncu_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'bvh_trace_opacity' -c 1 \
+      -o $out/bvh_trace_full -f python bench.py --workload visibility > $out/ncu_bvh.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'radiance_(cache|select|loss_fwd)' -c 4 \
+      -o $out/radiance_full -f python bench.py --workload radiance --steps 1 --warmup 1 > $out/ncu_radiance.log 2>&1
   ls -la $out
 fi
