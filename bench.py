@@ -48,6 +48,7 @@ import numpy as np
 import torch
 
 P_SURFELS, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT, N_VIEWS = 300_000, 800, 800, 64, 4, 52, 8
+C5_SHAPE = ("C5", 2_000_000, 1920, 1080, 200)   # BASELINE.json configs[4]
 WORKLOAD = ("C3-train: stage-2 svgss+render_equation fwd+bwd, %dk SV surfels, one %dx%d view/iter, Ns=%d, S=%d, VS=%d"
             % (P_SURFELS // 1000, WIDTH, HEIGHT, NS, S_FEAT, VS_FEAT))
 METRIC, UNIT = "fwd+bwd iters/sec at 800x800", "it/s"
@@ -671,11 +672,14 @@ def measure_c4(args, ctx: Ctx, steps: int, warmup: int) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------
-def measure_relight(args, ctx: Ctx, steps: int, warmup: int, clocks: ClockSampler = None) -> dict:
+def measure_relight(args, ctx: Ctx, steps: int, warmup: int, clocks: ClockSampler = None, shape=None) -> dict:
     """C3-eval (BASELINE.json configs[2]): relighting frame = render_equation over all 300k surfels with
     Ns=384 samples under a fixed HDR env map (EnvLight semantics, scene/envmap.py:54-72) + svgss forward
     with the eval G-buffer (S=7, VS=64) at 800x800. Forward only; reports ms/frame. Under torchrun the
-    view x envmap grid is sharded round-robin with no collective."""
+    view x envmap grid is sharded round-robin with no collective.
+    shape = (label, P, W, H, n_views): C5 (BASELINE.json configs[4]) is the same frame at 2 M surfels, 1920x1080, with a
+    200-view x 5-env-map sweep; a bounded number of its frames is timed and the sweep time follows from ms/frame."""
+    label, P_SURFELS, WIDTH, HEIGHT, N_VIEWS = shape if shape is not None else ("C3-eval", 300_000, 800, 800, 8)
     from svgir_b200 import _lib, pipeline, scene, shading
     from svgir_b200 import dist as svdist
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
@@ -783,10 +787,12 @@ def measure_relight(args, ctx: Ctx, steps: int, warmup: int, clocks: ClockSample
         "metric": "relight ms/frame", "value": round(ms_frame / world, 4), "unit": "ms/frame", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms_frame, 4), "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3-eval: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
-                               "S=7/VS=64 at %dx%d, fixed HDR env map" % (ns, P_SURFELS // 1000, WIDTH, HEIGHT),
+        "config": {"workload": "%s: relight frame = render_equation (Ns=%d) over %dk surfels + svgss forward "
+                               "S=7/VS=64 at %dx%d, fixed HDR env map" % (label, ns, P_SURFELS // 1000, WIDTH, HEIGHT),
                    "grid": "%d views x %d env maps, round-robin over ranks" % (N_VIEWS, n_env),
-                   "l2": "working set > L2 (light buffers 3.7 GB/frame)"},
+                   "l2": "working set > L2 (light buffers %.1f GB resident)" % (P_SURFELS * ns * 32 / 1e9)},
+        "sweep": {"frames": N_VIEWS * n_env, "seconds_at_this_rate": round(N_VIEWS * n_env * ms_frame / world / 1e3, 3),
+                  "frames_per_s_all_ranks": round(world * 1e3 / ms_frame, 1)},
         "workload_stats": {"R": int(res["num_rendered"]), "surfels_shaded": n_sh},
         "gpu_launches": int(launches),
         "launch_mode": "eager" if runner is None else "cuda-graph (1 capture, %d svgir kernels/frame)" % runner.launches_per_frame,
@@ -1156,6 +1162,10 @@ def run_ours(args):
         extra("c4", lambda: {k: v for k, v in measure_c4(args, ctx, steps=5, warmup=3).items()
                              if k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "grad_allreduce",
                                       "kernels_ms", "gpu_launches", "R_last_step_local")})
+        # every N: C5 (2 M surfels, 1920x1080, 200 views x 5 env maps sharded view x env map over the ranks, no collective)
+        extra("c5", lambda: {k: v for k, v in measure_relight(args, ctx, steps=8, warmup=2, shape=C5_SHAPE).items()
+                             if k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "workload_stats", "sweep",
+                                      "e2e", "kernels_ms", "launch_mode")})
         if ctx.world == 1:
             extra("relight", lambda: {k: v for k, v in measure_relight(args, ctx, steps=10, warmup=3).items()
                                       if k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "workload_stats", "e2e",
@@ -1185,6 +1195,8 @@ def run_workload(args):
         clocks.start()
     if args.workload == "relight":
         out = measure_relight(args, ctx, args.steps, args.warmup, clocks)
+    elif args.workload == "c5":
+        out = measure_relight(args, ctx, args.steps, args.warmup, clocks, shape=C5_SHAPE)
     elif args.workload == "c4":
         clocks.mark(True)
         out = measure_c4(args, ctx, args.steps, args.warmup)
@@ -1221,7 +1233,7 @@ def main():
     ap.add_argument("--bg-ctas", type=int, default=4, help="--reduce overlap: CTA limit of the communicator that carries the "
                     "segment overlapped with the shading backward (0 = default communicator for both segments)")
     ap.add_argument("--eager", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4", "visibility", "radiance"],
+    ap.add_argument("--workload", default="train", choices=["train", "relight", "c4", "c5", "visibility", "radiance"],
                     help="train = C3-train fwd+bwd it/s (headline, plus the extra keys); relight = C3-eval forward ms/frame (Ns=384, "
                          "S=7, VS=64); c4 = 1M surfels, 8 views per step sharded over the ranks (strong scaling); visibility = LBVH "
                          "build + opacity trace vs the reference kernels")

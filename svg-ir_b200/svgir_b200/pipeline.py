@@ -145,6 +145,8 @@ def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: 
         prestate, work = preprocess_geometry(raster_settings, means3D, pc.opacity, pc.scaling, pc.rotation, None,
                                              pc.shs, None)
         raster_settings = raster_settings._replace(prestate=prestate)
+        if OVERLAP_BINNING:
+            raster.start_binning(prestate)   # tile binning on a side stream, under the shading (no-op without a capacity hint)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
 
     # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel. FUSED_VIEWDIRS: the view
@@ -322,6 +324,7 @@ def reduce_segments(pc: SurfelModel) -> list:
 # between the kernels, one arena memset, binning / parameter backward on a side stream); False = `training_step`
 # (the autograd mirror of the reference's control flow) is what gets captured.
 FUSED_STEP = True
+OVERLAP_BINNING = True    # render_view / training_step: bin on a side stream while the shading kernel runs
 
 
 class BinOverflow(RuntimeError):

@@ -204,6 +204,7 @@ class RasterState:
         self.dims = None
         self.src = None
         self.rendered = False
+        self.binned = None        # event: start_binning() launched part 2a on the side stream
 
     def resolve(self) -> int:
         """Wait for the (R, overflow) copy of an async forward; raises CapacityOverflow if the bins
@@ -327,6 +328,45 @@ def preprocess(s: RasterSettings, means3D, opacities, scales=None, rotations=Non
     return st
 
 
+_BIN_STREAMS: dict = {}
+
+
+def start_binning(st: RasterState) -> bool:
+    """Forward, part 2a, early: launches the tile binning (scan, duplicateWithKeys, sort -- geometry only) of a
+    `preprocess()`-ed state on a side stream, so that the caller's stream can run what produces `features` /
+    `vfeatures` (the render_equation shading) meanwhile; `forward(..., prestate=st)` then waits for it and only
+    composites. Fork and join are events, hence capturable. Needs a known binning capacity without a host read
+    (count mode "async" with a capacity hint); otherwise it does nothing and forward() bins in order. Returns
+    whether the binning was launched."""
+    if st.cfg is None or st.rendered or st.binned is not None:
+        return False
+    P, H, W, M = st.dims
+    dev = st.src.device
+    mode = COUNT_MODE if SPECULATIVE else "exact"
+    hint = _CAP_HINT.get((dev.index, P, W, H)) if mode == "async" else None
+    if hint is None:
+        return False
+    t, cst = st.t, st.cstate
+    cap = max(int(hint), 1)
+    t["keys"] = torch.empty((cap,), dtype=torch.int64, device=dev)
+    t["point_list"] = torch.empty((cap,), dtype=torch.int32, device=dev)
+    t["sorted_keys"] = None
+    cst.keys, cst.point_list, cst.sorted_keys, cst.cap_R = t["keys"].data_ptr(), t["point_list"].data_ptr(), None, cap
+    side = _BIN_STREAMS.get(dev.index)
+    if side is None:
+        side = _BIN_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().svgir_raster_bin(C.byref(st.cfg), C.byref(st.cin), C.byref(cst), C.byref(st.cout),
+                                               C.c_void_p(side.cuda_stream)), "raster_bin")
+    st.binned = torch.cuda.Event()
+    st.binned.record(side)
+    return True
+
+
 def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, cov3D_precomp=None,
             shs=None, colors_precomp=None, features=None, vfeatures=None, want_sorted_keys=False,
             prestate: Optional[RasterState] = None):
@@ -395,9 +435,16 @@ def forward(s: RasterSettings, means3D, opacities, scales=None, rotations=None, 
             raise RuntimeError("svgir_b200: a forward captured into a CUDA graph needs a binning capacity "
                                "(run one eager forward first, or raster.reserve())")
         if hint is not None and mode == "async":
-            alloc_bins(hint)
-            _lib.check(L.svgir_raster_render(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
-                       "raster_render")
+            if st.binned is not None and not want_sorted_keys:   # start_binning() ran it on the side stream
+                torch.cuda.current_stream(dev).wait_event(st.binned)
+                _lib.check(L.svgir_raster_composite(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
+                           "raster_composite")
+            else:
+                if st.binned is not None:
+                    torch.cuda.current_stream(dev).wait_event(st.binned)
+                alloc_bins(hint)
+                _lib.check(L.svgir_raster_render(C.byref(cfg), C.byref(cin), C.byref(cst), C.byref(cout), stream),
+                           "raster_render")
             st.count_host = _pinned_slot(capturing)
             st.count_host.copy_(t["num_rendered"], non_blocking=True)
             if not capturing:
