@@ -255,7 +255,15 @@ typedef struct svgir_shade_in {
     const float* campos;         /* [3] device, or NULL */
     const int32_t* skip_flag;    /* optional device flag: the backward does nothing when *skip_flag != 0 (the
                                     rasteriser's binning-overflow flag: an overflowed step contributes zero) */
+    const float* env_taps;       /* optional [N,Ns,3] from svgir_env_taps for THESE incident_dirs / env size / transform:
+                                    the lat-long texel corner and bilinear weights of every sample, so that the kernels
+                                    skip acos / atan2 (the directions are fixed between two update_radiace calls and
+                                    across the views and env maps of a relight sweep). Same values, bit for bit. */
 } svgir_shade_in;
+
+/* Env-map tap cache: taps[i] = { bits(x0 | y0 << 16) (signed 16-bit halves), wx1, wy1 } of the bilinear lat-long lookup
+ * (scene/direct_light_map.py:70-83) of direction dirs[i] (after the optional 3x3 transform) in an env_h x env_w map. */
+int svgir_env_taps(long long n, int env_h, int env_w, const float* transform, const float* dirs, float* taps, void* stream);
 
 typedef struct svgir_shade_out {
     float* pbr; float* diffuse_light; float* specular; float* direct; float* indirect; /* [N,12]; any may be NULL */

@@ -30,6 +30,18 @@ __device__ __forceinline__ EnvTap env_coords(float dx, float dy, float dz, int H
     return t;
 }
 
+// tap cache encoding (svgir_env_taps): word 0 = x0 | y0 << 16 (signed halves: -1 .. We-1 fit), words 1, 2 = wx1, wy1
+__device__ __forceinline__ float env_tap_pack(const EnvTap& t) {
+    return __int_as_float((t.x0 & 0xffff) | (t.y0 << 16));
+}
+__device__ __forceinline__ EnvTap env_tap_unpack(float w0, float wx1, float wy1) {
+    const int b = __float_as_int(w0);
+    EnvTap t;
+    t.x0 = (int)(short)(b & 0xffff); t.y0 = b >> 16;
+    t.wx1 = wx1; t.wy1 = wy1;
+    return t;
+}
+
 __device__ __forceinline__ void env_fetch(const float* env, int He, int We, const EnvTap& t, float out[3]) {
     const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
     out[0] = out[1] = out[2] = 0.f;
@@ -42,6 +54,27 @@ __device__ __forceinline__ void env_fetch(const float* env, int He, int We, cons
         out[0] = fmaf(e[0], w, out[0]);
         out[1] = fmaf(e[1], w, out[1]);
         out[2] = fmaf(e[2], w, out[2]);
+    }
+}
+
+// The same lookup on a padded copy of the map, env4 [He][We] float4 (what the shading kernels keep in shared memory):
+// four 128-bit loads instead of twelve scalar ones, out-of-range taps handled by a clamped address and a zero weight
+// (grid_sample's zero padding) instead of a branch. Same products, same order of additions as env_fetch.
+__device__ __forceinline__ void env_fetch4(const float4* env4, int He, int We, const EnvTap& t, float out[3]) {
+    const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+    out[0] = out[1] = out[2] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = t.x0 + (k & 1), y = t.y0 + (k >> 1);
+        const bool in = x >= 0 && x <= We - 1 && y >= 0 && y <= He - 1;
+        const int xc = min(max(x, 0), We - 1), yc = min(max(y, 0), He - 1);
+        const float w = ((k & 1) ? t.wx1 : wx0) * ((k >> 1) ? t.wy1 : wy0);
+        const float4 e = env4[yc * We + xc];
+        if (in) {   // predicated adds: skipping (not adding a zero product) keeps -0 / NaN behaviour of env_fetch
+            out[0] = fmaf(e.x, w, out[0]);
+            out[1] = fmaf(e.y, w, out[1]);
+            out[2] = fmaf(e.z, w, out[2]);
+        }
     }
 }
 

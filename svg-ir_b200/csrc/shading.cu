@@ -72,6 +72,7 @@ struct ShadeArgs {
     const float* means3D;      // viewdirs == nullptr: view vector = campos - means3D[n] (normalised in the kernel)
     const float* campos;
     const int32_t* skip_flag;  // backward only: return immediately when *skip_flag != 0
+    const float* taps;         // optional [N,Ns,3] cached env taps (svgir_env_taps): no acos / atan2 per sample
     int view_stride;           // row stride of view3x3: 3, or 4 when it points at the 4x4 world-view matrix itself
 };
 
@@ -120,7 +121,7 @@ __device__ __forceinline__ float inv_len(float ss) {
 
 // Raw per-sample inputs of one lane: loaded one (surfel, pass) ahead of their use so that the HBM
 // latency of the next 32 samples hides behind the arithmetic of the current ones.
-struct RawSample { float wx, wy, wz, r0, r1, r2, vis, area; };
+struct RawSample { float wx, wy, wz, r0, r1, r2, vis, area, t0, t1, t2; };
 
 __device__ __forceinline__ void fetch_raw(const ShadeArgs& a, int n, int s0, int lane, RawSample& r) {
     const int s = s0 + lane;
@@ -130,6 +131,7 @@ __device__ __forceinline__ void fetch_raw(const ShadeArgs& a, int n, int s0, int
     const float* rad = a.radiance + is * 3;
     r.r0 = __ldg(rad); r.r1 = __ldg(rad + 1); r.r2 = __ldg(rad + 2);
     r.vis = __ldg(a.visibility + is); r.area = __ldg(a.areas + is);
+    if (a.taps) { const float* tp = a.taps + is * 3; r.t0 = __ldg(tp); r.t1 = __ldg(tp + 1); r.t2 = __ldg(tp + 2); }
     // nothing here may consume the loaded values: the point is to leave them in flight
 }
 // a padded lane (sample index >= Ns) contributes nothing
@@ -170,6 +172,7 @@ struct Sample {
     EnvTap tap;
 };
 
+template <bool ENV4>   // ENV4: `env` is the padded float4 copy in shared memory
 __device__ __forceinline__ void make_sample(const ShadeArgs& a, const float* env, const RawSample& r, float Vx,
                                             float Vy, float Vz, Sample& o) {
     o.wx = r.wx; o.wy = r.wy; o.wz = r.wz;
@@ -182,16 +185,21 @@ __device__ __forceinline__ void make_sample(const ShadeArgs& a, const float* env
     o.voh_raw = Vx * o.hx + Vy * o.hy + Vz * o.hz;
     const float voh = fminf(fmaxf(o.voh_raw, 1e-6f), 1.f);
     o.p = exp2f((-5.55473f * voh - 6.98316f) * voh);
-    float qx = o.wx, qy = o.wy, qz = o.wz;  // direct_light uses the raw direction
-    if (a.transform) {
-        const float* t = a.transform;  // dirs @ transform.T
-        const float tx = qx * t[0] + qy * t[1] + qz * t[2];
-        const float ty = qx * t[3] + qy * t[4] + qz * t[5];
-        const float tz = qx * t[6] + qy * t[7] + qz * t[8];
-        qx = tx; qy = ty; qz = tz;
+    if (a.taps) {
+        o.tap = env_tap_unpack(r.t0, r.t1, r.t2);   // cached: the same env_coords result, computed once per run
+    } else {
+        float qx = o.wx, qy = o.wy, qz = o.wz;  // direct_light uses the raw direction
+        if (a.transform) {
+            const float* t = a.transform;  // dirs @ transform.T
+            const float tx = qx * t[0] + qy * t[1] + qz * t[2];
+            const float ty = qx * t[3] + qy * t[4] + qz * t[5];
+            const float tz = qx * t[6] + qy * t[7] + qz * t[8];
+            qx = tx; qy = ty; qz = tz;
+        }
+        o.tap = env_coords(qx, qy, qz, a.He, a.We);
     }
-    o.tap = env_coords(qx, qy, qz, a.He, a.We);
-    env_fetch(env, a.He, a.We, o.tap, o.raw);
+    if (ENV4) env_fetch4(reinterpret_cast<const float4*>(env), a.He, a.We, o.tap, o.raw);
+    else env_fetch(env, a.He, a.We, o.tap, o.raw);
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
         o.lg[ch] = fminf(fmaxf(o.raw[ch] * a.env_scale, 0.f), 64.f);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
     float* env_s = smem_f + WPC * 4 * VUF_FLOATS;
     const float* env = a.env_act;
     if (ENV_SMEM) {
-        for (int i = threadIdx.x; i < a.He * a.We * 3; i += SH_THREADS) env_s[i] = a.env_act[i];
+        for (int i = threadIdx.x; i < a.He * a.We * 4; i += SH_THREADS) env_s[i] = (i & 3) < 3 ? a.env_act[(i >> 2) * 3 + (i & 3)] : 0.f;
         __syncthreads();
         env = env_s;
     }
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const ShadeArgs a
             if (s0 + 32 < Ns) fetch_raw(a, n, s0 + 32, lane, raw);
             else if (n_next < a.N) fetch_raw(a, n_next, 0, lane, raw);
             Sample sm;
-            make_sample(a, env, cur, Vx, Vy, Vz, sm);
+            make_sample<ENV_SMEM>(a, env, cur, Vx, Vy, Vz, sm);
             m_vis += cur.vis;
             m_l[0] += cur.r0; m_l[1] += cur.r1; m_l[2] += cur.r2;
             float A0[3], A1[3];
@@ -481,7 +489,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
     float* env_s = smem_b + WPC * 4 * VU_FLOATS;                    // activated env (if it fits)
     const float* env = a.env_act;
     if (ENV_SMEM) {
-        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) env_s[i] = a.env_act[i];
+        for (int i = threadIdx.x; i < nenv; i += SHB_THREADS) env_s[i] = a.env_act[i];   // scalar layout: the padded float4 lookup costs this kernel registers it does not have (0.508 -> 0.526 ms)
         __syncthreads();
         env = env_s;
     }
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
             const bool ok = s < Ns;
             const size_t is = (size_t)n * Ns + (ok ? s : Ns - 1);
             Sample sm;
-            make_sample(a, env, cur, Vx, Vy, Vz, sm);
+            make_sample<false>(a, env, cur, Vx, Vy, Vz, sm);
             float dAg[3] = {0, 0, 0}, dAl[3] = {0, 0, 0}, dp_acc = 0.f, dhN[3] = {0, 0, 0};
 #pragma unroll
             for (int v = 0; v < 4; v++) {
@@ -772,6 +780,22 @@ __global__ void __launch_bounds__(SHB_THREADS, SHB_MIN_CTAS) shade_bwd_kernel(co
     }
 }
 
+// ---- env tap cache --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) env_taps_kernel(long long n, int He, int We, const float* __restrict__ transform,
+                                                       const float* __restrict__ dirs, float* __restrict__ taps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+    if (transform) {
+        const float tx = x * transform[0] + y * transform[1] + z * transform[2];
+        const float ty = x * transform[3] + y * transform[4] + z * transform[5];
+        const float tz = x * transform[6] + y * transform[7] + z * transform[8];
+        x = tx; y = ty; z = tz;
+    }
+    const EnvTap t = env_coords(x, y, z, He, We);
+    taps[3 * i] = env_tap_pack(t); taps[3 * i + 1] = t.wx1; taps[3 * i + 2] = t.wy1;
+}
+
 // ---- stand-alone env lookup (DirectLightMap.direct_light / EnvLight.direct_light) ---------------
 __global__ void __launch_bounds__(256) direct_light_fwd_kernel(int n, int He, int We, float scale,
                                                                const float* __restrict__ env_act,
@@ -850,7 +874,7 @@ static int shade_grid(int N, int threads, int ctas_per_sm) {
 
 template <bool SPLIT, bool MET>
 static void launch_shade_fwd(const ShadeArgs& a, const ShadeOutK& so, cudaStream_t s) {
-    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
+    const size_t env_bytes = (size_t)a.He * a.We * 4 * sizeof(float);   // padded float4 texels
     const size_t vu_bytes = (size_t)(SH_THREADS / 32) * 4 * VUF_FLOATS * sizeof(float);
     const int grid = shade_grid(a.N, SH_THREADS, 2);
     if (env_bytes + vu_bytes <= 96 * 1024) {
@@ -896,7 +920,7 @@ static int shade_prepare(const svgir_shade_cfg* c, const svgir_shade_in* in, Sha
     a.normals = in->normals; a.viewdirs = in->viewdirs; a.radiance = in->radiance;
     a.visibility = in->visibility; a.dirs = in->incident_dirs; a.areas = in->incident_areas;
     a.list = in->surfel_list; a.list_count = in->surfel_list ? in->surfel_count : nullptr;
-    a.means3D = in->means3D; a.campos = in->campos; a.skip_flag = in->skip_flag;
+    a.means3D = in->means3D; a.campos = in->campos; a.skip_flag = in->skip_flag; a.taps = in->env_taps;
     a.view_stride = (c->flags & SVGIR_SHADE_VIEW_4X4) ? 4 : 3;
     if (in->surfel_list && !in->surfel_count) { set_error("shade: surfel_list needs surfel_count"); return SVGIR_ERR_INVALID; }
     return SVGIR_OK;
@@ -958,6 +982,16 @@ int svgir_shade_backward(const svgir_shade_cfg* c, const svgir_shade_in* in, con
         env_grad_finalize_kernel<<<(ntex * 3 + 255) / 256, 256, 0, s>>>(ntex, SVGIR_SHADE_ENV_COPIES, c->env_mode, gr->d_env_scratch, in->env, gr->d_env);
     }
     return check_launch("shade_backward", c->debug, s);
+}
+
+int svgir_env_taps(long long n, int env_h, int env_w, const float* transform, const float* dirs, float* taps, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n < 0 || env_h <= 0 || env_w <= 0 || env_h > 32767 || env_w > 32767 || (n > 0 && (!dirs || !taps))) { set_error("env_taps: bad args"); return SVGIR_ERR_INVALID; }
+    if (n == 0) return SVGIR_OK;
+    const long long blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffLL) { set_error("env_taps: too many directions for one launch"); return SVGIR_ERR_INVALID; }
+    { TimedScope ts_("env_taps", s); env_taps_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, env_h, env_w, transform, dirs, taps); }
+    return check_launch("env_taps", false, s);
 }
 
 int svgir_direct_light_forward(int n, int env_h, int env_w, int env_mode, const float* env, float* env_act_scratch,

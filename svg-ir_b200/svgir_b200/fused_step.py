@@ -212,6 +212,9 @@ class FusedTrainStep:
             pc.radiance.data_ptr(), pc.visibility.data_ptr(), pc.incident_dirs.data_ptr(), pc.incident_areas.data_ptr(),
             env3.data_ptr(), None, self.env_act.data_ptr(), cam.world_view_transform.data_ptr(), t["vis_list"].data_ptr(),
             t["vis_count"].data_ptr(), pc.xyz.data_ptr(), cam.camera_center.data_ptr(), t["num_rendered"][1:].data_ptr())
+        # env taps of the (fixed) incident directions: no acos / atan2 per sample in the shading kernels
+        self.env_taps = shading.refresh_env_taps(pc.incident_dirs, He, We)
+        self.sin.env_taps = None if self.env_taps is None else self.env_taps.data_ptr()
         vp, fp = self.vfeats.data_ptr(), self.feats.data_ptr()
         self.sout = shading.ShadeOut(vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None, vp + 4 * 12,
                                      self.sums.data_ptr(), None, VS, S, S, 0)
@@ -289,6 +292,14 @@ class FusedTrainStep:
         self.t["keys"] = torch.empty((cap,), dtype=torch.int64, device=self.dev)
         self.t["point_list"] = torch.empty((cap,), dtype=torch.int32, device=self.dev)
         self.cst.keys, self.cst.point_list, self.cst.cap_R = self.t["keys"].data_ptr(), self.t["point_list"].data_ptr(), cap
+
+    def refresh_taps(self):
+        """Call after the incident directions were re-sampled in place (update_radiace): recomputes the cached env taps
+        into the buffer the step's kernels already point at. A no-op when nothing changed."""
+        if self.env_taps is not None:
+            t = shading.refresh_env_taps(self.pc.incident_dirs, *self.env_hw)
+            if t is None or t.data_ptr() != self.env_taps.data_ptr():
+                raise RuntimeError("FusedTrainStep: the incident-direction buffer was replaced; rebuild the step")
 
     def calibrate(self) -> int:
         """Sizes the binning buffers from one eager per-surfel preprocess of the current camera (one host sync)."""

@@ -507,6 +507,8 @@ class GraphedTrainingStep:
 
     def load_inputs(self, cam: ViewCamera, gt_image: torch.Tensor):
         c = self._check_intrinsics(cam)
+        if self.fs is not None:
+            self.fs.refresh_taps()   # incident directions re-sampled in place since the capture? (a version compare)
         if cam.block is not None and c.block is not None:
             c.block.copy_(cam.block, non_blocking=True)   # one copy for all per-view constants
             if gt_image is not self.gt:
@@ -564,6 +566,8 @@ class GraphedTrainingStep:
         self._consumed = torch.cuda.Event()
         self._consumed.record(cur)
         self._staged = None
+        if self.fs is not None:
+            self.fs.refresh_taps()
         if self.graph is None:
             self._capture()
         self.graph.replay()
@@ -659,6 +663,8 @@ class GraphedRelightFrame:
                 getattr(c, k).copy_(getattr(cam, k), non_blocking=True)
         if env_map is not None and env_map is not self.env:
             self.env.copy_(env_map, non_blocking=True)
+        # the captured shading kernel points at the cached env taps of pc.incident_dirs: recomputed in place if those changed
+        shading.refresh_env_taps(self.pc.incident_dirs, int(self.env.shape[-3]), int(self.env.shape[-2]))
 
     def __call__(self, cam: ViewCamera, env_map: Optional[torch.Tensor] = None, check: bool = True) -> dict:
         self.load_inputs(cam, env_map)

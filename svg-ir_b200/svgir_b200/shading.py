@@ -14,6 +14,7 @@ All arithmetic runs in libsvgir_b200.so (csrc/shading.cu); there is no torch fal
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from typing import Optional
 
 import torch
@@ -38,7 +39,7 @@ class ShadeIn(C.Structure):
     _fields_ = [(n, c_fp) for n in ("base_color", "roughness", "metallic", "normals", "viewdirs", "radiance",
                                     "visibility", "incident_dirs", "incident_areas", "env", "env_transform",
                                     "env_act_scratch", "view3x3", "surfel_list", "surfel_count",
-                                    "means3D", "campos", "skip_flag")]
+                                    "means3D", "campos", "skip_flag", "env_taps")]
 
 
 class ShadeOut(C.Structure):
@@ -73,6 +74,8 @@ def _L():
         L.svgir_direct_light_forward.restype = C.c_int
         L.svgir_direct_light_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_void_p]
         L.svgir_direct_light_backward.restype = C.c_int
+        L.svgir_env_taps.argtypes = [C.c_longlong, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_void_p]
+        L.svgir_env_taps.restype = C.c_int
         _bound = True
     return L
 
@@ -94,6 +97,54 @@ def _stream(dev):
 
 
 ENV_COPIES = 16       # SVGIR_SHADE_ENV_COPIES
+
+# ---- env tap cache -------------------------------------------------------------------------------------------------
+# The incident directions of a model are fixed between two update_radiace / update_visibility calls (training) and
+# across all views and env maps of a relight sweep, so the texel corner + bilinear weights of every (surfel, sample)
+# -- the acos / atan2 part of DirectLightMap.direct_light, 7-14 % of the shading kernels' instructions -- are computed
+# once (svgir_env_taps) and handed to the kernels through svgir_shade_in.env_taps. Keyed by the directions' storage,
+# shape and version, the env size and the transform; a changed version recomputes INTO THE SAME buffer, so CUDA graphs
+# that baked the pointer stay valid (their owners call refresh_env_taps before a replay).
+ENV_TAP_CACHE = True
+_TAP_CACHE: "OrderedDict[tuple, list]" = OrderedDict()
+_TAP_CACHE_SIZE = 4
+
+
+def env_taps(dirs: torch.Tensor, env_h: int, env_w: int, transform: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[...,3] directions -> [...,3] taps (svgir_env_taps)."""
+    L = _L()
+    d = _c(dirs)
+    n = d.numel() // 3
+    taps = out if out is not None else torch.empty(tuple(d.shape), dtype=torch.float32, device=d.device)
+    if n:
+        with torch.cuda.device(d.device):
+            _lib.check(L.svgir_env_taps(n, int(env_h), int(env_w), _p(_c(transform)), _p(d), _p(taps), _stream(d.device)),
+                       "env_taps")
+    return taps
+
+
+def _cached_taps(dirs: Optional[torch.Tensor], env_h: int, env_w: int, transform: Optional[torch.Tensor]):
+    if not ENV_TAP_CACHE or dirs is None or not dirs.is_cuda or dirs.dtype != torch.float32 or not dirs.is_contiguous():
+        return None
+    key = (dirs.data_ptr(), tuple(dirs.shape), int(env_h), int(env_w), None if transform is None else transform.data_ptr())
+    ver = (dirs._version, None if transform is None else transform._version)
+    ent = _TAP_CACHE.get(key)
+    if ent is not None and ent[1] == ver:
+        _TAP_CACHE.move_to_end(key)
+        return ent[0]
+    taps = env_taps(dirs, env_h, env_w, transform, out=None if ent is None else ent[0])
+    _TAP_CACHE[key] = [taps, ver, dirs, transform]     # the entry keeps `dirs` alive: its address cannot be recycled
+    _TAP_CACHE.move_to_end(key)
+    while len(_TAP_CACHE) > _TAP_CACHE_SIZE:
+        _TAP_CACHE.popitem(last=False)
+    return taps
+
+
+def refresh_env_taps(dirs: torch.Tensor, env_h: int, env_w: int, transform: Optional[torch.Tensor] = None):
+    """Recomputes the cached taps of `dirs` in place if `dirs` (or the transform) was modified since; returns them."""
+    return _cached_taps(dirs, env_h, env_w, transform)
+
 MODE_LEARNABLE = 0  # softplus(param), x2   (DirectLightMap)
 MODE_FIXED = 1      # linear map as given, x1 (EnvLight after its 32x64 resize)
 
@@ -139,6 +190,7 @@ class _ShadeFn(torch.autograd.Function):
         cin = ShadeIn(_p(t["base_color"]), _p(t["roughness"]), _p(t["metallic"]), _p(t["normals"]), _p(t["viewdirs"]),
                       _p(t["radiance"]), _p(t["visibility"]), _p(t["incident_dirs"]), _p(t["incident_areas"]),
                       _p(t["env"]), _p(t["transform"]), _p(scratch), None)
+        cin.env_taps = _p(_cached_taps(t["incident_dirs"], He, We, t["transform"]))
         sums = torch.empty((2, N, 12), **f32)
         cout = ShadeOut(*[_p(o) for o in outs], _p(mv), _p(ml), _p(mi), _p(mg), None, _p(sums[0]), _p(sums[1]), 0, 0, 0, 0)
         if N > 0:
@@ -176,6 +228,7 @@ class _ShadeFn(torch.autograd.Function):
         cfg = ShadeCfg(N, Ns, He, We, env_mode, debug)
         cin = ShadeIn(_p(base_color), _p(roughness), _p(metallic), _p(normals), _p(viewdirs), _p(radiance),
                       _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), None)
+        cin.env_taps = _p(_cached_taps(dirs, He, We, transform))
         cg = ShadeGrads(*[_p(x) for x in gs], _p(d_base), _p(d_rough), _p(d_met), _p(d_norm), _p(d_view), _p(d_rad),
                         _p(d_vis), _p(d_env), None, _p(sums[0]), _p(sums[1]),
                         _p(torch.empty((ENV_COPIES, He, We, 4), **f32)) if d_env is not None else None, 0, 0, 0, 0)
@@ -243,6 +296,7 @@ class _ShadePackedFn(torch.autograd.Function):
                       _p(t["env"]), _p(t["transform"]), _p(scratch), _p(t["view3x3"]),
                       _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None,
                       _p(t["means3D"]), _p(t["campos"]), None)
+        cin.env_taps = _p(_cached_taps(t["incident_dirs"], He, We, t["transform"]))
         vp, fp = vfeats.data_ptr(), feats.data_ptr()
         # sums saved for backward: un-split total in training (only pbr / diffuse carry gradients there)
         sums = torch.empty((1 if is_training else 2, N, 12), **f32)
@@ -300,6 +354,7 @@ class _ShadePackedFn(torch.autograd.Function):
                       _p(visibility), _p(dirs), _p(areas), _p(env), _p(transform), _p(scratch), _p(view3x3),
                       _p(work[0]) if work is not None else None, _p(work[1]) if work is not None else None,
                       _p(means3D), _p(campos), None)
+        cin.env_taps = _p(_cached_taps(dirs, He, We, transform))
         vp, fp = g_vfeats.data_ptr(), g_feats.data_ptr()
         if is_training:
             gin = (vp, vp + 4 * 40, None, None, None, fp, fp + 4, None, None)

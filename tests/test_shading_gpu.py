@@ -242,3 +242,54 @@ def test_shade_full_size_differential(N, Ns, chunk):
         assert float(e.max()) <= max(3.0 * float(e_ref.max()), 3.0), (k, float(e.max()), float(e_ref.max()))
     for k, gref in ref_g.items():
         assert rel(ours_g[k], gref) < 1e-3, (k, rel(ours_g[k], gref))
+
+
+def test_env_tap_cache_is_bit_identical_and_follows_in_place_updates():
+    """svgir_env_taps + svgir_shade_in.env_taps: the cached texel corner / weights are the kernels' own env_coords
+    results, so outputs and gradients are bit-equal with and without the cache; re-sampling the directions in place
+    is picked up through the tensor version (the buffer is refreshed in place, as graphs that baked it need)."""
+    from svgir_b200 import shading
+    g = dict(np.load(os.path.join(GOLD, "ref_shading_train_small.npz")))
+    names = ("base_color", "roughness", "shading_normals", "viewdirs", "env_param")
+
+    def run(t, cache):
+        shading.ENV_TAP_CACHE = cache
+        for k in names:
+            t[k].grad = None
+        r = shading.shade_surfels(t["base_color"], t["roughness"], t["shading_normals"], t["viewdirs"], t["radiance"],
+                                  (t["env_param"], shading.MODE_LEARNABLE), t["visibility"], t["incident_dirs"],
+                                  t["incident_areas"])
+        (r["pbr"].sum() + 0.5 * r["specular"].sum() + r["mean_incident_lights"].sum()).backward()
+        shading.ENV_TAP_CACHE = True
+        return [r[k].detach().clone() for k in ("pbr", "diffuse_light", "specular")] + [t[k].grad.clone() for k in names]
+
+    t = {k[3:]: torch.tensor(v).cuda() for k, v in g.items() if k.startswith("in_")}
+    for k in names:
+        t[k].requires_grad_(True)
+    shading._TAP_CACHE.clear()
+    a = run(t, False)
+    assert not shading._TAP_CACHE
+    b = run(t, True)
+    assert len(shading._TAP_CACHE) == 1
+    for x, y in zip(a[:3] + a[3:4] + a[5:7], b[:3] + b[3:4] + b[5:7]):     # forward + deterministic gradients: bit-equal
+        assert torch.equal(x, y)
+    for x, y in zip(a, b):                                                   # atomically accumulated ones: order only
+        assert _rel(y.cpu().numpy(), x.cpu().numpy()) < 1e-6
+    taps = next(iter(shading._TAP_CACHE.values()))[0]
+    ptr = taps.data_ptr()
+    want = shading.env_taps(t["incident_dirs"], t["env_param"].shape[-3], t["env_param"].shape[-2])
+    assert torch.equal(taps, want)
+    # the directions are re-sampled in place (update_radiace): same buffer, new content
+    with torch.no_grad():
+        d = t["incident_dirs"]
+        d.copy_(torch.nn.functional.normalize(d + 0.3 * torch.roll(d, 1, dims=1), dim=-1))
+    c_off = run(t, False)
+    c_on = run(t, True)
+    assert len(shading._TAP_CACHE) == 1 and next(iter(shading._TAP_CACHE.values()))[0].data_ptr() == ptr
+    assert torch.equal(c_off[0], c_on[0]) and not torch.equal(c_on[0], b[0])
+    # tap words decode to the lookup's texel corner: an in-range direction lands inside the map
+    He, We = int(t["env_param"].shape[-3]), int(t["env_param"].shape[-2])
+    w0 = taps.reshape(-1, 3)[:, 0].contiguous().view(torch.int32)
+    x0 = ((w0 & 0xffff) ^ 0x8000) - 0x8000
+    y0 = w0 >> 16
+    assert int(x0.min()) >= -1 and int(x0.max()) <= We - 1 and int(y0.min()) >= -1 and int(y0.max()) <= He - 1
