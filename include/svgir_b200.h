@@ -645,6 +645,7 @@ typedef struct svgir_radiance_loss_in {
     float* env_act_scratch;      /* [env_h*env_w*3] */
     const int32_t* skip_flag;    /* optional device flag: nonzero = the backward adds nothing (the fused training step
                                     passes its binning-overflow flag: an overflowed step contributes no gradient) */
+    const float* env_taps;       /* optional [P,S,3] from svgir_env_taps(incident_dirs, env_h, env_w): skips acos / atan2 */
 } svgir_radiance_loss_in;
 
 /* loss [1] = mean |irradiance - nan_to_num(radiances[n, sel[n]] * ratio)| over [P,3]. Written: irradiance [P,3];

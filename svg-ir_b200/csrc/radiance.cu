@@ -217,6 +217,7 @@ struct RLArgs {
         *roughness, *env_act, *env_param;
     const int32_t* hit;
     const int32_t* skip_flag;
+    const float* taps;
 };
 
 // shading_brdf_simple (pbr.slang:283-330): specular part and, optionally, its derivative w.r.t. roughness.
@@ -330,7 +331,7 @@ __device__ __forceinline__ void load_hit_surfel(const RLArgs& a, int h, HitSurfe
 
 // Raw inputs of one secondary sample of render_irradiance_sample (:1212-1303): loaded unconditionally so that all the
 // gathers of a surfel are in flight together.
-struct SecRaw { int hit2; float rx, ry, rz, u, v, area; };
+struct SecRaw { int hit2; float rx, ry, rz, u, v, area, t0, t1, t2; };
 __device__ __forceinline__ void load_secondary_raw(const RLArgs& a, int h, int s2, SecRaw& r) {
     const size_t i = (size_t)h * a.S + (s2 < a.S ? s2 : 0);
     r.hit2 = s2 < a.S ? __ldg(a.hit + i) : 0;           // anything but -1 closes the sample
@@ -339,6 +340,7 @@ __device__ __forceinline__ void load_secondary_raw(const RLArgs& a, int h, int s
     const float2 uv = __ldg(reinterpret_cast<const float2*>(a.uv) + i);
     r.u = uv.x; r.v = uv.y;
     r.area = __ldg(a.areas + i);
+    if (a.taps) { const float* tp = a.taps + i * 3; r.t0 = __ldg(tp); r.t1 = __ldg(tp + 1); r.t2 = __ldg(tp + 2); }
 }
 
 struct SecSample { float Lx, Ly, Lz, Hx, Hy, Hz, VoH, w[4], E[3]; EnvTap tap; float escale; };
@@ -351,7 +353,7 @@ __device__ __forceinline__ void make_secondary(const RLArgs& a, const SecRaw& r,
     q.VoH = fminf(fmaxf(Vx * q.Hx + Vy * q.Hy + Vz * q.Hz, 1e-6f), 1.f);
     q.w[0] = (1 - r.u) * (1 - r.v); q.w[1] = r.u * (1 - r.v); q.w[2] = (1 - r.u) * r.v; q.w[3] = r.u * r.v;
     // envmap[h,s2] = direct_light(dirs[h,s2]) * areas[h,s2] (gaussian_model.py:547), on the raw direction
-    q.tap = env_coords(r.rx, r.ry, r.rz, a.He, a.We);
+    q.tap = a.taps ? env_tap_unpack(r.t0, r.t1, r.t2) : env_coords(r.rx, r.ry, r.rz, a.He, a.We);
     q.escale = a.env_scale * r.area;
     float e[3];
     env_fetch(a.env_act, a.He, a.We, q.tap, e);
@@ -571,7 +573,7 @@ static int rl_prepare(const svgir_radiance_loss_cfg* c, const svgir_radiance_los
     a.means3D = in->means3D; a.campos = in->campos; a.geo_normal = in->geo_normal; a.dirs = in->incident_dirs;
     a.areas = in->incident_areas; a.vis = in->visibility; a.uv = in->uv; a.radiances = in->radiances;
     a.ratio = in->radiance_ratio; a.normals = in->normals; a.albedo = in->albedo; a.roughness = in->roughness;
-    a.env_act = in->env_act_scratch; a.env_param = in->env; a.hit = in->hit_index; a.skip_flag = in->skip_flag;
+    a.env_act = in->env_act_scratch; a.env_param = in->env; a.hit = in->hit_index; a.skip_flag = in->skip_flag; a.taps = in->env_taps;
     return SVGIR_OK;
 }
 

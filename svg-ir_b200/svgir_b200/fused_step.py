@@ -258,7 +258,9 @@ class FusedTrainStep:
                 pc.xyz.data_ptr(), cam.camera_center.data_ptr(), rc.geo_normal.data_ptr(), rc.incident_dirs.data_ptr(),
                 rc.incident_areas.data_ptr(), rc.visibility_tracing.data_ptr(), hit.data_ptr(), rc.uv_buffers.data_ptr(),
                 rc.radiances.data_ptr(), self.rad["ratio"].data_ptr(), pc.shading_normal.data_ptr(), pc.base_color.data_ptr(),
-                pc.roughness.data_ptr(), env3.data_ptr(), self.rad["env_act"].data_ptr(), t["num_rendered"][1:].data_ptr())
+                pc.roughness.data_ptr(), env3.data_ptr(), self.rad["env_act"].data_ptr(), t["num_rendered"][1:].data_ptr(), None)
+            self.rad["taps"] = shading.refresh_env_taps(rc.incident_dirs, He, We)
+            self.rin.env_taps = None if self.rad["taps"] is None else self.rad["taps"].data_ptr()
         self.cap = 0
         self._alloc_bins(capacity if capacity else raster._CAP_HINT.get((dev.index, P, W, H), 0))
         self.launches = 0
@@ -300,6 +302,8 @@ class FusedTrainStep:
             t = shading.refresh_env_taps(self.pc.incident_dirs, *self.env_hw)
             if t is None or t.data_ptr() != self.env_taps.data_ptr():
                 raise RuntimeError("FusedTrainStep: the incident-direction buffer was replaced; rebuild the step")
+        if self.rc is not None and self.rad.get("taps") is not None:
+            shading.refresh_env_taps(self.rc.incident_dirs, *self.env_hw)
 
     def calibrate(self) -> int:
         """Sizes the binning buffers from one eager per-surfel preprocess of the current camera (one host sync)."""

@@ -38,7 +38,7 @@ class RadianceLossCfg(C.Structure):
 class RadianceLossIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "means3D", "campos", "geo_normal", "incident_dirs", "incident_areas", "visibility", "hit_index", "uv", "radiances",
-        "radiance_ratio", "normals", "albedo", "roughness", "env", "env_act_scratch", "skip_flag")]
+        "radiance_ratio", "normals", "albedo", "roughness", "env", "env_act_scratch", "skip_flag", "env_taps")]
 
 
 _BOUND = False
@@ -155,7 +155,10 @@ class _RadianceLossFn(torch.autograd.Function):
                              t["areas"].data_ptr(), t["vis"].data_ptr(), hit_c.data_ptr(), t["uv"].data_ptr(),
                              t["radiances"].data_ptr(), None if t["ratio"] is None else t["ratio"].data_ptr(),
                              t["normals"].data_ptr(), t["albedo"].data_ptr(), t["roughness"].data_ptr(), t["env"].data_ptr(),
-                             scratch_env.data_ptr(), None)
+                             scratch_env.data_ptr(), None, None)
+        from . import shading as _sh
+        taps = _sh.refresh_env_taps(dirs if dirs.is_contiguous() and dirs.dtype == torch.float32 else t["dirs"], He, We)
+        cin.env_taps = None if taps is None else taps.data_ptr()
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         irr = torch.empty((P, 3), dtype=torch.float32, device=dev)
         sel = torch.empty((P,), dtype=torch.int32, device=dev)
@@ -164,7 +167,7 @@ class _RadianceLossFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(L.svgir_radiance_loss_forward(C.byref(cfg), C.byref(cin), loss.data_ptr(), irr.data_ptr(), sel.data_ptr(),
                                                      saved.data_ptr(), scratch.data_ptr(), _stream(dev)), "radiance_loss_forward")
-        ctx.cfg, ctx.cin, ctx.keep = cfg, cin, (t, hit_c, scratch_env)
+        ctx.cfg, ctx.cin, ctx.keep = cfg, cin, (t, hit_c, scratch_env, taps)
         ctx.save_for_backward(irr, saved)
         ctx.mark_non_differentiable(irr, sel)
         return loss[0], irr, sel
@@ -173,7 +176,7 @@ class _RadianceLossFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_irr, _g_sel):
         L = _L()
         irr, saved = ctx.saved_tensors
-        t, _hit, _scr = ctx.keep
+        t, _hit, _scr, _taps = ctx.keep
         cfg = ctx.cfg
         dev = irr.device
         need_a, need_r, need_e = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
