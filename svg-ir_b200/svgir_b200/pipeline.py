@@ -707,4 +707,15 @@ def smoke_step(P=3000, W=96, H=64, Ns=16) -> dict:
     assert torch.isfinite(loss)
     for t in pc.trainable() + [env]:
         assert t.grad is not None and torch.isfinite(t.grad).all()
-    return {"loss": float(loss), "launches": launch_count(), "num_rendered": res["num_rendered"]}
+    n_launch = launch_count()
+    # the same step as the bench runs it: FusedTrainStep captured into a CUDA graph, replayed twice
+    want = [t.grad.detach().clone() for t in pc.trainable() + [env]]
+    runner = GraphedTrainingStep(pc, env, bg, cam, gt)
+    for _ in range(2):
+        gloss, gres = runner(cam, gt)
+    torch.cuda.synchronize()
+    assert abs(float(gloss) - float(loss)) <= 1e-5 * abs(float(loss)), (float(gloss), float(loss))
+    for t, w in zip(pc.trainable() + [env], want):
+        assert float((t.grad - w).norm()) <= 1e-3 * float(w.norm()) + 1e-12
+    return {"loss": float(loss), "launches": n_launch, "num_rendered": res["num_rendered"],
+            "graph_launches_per_step": runner.launches_per_step}
