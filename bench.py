@@ -666,6 +666,8 @@ def measure_c4(args, ctx: Ctx, steps: int, warmup: int) -> dict:
         "kernels_ms": kt}
     runner = runner_last = None
     del pc, env, params, bucket, peer, mats
+    from svgir_b200 import shading as _shading
+    _shading.clear_env_tap_cache()   # its entries pin the model's direction buffers
     gc.collect()
     torch.cuda.empty_cache()
     return out
@@ -805,6 +807,8 @@ def measure_relight(args, ctx: Ctx, steps: int, warmup: int, clocks: ClockSample
         "kernels_ms": {k: round(v, 4) for k, v in kt.items()}}
     runner = None
     del pc, mats
+    from svgir_b200 import shading as _shading
+    _shading.clear_env_tap_cache()   # its entries pin the model's direction buffers
     gc.collect()
     torch.cuda.empty_cache()
     return out
@@ -974,7 +978,8 @@ def measure_radiance(args, ctx: Ctx, steps: int = 10, warmup: int = 3) -> dict:
                              "loss_radiance": float(runner.fs.result["loss_radiance"]),
                              "note": "the headline step plus get_radiance_loss; select+forward and backward kernels run on "
                                      "the side stream under the rasteriser"}
-    out["config"] = {"workload": "C3-train + radiance term: 300k surfels x 64 samples, env 16x32", "parity": "unpinned (Slang "
+    out["config"] = {"workload": "C3-train + radiance term: %dk surfels x %d samples, env %dx%d" % (
+        P_SURFELS // 1000, NS, int(env.shape[-3]), int(env.shape[-2])), "parity": "unpinned (Slang "
                      "kernels cannot run here; numpy restatement oracle/radiance_oracle.py)"}
     return out
 
@@ -1102,6 +1107,8 @@ def measure_reference_cuda(steps: int, warmup: int) -> dict:
            "oracle/_ref/libsvgss_ref.so) + the torch restatement of the reference's shading graph (oracle/shading_oracle.py; "
            "the reference Python cannot travel to the GPU box) on the same B200, same inputs as the headline"}
     del t, geo, r
+    from svgir_b200 import shading as _shading
+    _shading.clear_env_tap_cache()   # its entries pin the model's direction buffers
     gc.collect()
     torch.cuda.empty_cache()
     return out

@@ -141,6 +141,11 @@ def _cached_taps(dirs: Optional[torch.Tensor], env_h: int, env_w: int, transform
     return taps
 
 
+def clear_env_tap_cache():
+    """Drops the cached taps (each entry keeps its directions tensor and a same-sized tap buffer alive)."""
+    _TAP_CACHE.clear()
+
+
 def refresh_env_taps(dirs: torch.Tensor, env_h: int, env_w: int, transform: Optional[torch.Tensor] = None):
     """Recomputes the cached taps of `dirs` in place if `dirs` (or the transform) was modified since; returns them."""
     return _cached_taps(dirs, env_h, env_w, transform)
