@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- torch-CPU restatement of the reference's densification bookkeeping
 (/root/reference/scene/gaussian_model.py): add_densification_stats :1270-1276, densify_and_clone :1188-1222,
 densify_and_split :1136-1186, prune_points / _prune_optimizer :1019-1057, cat_tensors_to_optimizer /
-densification_postfix :1059-1134, densify_and_prune :1224-1250. The reference's GaussianModel cannot be imported here
-(plyfile, simple_knn, slangtorch, hard-coded device="cuda"), so this oracle is NOT pinned by reference outputs --
-parity for SURVEY row 8(f)-3's densification half is "unpinned" (DESIGN.md); every function cites the lines it follows.
+densification_postfix :1059-1134, densify_and_prune :1224-1250. PINNED: tests/golden/ref_model.npz holds the inputs and
+outputs (all 13 parameter groups, both Adam moments, the statistics) of the reference's own densify_and_prune run on CPU
+with its device="cuda" factories redirected and its torch.normal draws recorded (tests/golden/make_golden_model.py);
+tests/test_model_golden_cpu.py requires this restatement to reproduce them bit for bit.
 The Adam half needs no restatement: the reference's optimiser IS torch.optim.Adam (:769), which the tests run directly.
 torch.normal(mean=0, std=stds) is taken as stds * z with caller-supplied z ~ N(0,1). Only tests/ may import this."""
 import torch

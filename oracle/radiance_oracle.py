@@ -12,6 +12,10 @@ loss, which csrc/radiance.cu implements:
     shading_brdf_simple              /root/reference/pbgi/bvhworkers/pbr.slang:283-330
     DirectLightMap.direct_light      /root/reference/scene/direct_light_map.py:70-83
 
+PARITY: the host-visible half of get_radiance_loss -- select_samples, direct_light * areas, the transposed normal layout,
+the target gather / nan_to_num / L1 -- IS pinned: tests/golden/ref_model.npz (case C) was produced by the reference's own
+get_radiance_loss with only its Slang call replaced by a recorder (tests/golden/make_golden_model.py;
+tests/test_model_golden_cpu.py). The Slang kernels themselves (closest hit, radiance cache, render_irradiance_sample) are
 PARITY UNPINNED: the reference runs these kernels through slangtorch (a third-party Slang JIT that is neither in
 /root/reference nor in this image), and it ships no test, fixture or golden vector for them, so this restatement could
 not be checked against the reference's own output. Where the reference's kernels are racy or depend on the LBVH

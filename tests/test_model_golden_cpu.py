@@ -1,0 +1,104 @@
+"""tests/golden/ref_model.npz -- produced by the reference's OWN GaussianModel code run on CPU
+(tests/golden/make_golden_model.py) -- pins:
+  A  oracle/optim_oracle.densify_and_prune (the checker of the densification kernels) to densify_and_prune + the Adam
+     state surgery of scene/gaussian_model.py:1020-1250;
+  B  svgir_b200.optim.NAN_FIX to replace_nangrad_to_zero (:775-800);
+  C  the host-visible half of get_radiance_loss (:544-575): sample selection, envmap = direct_light(dirs) * areas, the
+     transposed normal layout, target gather / nan_to_num / L1 -- oracle/radiance_oracle.py -- and the getters'
+     activations in svgir_b200.io.surfel_model_tensors (:270-351);
+  D  the chunking of update_radiace (:487-497) that RadianceCache.update reproduces, and its random-offset sampling."""
+import math
+import os
+
+import numpy as np
+import torch
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model.npz"))
+GROUPS = ("xyz", "normal", "rotation", "scaling", "opacity", "f_dc", "f_rest", "base_color", "roughness", "incidents_dc",
+          "incidents_rest", "visibility_dc", "visibility_rest")
+
+
+def test_densify_oracle_equals_reference_densify_and_prune():
+    from oracle import optim_oracle as oo
+    t = {k: torch.from_numpy(G["A_in_" + k]) for k in GROUPS}
+    mom = {k: (torch.from_numpy(G["A_in_exp_avg_" + k]), torch.from_numpy(G["A_in_exp_avg_sq_" + k])) for k in GROUPS}
+    stats = {k: torch.from_numpy(G["A_in_" + k]).clone() for k in ("xyz_gradient_accum", "denom", "normal_gradient_accum", "weights_accum")}
+    max_grad, min_opacity, extent, max_screen, max_grad_normal, percent_dense, wthr = G["A_cfg"].tolist()
+    t2, mom2, st2 = oo.densify_and_prune(t, mom, stats, max_grad, min_opacity, extent, max_screen, max_grad_normal,
+                                         percent_dense, wthr, torch.from_numpy(G["A_z"]))
+    P2 = G["A_out_xyz"].shape[0]
+    assert P2 != t["xyz"].shape[0] and G["A_z"].shape[0] > 0, "the golden case must clone, split and prune"
+    for k in GROUPS:
+        assert tuple(t2[k].shape) == G["A_out_" + k].shape, k
+        np.testing.assert_array_equal(t2[k].numpy(), G["A_out_" + k], err_msg=k)      # same torch ops on CPU: bit-equal
+        np.testing.assert_array_equal(mom2[k][0].numpy(), G["A_out_exp_avg_" + k], err_msg=k)
+        np.testing.assert_array_equal(mom2[k][1].numpy(), G["A_out_exp_avg_sq_" + k], err_msg=k)
+    for k in ("xyz_gradient_accum", "denom", "normal_gradient_accum", "weights_accum"):
+        np.testing.assert_array_equal(st2[k].numpy(), G["A_out_" + k], err_msg=k)
+    assert not G["A_out_max_radii2D"].any() and G["A_out_max_radii2D"].shape == (P2,)
+
+
+def test_nan_fix_table_equals_reference_replace_nangrad_to_zero():
+    from svgir_b200.optim import NAN_FIX
+    for k in GROUPS:
+        gin, gout = G["B_in_" + k], G["B_out_" + k]
+        nan = np.isnan(gin)
+        assert nan.any(), k
+        np.testing.assert_array_equal(gout[~nan], gin[~nan])
+        if k in NAN_FIX:
+            assert (gout[nan] == np.float32(NAN_FIX[k])).all(), k
+        else:
+            assert np.isnan(gout[nan]).all(), k                   # groups the reference does not patch
+
+
+def test_radiance_loss_host_side_equals_reference():
+    from oracle import radiance_oracle as ro
+    from svgir_b200 import io
+    N, S = G["C_in_visibility"].shape[:2]
+    raw = {"xyz": torch.from_numpy(G["C_in_xyz"]), "rotation": torch.from_numpy(G["C_in_rotation"]),
+           "normal": torch.from_numpy(G["C_in_normal"]), "base_color": torch.from_numpy(G["C_in_base_color"]),
+           "roughness": torch.from_numpy(G["C_in_roughness"]), "opacity": torch.zeros(N, 1), "scaling": torch.zeros(N, 3),
+           "shs_dc": torch.zeros(N, 1, 3), "shs_rest": torch.zeros(N, 15, 3)}
+    act = io.surfel_model_tensors(raw, base_color_scale=torch.ones(3))
+    np.testing.assert_allclose(act["geo_normal"].numpy(), G["C_out_geo_normal"], atol=1e-6)
+    np.testing.assert_allclose(act["shading_normal"].numpy(), G["C_out_shading_normal"], atol=1e-6)
+    np.testing.assert_allclose(act["base_color"].numpy(), G["C_out_albedo"], atol=1e-7)
+    np.testing.assert_allclose(act["roughness"].numpy(), G["C_out_roughness"], atol=1e-7)
+    assert (G["C_out_metallic"] == np.float32(0.02)).all()                                     # get_metallic (:350-351)
+    # the kernel's normal argument: get_shading_normal.transpose(1, 2).reshape(N, -1) = element 4*c + v
+    n12 = act["shading_normal"].transpose(1, 2).reshape(N, -1).numpy()
+    np.testing.assert_allclose(n12, G["C_out_normal"], atol=1e-6)
+    # selection
+    sel, score = ro.select_samples(G["C_in_xyz"], G["C_in_campos"], G["C_out_geo_normal"], G["C_in_incident_dirs"],
+                                   G["C_in_visibility"][..., 0])
+    ref_sel = G["C_out_max_idx"][:, 0]
+    differs = np.nonzero(sel != ref_sel)[0]
+    for n in differs:     # a different pick is acceptable only between scores that tie to the last bit
+        assert abs(score[n, sel[n]] - score[n, ref_sel[n]]) <= 1e-6 * max(1.0, abs(score[n, sel[n]])), n
+    assert len(differs) <= 1
+    assert (ref_sel[:8] == 0).all() and (sel[:8] == 0).all()        # fully visible surfels: every score is +-0 -> first index
+    # envmap = direct_light(dirs) * areas, direct_light = 2 * grid_sample(softplus(env))
+    env_act = np.log1p(np.exp(G["C_in_env_param"][0].astype(np.float64)))
+    envmap = ro.direct_light(env_act, G["C_in_incident_dirs"], 2.0) * G["C_in_incident_areas"].astype(np.float64)
+    np.testing.assert_allclose(envmap, G["C_out_envmap"], rtol=2e-5, atol=2e-6)
+    # target gather, nan_to_num, L1
+    tgt = np.nan_to_num(G["C_in_radiances"].astype(np.float64)[np.arange(N), ref_sel] * float(G["C_in_ratio"]), nan=0.0)
+    loss = np.abs(G["C_in_fake_irradiance"].astype(np.float64) - tgt).mean()
+    assert abs(loss - float(G["C_out_loss"])) < 1e-6
+    assert np.isnan(G["C_in_radiances"][3]).any()                   # the case exercises nan_to_num
+
+
+def test_update_radiace_chunking_and_sampling():
+    from oracle import render_equation_sh_oracle as RO
+    for tag in ("a", "b", "c"):
+        P, S = G["D_%s_PS" % tag].tolist()
+        chunk = P // ((S - 1) // 24 + 1)                              # RadianceCache.update
+        mine = [min(chunk, P - o) for o in range(0, P, chunk)]
+        assert mine == G["D_%s_chunks" % tag].tolist(), tag
+    # the directions of a chunk: fibonacci_sphere_sampling(geo_normal, S, random_rotate=True) with torch.rand(chunk, 1)
+    q = torch.from_numpy(G["D_c_rotation"])
+    q = torch.nn.functional.normalize(q, dim=-1)
+    r, x, y, z = q.unbind(1)
+    gn = torch.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], 1)
+    d, _ = RO.fibonacci_sphere_sampling(gn, 24, rand_u=torch.from_numpy(G["D_c_rand"]))
+    assert np.abs(d.numpy() - G["D_c_dirs"]).max() <= 2e-6

@@ -125,3 +125,42 @@ def test_densification_stats_kernel():
         OO.add_densification_stats(ref, vg, radii > 0, w)
     for k in ref:
         torch.testing.assert_close(getattr(st, k).cpu(), ref[k], rtol=1e-6, atol=1e-9)
+
+
+def test_densify_and_prune_matches_reference_golden():
+    """The kernels on the inputs of tests/golden/ref_model.npz (case A) against what the reference's own
+    densify_and_prune + optimiser surgery produced for them on CPU (tests/golden/make_golden_model.py)."""
+    import os
+    import numpy as np
+    from svgir_b200 import optim
+    dev = torch.device("cuda:0")
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model.npz"))
+    groups = ("xyz", "normal", "rotation", "scaling", "opacity", "f_dc", "f_rest", "base_color", "roughness", "incidents_dc",
+              "incidents_rest", "visibility_dc", "visibility_rest")
+    t = {k: torch.from_numpy(G["A_in_" + k]) for k in groups}
+    stats = {k: torch.from_numpy(G["A_in_" + k]) for k in ("xyz_gradient_accum", "denom", "normal_gradient_accum", "weights_accum")}
+    max_grad, min_opacity, extent, max_screen, max_grad_normal, percent_dense, wthr = G["A_cfg"].tolist()
+    args = dict(max_grad=max_grad, min_opacity=min_opacity, extent=extent, max_screen_size=max_screen, max_grad_normal=max_grad_normal,
+                percent_dense=percent_dense, weights_threshold=wthr)
+    z = torch.from_numpy(G["A_z"])
+    n_split = z.shape[0] // 2
+    P = t["xyz"].shape[0]
+    tc = {k: v.to(dev).contiguous() for k, v in t.items()}
+    opt = optim.FusedAdam([{"params": [tc[k].requires_grad_(True)], "lr": 1e-3, "name": k} for k in tc])
+    for k in tc:
+        opt.state[k] = {"exp_avg": torch.from_numpy(G["A_in_exp_avg_" + k]).to(dev), "exp_avg_sq": torch.from_numpy(G["A_in_exp_avg_sq_" + k]).to(dev)}
+    st = optim.DensificationState(P, dev)
+    st.weights_accum.copy_(stats["weights_accum"]); st.xyz_gradient_accum.copy_(stats["xyz_gradient_accum"])
+    st.denom.copy_(stats["denom"]); st.max_radii2D.copy_(torch.from_numpy(G["A_in_max_radii2D"]))
+    out, new_stats, info = optim.densify_and_prune(tc, st, optimizer=opt, normal_samples=_z_for_kernel(t, stats, args, z, n_split), **args)
+    assert info["n_after"] == G["A_out_xyz"].shape[0] and info["cloned"] > 0 and info["split"] > 0
+    for k in groups:
+        a, b = out[k].detach().cpu().numpy(), G["A_out_" + k]
+        if k in ("xyz", "scaling"):
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6, err_msg=k)      # exp / log / the rotation in fp32 on the device
+        else:
+            np.testing.assert_array_equal(a, b, err_msg=k)
+        np.testing.assert_array_equal(opt.state[k]["exp_avg"].cpu().numpy(), G["A_out_exp_avg_" + k], err_msg=k)
+        np.testing.assert_array_equal(opt.state[k]["exp_avg_sq"].cpu().numpy(), G["A_out_exp_avg_sq_" + k], err_msg=k)
+    for k in ("weights_accum", "xyz_gradient_accum", "denom"):
+        np.testing.assert_array_equal(getattr(new_stats, k).cpu().numpy(), G["A_out_" + k])
