@@ -150,7 +150,10 @@ class FusedAdam:
         """Shaped like torch.optim.Adam.state_dict() (what capture() stores as opt_dict, gaussian_model.py:195-232)."""
         return {"state": {i: {"step": torch.tensor(float(self.step_count)), "exp_avg": self.state[g["name"]]["exp_avg"],
                               "exp_avg_sq": self.state[g["name"]]["exp_avg_sq"]} for i, g in enumerate(self.param_groups)},
-                "param_groups": [{"name": g["name"], "lr": g["lr"], "betas": self.betas, "eps": self.eps, "params": [i]}
+                # every key torch.optim.Adam's step reads from a group (a loaded group replaces the live one wholesale)
+                "param_groups": [{"name": g["name"], "lr": g["lr"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
+                                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                                  "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": [i]}
                                  for i, g in enumerate(self.param_groups)]}
 
     def load_state_dict(self, sd: dict):

@@ -8,7 +8,15 @@
      replaced by a recorder that returns a seeded tensor, so max_idx, the envmap = direct_light(dirs) * areas, the
      transposed normal layout, the gathered target and the L1 value are the reference's own;
   D  the chunking of update_radiace (:487-497): chunk boundaries and the per-chunk torch.rand draws of
-     sample_incident_rays (its tracer calls are replaced by recorders).
+     sample_incident_rays (its tracer calls are replaced by recorders);
+  E  checkpoints: ref_checkpoint.pth = torch.save((capture(), iteration)) of a reference model with a live optimiser
+     (:195-225), and the reverse direction checked HERE: a checkpoint written by svgir_b200.io.save_checkpoint with a
+     FusedAdam.state_dict() is restored by the reference's restore() (:227-268), tensors and Adam state equal, and the
+     restored optimiser steps;
+  F  PLY: the structured array the reference's save_ply builds (:855-881) for a stage-1 model, recorded at the
+     PlyElement.describe call; the reference's load_ply (:891-1003) reading files written by svgir_b200.io.save_ply
+     (served through svgir_b200.io.read_ply_vertices, `plyfile` being absent) reproduces the model, and its PBR branch
+     equals io.load_ply(reference_roughness_quirk=True); the reference's own writer raises for a PBR model.
 
 Run in the build container only:   python tests/golden/make_golden_model.py
 
@@ -236,6 +244,144 @@ def main():
             torch.manual_seed(77)
             out["D_c_rand"] = np.concatenate([torch.rand(c[0], 1).numpy() for c in calls], 0)
         print("D[%s]: chunks %s" % (tag, [c[0] for c in calls]))
+
+    # ---- E: checkpoint interchange ------------------------------------------------------------------------------------
+    # E1: a checkpoint written by the reference (train.py: torch.save((gaussians.capture(), iteration), path))
+    m5, g5 = make_model(gm, 20, 15)
+    m5.training_setup(Opt())
+    for k, p in group_params(m5).items():
+        p.grad = 0.1 * torch.randn(p.shape, generator=g5)
+    m5.optimizer.step()
+    m5._radiances = torch.rand(20, 8, 3, generator=g5)
+    m5.max_radii2D = torch.rand(20, generator=g5)
+    m5.weights_accum = torch.rand(20, 1, generator=g5)
+    torch.save((m5.capture(), 4321), os.path.join(HERE, "ref_checkpoint.pth"))
+    for k in GROUPS:
+        out["E_" + k] = getattr(m5, ATTR[k]).detach().numpy().copy()
+        out["E_exp_avg_" + k] = m5.optimizer.state[group_params(m5)[k]]["exp_avg"].numpy().copy()
+    out["E_radiances"] = m5._radiances.numpy().copy()
+    out["E_max_radii2D"] = m5.max_radii2D.numpy().copy()
+    out["E_weights_accum"] = m5.weights_accum.numpy().copy()
+    # E2: a checkpoint written by THIS repo (svgir_b200.io.save_checkpoint + FusedAdam.state_dict) restored by the reference
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "svg-ir_b200"))
+    from svgir_b200 import io as sio, optim as sopt
+    import tempfile
+    names = {"xyz": "xyz", "normal": "normal", "f_dc": "shs_dc", "f_rest": "shs_rest", "scaling": "scaling", "rotation": "rotation",
+             "opacity": "opacity", "base_color": "base_color", "roughness": "roughness", "incidents_dc": "incidents_dc",
+             "incidents_rest": "incidents_rest", "visibility_dc": "visibility_dc", "visibility_rest": "visibility_rest"}
+    g6 = torch.Generator().manual_seed(16)
+    mine = {names[k]: torch.randn(tuple(getattr(m5, ATTR[k]).shape), generator=g6) for k in GROUPS}
+    order = [grp["name"] for grp in m5.optimizer.param_groups]
+    fa = sopt.FusedAdam.__new__(sopt.FusedAdam)     # its constructor insists on CUDA tensors; only state_dict() is needed here
+    fa.param_groups = [{"name": k, "params": [mine[names[k]]], "lr": 1e-3 * (i + 1)} for i, k in enumerate(order)]
+    fa.betas, fa.eps, fa.state = (0.9, 0.999), 1e-15, {}
+    for k in order:
+        fa.state[k] = {"exp_avg": torch.randn(mine[names[k]].shape, generator=g6), "exp_avg_sq": torch.rand(mine[names[k]].shape, generator=g6)}
+    fa.step_count = 17
+    model = dict(mine, active_sh_degree=3, max_radii2D=torch.rand(20, generator=g6), weights_accum=torch.rand(20, 1, generator=g6),
+                 xyz_gradient_accum=torch.rand(20, 1, generator=g6), normal_gradient_accum=torch.zeros(20, 1),
+                 denom=torch.ones(20, 1), opt_dict=fa.state_dict(), spatial_lr_scale=2.5,
+                 radiances=torch.rand(20, 8, 3, generator=g6), radiance_ratio=torch.tensor(0.9))
+    with tempfile.TemporaryDirectory() as td:
+        sio.save_checkpoint(os.path.join(td, "chkpnt.pth"), model, 99)
+        model_args, it = torch.load(os.path.join(td, "chkpnt.pth"), weights_only=False)
+    m6 = gm.GaussianModel(3, render_type="render_relight")
+    m6.restore(model_args, Opt(), is_training=True, restore_optimizer=True)
+    ok = it == 99 and m6.spatial_lr_scale == 2.5
+    for k in GROUPS:
+        ok = ok and torch.equal(getattr(m6, ATTR[k]).detach(), mine[names[k]])
+        stt = m6.optimizer.state[group_params(m6)[k]]
+        ok = ok and torch.equal(stt["exp_avg"], fa.state[k]["exp_avg"]) and torch.equal(stt["exp_avg_sq"], fa.state[k]["exp_avg_sq"])
+        ok = ok and float(stt["step"]) == 17.0
+    ok = ok and torch.equal(m6._radiances, model["radiances"]) and torch.equal(m6.weights_accum, model["weights_accum"])
+    for k, p in group_params(m6).items():          # the restored optimiser must be able to step
+        p.grad = torch.zeros_like(p)
+    m6.optimizer.step()
+    assert ok, "the reference could not restore a checkpoint written by svgir_b200.io"
+    out["E_reference_restored_our_checkpoint"] = np.int64(1)
+    print("E: reference checkpoint written; the reference restored ours and stepped its optimiser")
+
+    # ---- F: PLY ---------------------------------------------------------------------------------------------------------
+    # `plyfile` is absent; what the reference hands to it (PlyElement.describe) and asks from it (PlyData.read) is the
+    # whole interface, so the stand-ins below RECORD the structured array of save_ply and SERVE a file through this
+    # repo's own reader to load_ply.
+    rec_ply = {}
+
+    class PlyElement:
+        @staticmethod
+        def describe(arr, name):
+            rec_ply["names"], rec_ply["data"], rec_ply["element"] = list(arr.dtype.names), np.array(arr.tolist(), np.float32), name
+            return (arr, name)
+
+    class PlyData:
+        def __init__(self, els=None):
+            self.els = els
+
+        def write(self, path):
+            rec_ply["written"] = path
+
+        @staticmethod
+        def read(path):
+            v = sio.read_ply_vertices(path)
+
+            class El:
+                properties = [types.SimpleNamespace(name=n) for n in v]
+
+                def __getitem__(self, k):
+                    return v[k]
+            return types.SimpleNamespace(elements=[El()])
+    gm.PlyElement, gm.PlyData = PlyElement, PlyData
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        # F1: stage-1 model (no PBR attributes): the reference's writer, recorded
+        m7 = gm.GaussianModel(3, render_type="render")
+        g7 = torch.Generator().manual_seed(17)
+        Pn = 12
+        for k, sh in {"xyz": (Pn, 3), "normal": (Pn, 12), "rotation": (Pn, 4), "scaling": (Pn, 3), "opacity": (Pn, 1),
+                      "f_dc": (Pn, 1, 3), "f_rest": (Pn, 15, 3)}.items():
+            setattr(m7, ATTR[k], torch.nn.Parameter(torch.randn(*sh, generator=g7)))
+        m7.save_ply(os.path.join(td, "ref", "point_cloud.ply"))
+        out["F1_names"] = np.array(rec_ply["names"])
+        out["F1_data"] = rec_ply["data"]
+        for k in ("xyz", "rotation", "scaling", "opacity", "f_dc", "f_rest"):
+            out["F1_in_" + k] = getattr(m7, ATTR[k]).detach().numpy().copy()
+        out["F1_geo_normal"] = m7.get_geo_normal.detach().numpy().copy()
+        # F2: the same model written by THIS repo's writer and read back by the reference's load_ply
+        ours = {"xyz": m7._xyz, "shs_dc": m7._shs_dc, "shs_rest": m7._shs_rest, "opacity": m7._opacity, "scaling": m7._scaling,
+                "rotation": m7._rotation}
+        sio.save_ply(os.path.join(td, "ours.ply"), ours, geo_normal=m7.get_geo_normal)
+        m8 = gm.GaussianModel(3, render_type="render")
+        m8.load_ply(os.path.join(td, "ours.ply"))
+        ok = all(torch.equal(getattr(m8, ATTR[k]).detach(), getattr(m7, ATTR[k]).detach()) for k in
+                 ("xyz", "rotation", "scaling", "opacity", "f_dc", "f_rest"))
+        ok = ok and torch.equal(m8._normal.detach(), m7.get_geo_normal.detach().repeat(1, 4))
+        assert ok, "the reference's load_ply did not reproduce the model from a file written by svgir_b200.io.save_ply"
+        out["F2_reference_loaded_our_ply"] = np.int64(1)
+        # F3: with PBR attributes the reference's writer names 12 roughness columns and supplies 4
+        m9, _ = make_model(gm, Pn, 18)
+        try:
+            m9.save_ply(os.path.join(td, "ref_pbr", "point_cloud.ply"))
+            out["F3_reference_pbr_save_raises"] = np.int64(0)
+        except ValueError as e:
+            out["F3_reference_pbr_save_raises"] = np.int64(1)
+            print("F3: reference save_ply with PBR attributes raises: %s" % str(e)[:90])
+        # F4: a PBR file written by this repo, read by the reference's load_ply: roughness comes back as the normal_* block
+        pbr = {"xyz": m9._xyz, "shs_dc": m9._shs_dc, "shs_rest": m9._shs_rest, "opacity": m9._opacity, "scaling": m9._scaling,
+               "rotation": m9._rotation, "base_color": m9._base_color, "normal": m9._normal, "roughness": m9._roughness,
+               "incidents_dc": m9._incidents_dc, "incidents_rest": torch.randn(Pn, 15, 3), "visibility_dc": m9._visibility_dc,
+               "visibility_rest": torch.randn(Pn, 15, 1)}
+        sio.save_ply(os.path.join(td, "ours_pbr.ply"), pbr, geo_normal=m9.get_geo_normal)
+        m10 = gm.GaussianModel(3, render_type="render_relight")
+        m10.load_ply(os.path.join(td, "ours_pbr.ply"))
+        mine = sio.load_ply(os.path.join(td, "ours_pbr.ply"), use_pbr=True, reference_roughness_quirk=True)
+        names2 = {"xyz": "xyz", "rotation": "rotation", "scaling": "scaling", "opacity": "opacity", "f_dc": "shs_dc", "f_rest": "shs_rest",
+                  "base_color": "base_color", "roughness": "roughness", "incidents_dc": "incidents_dc",
+                  "incidents_rest": "incidents_rest", "visibility_dc": "visibility_dc", "visibility_rest": "visibility_rest"}
+        ok = all(torch.equal(getattr(m10, ATTR[k]).detach(), mine[v]) for k, v in names2.items())
+        assert ok, "io.load_ply(reference_roughness_quirk=True) differs from the reference's load_ply"
+        assert torch.equal(m10._roughness.detach(), m9._normal.detach())        # the quirk itself
+        out["F4_reference_pbr_load_equals_ours_with_quirk"] = np.int64(1)
+    print("F: PLY names/data recorded (%d properties); reference loaded our files" % len(rec_ply["names"]))
 
     np.savez_compressed(os.path.join(HERE, "ref_model.npz"), **out)
     print("wrote ref_model.npz: %d arrays, %.1f KB" % (len(out), os.path.getsize(os.path.join(HERE, "ref_model.npz")) / 1e3))
