@@ -143,7 +143,7 @@ def main():
     m.max_radii2D = 40 * torch.rand(P, generator=g)
     for k in ("xyz_gradient_accum", "denom", "normal_gradient_accum", "weights_accum", "max_radii2D"):
         out["A_in_" + k] = getattr(m, k).numpy().copy()
-    cfg = dict(max_grad=0.0002, min_opacity=0.05, extent=5.0, max_screen_size=20, max_grad_normal=0.1)
+    cfg = dict(max_grad=0.0002, min_opacity=0.05, extent=25.0, max_screen_size=20, max_grad_normal=0.1)   # 0.001 * extent straddles the scales
     zs = []
     orig_normal = torch.normal
 
