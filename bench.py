@@ -484,10 +484,11 @@ def measure_train(args, ctx: Ctx, clocks: ClockSampler) -> dict:
     }
     kt = {k: (v[0] / max(v[1], 1)) for k, v in ktimes.items()}  # avg ms per launch
     dom = max(("composite_bwd", "composite_fwd", "shade_fwd", "shade_bwd"), key=lambda k: kt[k])
-    traffic = None
+    traffic, limiter = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        traffic, limiter = tj.get(dom), tj.get(dom + "_limiter")
     except Exception:
         pass
     achieved = alg[dom] / (kt[dom] * 1e-3) / 1e9 if kt[dom] > 0 else 0.0
@@ -530,7 +531,10 @@ def measure_train(args, ctx: Ctx, clocks: ClockSampler) -> dict:
              "one NCCL all-reduce after the step"), "note": reduce_note}, **(ar_check or {})),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
                      "peak_source": pk_src, "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4),
-                     "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4)},
+                     "traffic": traffic, "algorithmic_bytes": int(alg[dom]), "avg_ms": round(kt[dom], 4),
+                     # the compositors are not HBM-bound: what the committed ncu capture of this
+                     # kernel shows as its limiter (profiles/ncu_traffic.json <- profiles/r02/g9_ncu_step_full.txt)
+                     "limiter": limiter},
         "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
         # the same per-launch event times grouped by stage: svgss rasteriser forward+backward alone (BASELINE.json
         # configs[1]'s shape), the render_equation shading, the resolve+loss tail

@@ -72,6 +72,21 @@ def main():
         for key, short in SHORT.items():
             if key in name:
                 traffic[short] = int(rd + wr)
+                # what actually limits the kernel (bench.py copies this into roofline.limiter)
+                lim = {}
+                for k, m in (("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                             ("fma_pipe_pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                             ("lsu_pipe_pct", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                             ("shared_mem_pipe_pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                             ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                             ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                             ("registers_per_thread", "launch__registers_per_thread")):
+                    if m in hdr:
+                        try:
+                            lim[k] = round(float(r[hdr.index(m)].replace(",", "")), 1)
+                        except ValueError:
+                            pass
+                traffic[short + "_limiter"] = lim
     open(out, "w").write("\n".join(lines) + "\n")
     if traffic_path:
         try:
