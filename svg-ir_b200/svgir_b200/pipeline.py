@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from . import losses, raster, shading
+from . import _lib, losses, raster, shading
 from ._lib import launch_count
 
 _CONFIG_CACHE: dict = {}
@@ -140,19 +140,22 @@ def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: 
         projmatrix=cam.full_proj_transform, patch_bbox=cam.patch_bbox, prcppoint=cam.prcppoint,
         sh_degree=pc.active_sh_degree, campos=cam.camera_center, prefiltered=False, debug=debug,
         config=_config_tensor(pc.config, means3D.device))
-    work = None
+    work, binning_beside = None, False
     if not shade_culled:
         prestate, work = preprocess_geometry(raster_settings, means3D, pc.opacity, pc.scaling, pc.rotation, None,
                                              pc.shs, None)
         raster_settings = raster_settings._replace(prestate=prestate)
-        if OVERLAP_BINNING:
-            raster.start_binning(prestate)   # tile binning on a side stream, under the shading (no-op without a capacity hint)
+        binning_beside = OVERLAP_BINNING and raster.start_binning(prestate)   # side stream, under the shading (no-op
+        #                                                                        without a capacity hint)
     rasterizer = GaussianRasterizer(raster_settings=raster_settings)
 
     # shading + the features / vfeatures packing of svgss.py:116-166 in one fused kernel. FUSED_VIEWDIRS: the view
     # direction F.normalize(camera_center - means3D) of svgss.py:95 is evaluated inside the kernel (and its gradient
     # returned for means3D) instead of by torch ops around it -- the same code path fused_step.FusedTrainStep uses,
     # so both give bit-identical images; False = torch normalise, then the kernel (the reference's op order)
+    reserve = BINNING_RESERVE_SMS if (work is not None and binning_beside) else 0
+    if reserve:   # the shading grid is persistent: leave a few SMs to the binning kernels running beside it
+        _lib.lib().svgir_shade_reserve_sms(int(reserve))
     if FUSED_VIEWDIRS:
         features, vfeatures = shading.shade_and_pack(
             pc.base_color, pc.roughness, pc.shading_normal, None, pc.radiance, env_light, pc.visibility,
@@ -165,6 +168,8 @@ def _shade_and_rasterize(cam: ViewCamera, pc: SurfelModel, env_light, bg_color: 
             pc.incident_dirs, pc.incident_areas, cam.world_view_transform[:3, :3], is_training=is_training, debug=debug,
             work=work)
 
+    if reserve:
+        _lib.lib().svgir_shade_reserve_sms(0)
     raw = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=pc.shs, colors_precomp=None, opacities=pc.opacity,
         scales=pc.scaling, rotations=pc.rotation, cov3D_precomp=None, features=features, vfeatures=vfeatures)
@@ -325,6 +330,10 @@ def reduce_segments(pc: SurfelModel) -> list:
 # (the autograd mirror of the reference's control flow) is what gets captured.
 FUSED_STEP = True
 OVERLAP_BINNING = True    # render_view / training_step: bin on a side stream while the shading kernel runs
+# SMs left out of the (persistent) shading grid for the binning kernels beside it. In the relight frame the shading kernel
+# is 8x longer than the binning, so every reserved SM costs more than it gives (0 / 4 / 8 / 16 SMs: 1.410 / 1.417 / 1.443 /
+# 1.492 ms per frame); the training step, where binning is the longer chain, reserves 20 (fused_step.FWD_RESERVE_SMS).
+BINNING_RESERVE_SMS = 0
 
 
 class BinOverflow(RuntimeError):
