@@ -194,3 +194,44 @@ def test_loss_and_gradients(ref_grid):
         assert scale > 0, name
         assert err < 2e-4 * scale, (name, err, scale)
     assert not bool(rough.grad[:, 1:].any())                              # only column 0 is read (:1277)
+
+
+def test_update_samples_match_the_reference_update_radiace():
+    """The incident directions RadianceCache.update hands to the tracer, against what the reference's own update_radiace
+    (run on CPU, tests/golden/make_golden_model.py case D) handed to ITS tracer for the same rotations and the same
+    per-surfel random offsets (the offsets come from torch.rand on the model's device, so they are passed in here)."""
+    import os
+    from svgir_b200 import sampling
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model.npz"))
+    dev = torch.device("cuda:0")
+    q = torch.nn.functional.normalize(torch.from_numpy(G["D_c_rotation"]), dim=-1).to(dev)
+    r, x, y, z = q.unbind(1)
+    gn = torch.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], 1).contiguous()   # get_geo_normal
+    dirs, areas = sampling.fibonacci_sphere_sampling(gn, 24, random_rotate=True, rand_u=torch.from_numpy(G["D_c_rand"]).to(dev))
+    assert np.abs(dirs.cpu().numpy() - G["D_c_dirs"]).max() <= 3e-6          # fp32 sin / cos on the device
+    assert bool((areas == 2 * math.pi).all()) or float((areas - 2 * math.pi).abs().max()) < 1e-6
+
+
+def test_selection_and_target_match_the_reference_get_radiance_loss():
+    """The selection kernel and the target gather on the inputs of golden case C: max_idx as the reference's own
+    get_radiance_loss computed it (recorded at its render_irradiance_sample call), and -- with every cached hit set to
+    'none', so that the irradiance is 0 -- the loss mean|0 - nan_to_num(radiances[max_idx] * ratio)|."""
+    import os
+    from svgir_b200 import radiance
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model.npz"))
+    dev = torch.device("cuda:0")
+    t = lambda k: torch.from_numpy(G[k]).to(dev)
+    N, S = G["C_in_visibility"].shape[:2]
+    hit = torch.full((N, S, 1), -1, dtype=torch.int32, device=dev)
+    uv = torch.zeros(N, S, 2, device=dev)
+    loss, irr, sel = radiance.radiance_loss(
+        t("C_in_campos"), (t("C_in_env_param"), 0), t("C_in_xyz"), t("C_out_geo_normal"), t("C_in_incident_dirs"),
+        t("C_in_incident_areas"), t("C_in_visibility"), hit, uv, t("C_in_radiances"), torch.tensor(float(G["C_in_ratio"]), device=dev),
+        t("C_out_shading_normal"), t("C_out_albedo"), t("C_out_roughness"), return_aux=True)
+    ref_sel = G["C_out_max_idx"][:, 0]
+    got = sel.cpu().numpy()
+    assert (got != ref_sel).sum() <= 1          # only a last-bit tie between two scores may pick another sample
+    assert (got[:8] == 0).all()                 # fully visible surfels: every score is +-0 -> the first index
+    assert not bool(irr.any())
+    tgt = np.nan_to_num(G["C_in_radiances"].astype(np.float64)[np.arange(N), got] * float(G["C_in_ratio"]), nan=0.0)
+    assert abs(float(loss) - np.abs(tgt).mean()) < 1e-6
