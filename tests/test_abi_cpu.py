@@ -147,3 +147,27 @@ def test_unmodified_reference_wrapper_binds_to_our_C():
         for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             if k not in saved_utils:
                 del sys.modules[k]
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument validation of the round-2 entry points happens before anything touches the device: status
+    SVGIR_ERR_INVALID (-1) and a message in svgir_last_error(), as for the rasteriser (no compute call is made here)."""
+    import ctypes as C
+    from svgir_b200 import _lib, bvh, radiance, shading
+    L = _lib.lib()
+    radiance._L(); bvh._L(); shading._L()
+    msg = lambda: L.svgir_last_error().decode()
+    assert L.svgir_radiance_pack_surfels(5, None, None, 3, None, None, None, None, None, None) == -1 and "null" in msg()
+    tree = bvh.BvhStruct(0, 0, None, None, None, None, None, 0)
+    one = C.c_void_p(16)       # a non-null, aligned dummy: the tree check comes first
+    assert L.svgir_radiance_cache_build(C.byref(tree), 4, 8, 0, 0, one, one, one, one, one, one, one, one, None) == -1
+    assert "tree" in msg()
+    cfg = radiance.RadianceLossCfg(10, 0, 16, 32, 0, 0, 4, 0)          # S = 0
+    cin = radiance.RadianceLossIn()
+    assert L.svgir_radiance_loss_forward(C.byref(cfg), C.byref(cin), one, one, None, one, one, None) == -1 and "cfg" in msg()
+    cfg = radiance.RadianceLossCfg(10, 8, 16, 32, 0, 0, 4, 0)
+    assert L.svgir_radiance_loss_forward(C.byref(cfg), C.byref(cin), one, one, None, one, one, None) == -1 and "missing input" in msg()
+    assert L.svgir_env_taps(10, 0, 32, None, one, one, None) == -1 and "env_taps" in msg()
+    assert L.svgir_env_taps(10, 40000, 32, None, one, one, None) == -1          # the packed corner is 16 bits per axis
+    assert L.svgir_env_taps(0, 16, 32, None, None, None, None) == 0             # empty input: nothing to do
+    assert L.svgir_radiance_cache_build(C.byref(tree), 0, 8, 0, 0, None, None, None, None, None, None, None, None, None) == 0
